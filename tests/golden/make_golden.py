@@ -1,0 +1,145 @@
+#!/usr/bin/env python3
+"""Generate the golden parity fixtures in tests/golden/ by RUNNING THE REFERENCE ITSELF.
+
+Runs the unmodified reference binaries built by oracle/build_ref.py (oracle/_ref/<cfg>/athena) on the
+decks in tests/decks/ with small grids, and stores the t=0 and t=K restart dumps (FP64, active zones)
+plus the per-cycle `next dt` / radiation sub-cycle counts it printed.  Also stores function-level
+vectors from the reference's own lr_states()/fluxes() objects (oracle/_ref/<cfg>/libref_units.so).
+
+    python tests/golden/make_golden.py          # needs /root/reference (to build oracle/_ref) -- container only
+
+The committed .npz files are what the GPU box sees; nothing under /root/reference is read at test time.
+"""
+import ctypes as C
+import importlib.util
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from __graft_entry__ import load_package  # noqa: E402
+
+pkg = load_package()
+from athena_b200.restart import read_restart  # noqa: E402
+
+DECKS = os.path.join(ROOT, "tests", "decks")
+REFDIR = os.path.join(ROOT, "oracle", "_ref")
+
+# name -> (reference build, deck, overrides, [nlim...])
+CASES = {
+    "blast16": ("blast", "blast.athinput",
+                ["domain1/Nx1=16", "domain1/Nx2=16", "domain1/Nx3=16", "problem/radius=0.25"], [1, 6]),
+    "blastmix": ("blast", "blast.athinput",
+                 ["domain1/Nx1=20", "domain1/Nx2=12", "domain1/Nx3=16", "problem/radius=0.2",
+                  "domain1/x2min=-0.3", "domain1/x2max=0.3", "domain1/x3min=-0.4", "domain1/x3max=0.4",
+                  "domain1/bc_ix1=1", "domain1/bc_ox1=2", "domain1/bc_ix2=2", "domain1/bc_ox2=1",
+                  "domain1/bc_ix3=1", "domain1/bc_ox3=2"], [5]),
+    "ifront32": ("ifront", "ifront.athinput",
+                 ["domain1/Nx1=32", "domain1/Nx2=16", "domain1/Nx3=16"], [1, 4]),
+    "ioniz24": ("ioniz_sphere", "ioniz_sphere.athinput",
+                ["domain1/Nx1=24", "domain1/Nx2=24", "domain1/Nx3=24"], [1, 3]),
+}
+
+
+def run_reference(build, deck, overrides, nlim):
+    exe = os.path.join(REFDIR, build, "athena")
+    with tempfile.TemporaryDirectory() as tmp:
+        cmd = [exe, "-i", os.path.join(DECKS, deck), f"time/nlim={nlim}"] + overrides
+        r = subprocess.run(cmd, cwd=tmp, capture_output=True, text=True, check=True)
+        rst = sorted(f for f in os.listdir(tmp) if f.endswith(".rst"))
+        assert len(rst) == 2, rst
+        d0 = read_restart(os.path.join(tmp, rst[0]))
+        d1 = read_restart(os.path.join(tmp, rst[1]))
+    next_dt = [float(x) for x in re.findall(r"cycle=\d+ time=\S+ next dt=(\S+)", r.stdout)]
+    rad = [(int(a), int(b), int(c), float(d)) for a, b, c, d in re.findall(
+        r"Radiation done in (\d+) iterations: (\d+) thermal, (\d+) chemical; new dt = (\S+)", r.stderr)]
+    return d0, d1, next_dt, rad, cmd
+
+
+def pack(prefix, g, out):
+    for k, v in g.items():
+        out[f"{prefix}_{k}"] = v
+
+
+def make_runs():
+    for name, (build, deck, ov, nlims) in CASES.items():
+        for nlim in nlims:
+            d0, d1, next_dt, rad, cmd = run_reference(build, deck, ov, nlim)
+            out = {}
+            pack("U0", d0["grids"][0], out)
+            pack("U1", d1["grids"][0], out)
+            out["dt0"] = d0["dt"]; out["time0"] = d0["time"]
+            out["dt1"] = d1["dt"]; out["time1"] = d1["time"]; out["nstep1"] = d1["nstep"]
+            out["next_dt"] = np.array(next_dt)
+            out["rad"] = np.array(rad, dtype=np.float64).reshape(-1, 4)
+            out["deck"] = deck
+            out["overrides"] = np.array(ov)
+            out["build"] = build
+            path = os.path.join(HERE, f"{name}_k{nlim}.npz")
+            np.savez_compressed(path, **out)
+            print(path, os.path.getsize(path) // 1024, "KiB;", " ".join(cmd[3:]))
+
+
+def make_units(seed=20261018):
+    """Function-level vectors: reference lr_states()/fluxes()/Cons1D_to_Prim1D() on seeded random states."""
+    dp = C.POINTER(C.c_double)
+    P = lambda a: a.ctypes.data_as(dp)
+    for cfg, nscal in (("ifront", 1), ("blast", 0)):
+        ref = C.CDLL(os.path.join(REFDIR, cfg, "libref_units.so"))
+        ref.ref_set_gamma.argtypes = [C.c_double]
+        ref.ref_fluxes.argtypes = [dp, dp, dp, dp, C.c_double, dp]
+        ref.ref_prim_to_cons.argtypes = [dp, dp]
+        ref.ref_cons_to_prim.argtypes = [dp, dp]
+        ref.ref_cfast.argtypes = [dp]; ref.ref_cfast.restype = C.c_double
+        ref.ref_lr_states.argtypes = [dp, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, dp, dp]
+        gam = 5.0 / 3.0
+        ref.ref_set_gamma(gam)
+        rng = np.random.default_rng(seed + nscal)
+        nf = 4096
+        Wl = np.empty((nf, 6)); Wr = np.empty((nf, 6))
+        for W in (Wl, Wr):
+            W[:, 0] = rng.uniform(0.1, 2, nf); W[:, 1] = 2 * rng.normal(size=nf)
+            W[:, 2:4] = rng.normal(size=(nf, 2)); W[:, 4] = rng.uniform(0.01, 3, nf)
+            W[:, 5] = rng.uniform(0, 1, nf) if nscal else 0.0
+        Wr[::3, 0] *= 1e-3; Wr[::3, 4] *= 1e-4          # strong rarefactions: exercises the HLLE fallback
+        Wr[1::7, 1] += 6.0; Wl[1::7, 1] += 6.0          # supersonic: upwind shortcut
+        eta = np.where(np.arange(nf) % 2 == 0, rng.uniform(0, 2, nf), 0.0)
+        Ul = np.empty((nf, 6)); Ur = np.empty((nf, 6)); F = np.empty((nf, 6)); Wb = np.empty((nf, 6))
+        cf = np.empty(nf)
+        for t in range(nf):
+            ref.ref_prim_to_cons(P(Wl[t]), P(Ul[t])); ref.ref_prim_to_cons(P(Wr[t]), P(Ur[t]))
+            ref.ref_fluxes(P(Ul[t]), P(Ur[t]), P(Wl[t]), P(Wr[t]), eta[t], P(F[t]))
+            ref.ref_cons_to_prim(P(Ul[t]), P(Wb[t]))
+            cf[t] = ref.ref_cfast(P(Ul[t]))
+        npen, n = 64, 48
+        W = np.empty((npen, n, 6)); WL = np.zeros((npen, n, 6)); WR = np.zeros((npen, n, 6))
+        for t in range(npen):
+            w = W[t]
+            w[:, 0] = rng.uniform(0.1, 2, n); w[:, 1:4] = rng.normal(size=(n, 3)); w[:, 4] = rng.uniform(0.01, 3, n)
+            w[:, 5] = rng.uniform(0, 1, n) if nscal else 0.0
+            if t % 2:
+                w[:] = w[0] + np.cumsum(0.02 * w, axis=0)
+                w[:, 0] = np.abs(w[:, 0]) + 0.1; w[:, 4] = np.abs(w[:, 4]) + 0.01
+            ref.ref_lr_states(P(w), n, 0.01, 0.05, 3, n - 4, P(WL[t]), P(WR[t]))
+        path = os.path.join(HERE, f"units_nscal{nscal}.npz")
+        np.savez_compressed(path, gamma=gam, nscal=nscal, Wl=Wl, Wr=Wr, Ul=Ul, Ur=Ur, eta=eta, F=F, W_of_Ul=Wb, cfast_Ul=cf,
+                            pencil_W=W, pencil_Wl=WL, pencil_Wr=WR, pencil_dt=0.01, pencil_dx=0.05, pencil_il=3, pencil_iu=n - 4)
+        print(path, os.path.getsize(path) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    spec = importlib.util.spec_from_file_location("build_ref", os.path.join(ROOT, "oracle", "build_ref.py"))
+    br = importlib.util.module_from_spec(spec); spec.loader.exec_module(br)
+    if os.path.isdir(os.path.join(br.REF, "src")):
+        for c in ("ifront", "ioniz_sphere", "blast"):
+            br.build(c)
+        for c in ("ifront", "blast"):
+            br.build_units(c)
+    make_runs()
+    make_units()

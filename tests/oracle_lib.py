@@ -1,0 +1,154 @@
+"""ctypes binding of oracle/_build/libathena_oracle.so + a restatement of the reference's main loop
+(main.c:519-669) on top of it.  TEST INFRASTRUCTURE: imported only by tests/, smoke() and bench.py's
+cpu_baseline / --impl reference legs -- never by the product package."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+NG = 4
+dp = C.POINTER(C.c_double)
+GRAVFN = C.CFUNCTYPE(C.c_double, C.c_double, C.c_double, C.c_double)
+
+
+class OrcGrid(C.Structure):
+    _fields_ = [("nx1", C.c_int), ("nx2", C.c_int), ("nx3", C.c_int), ("nscal", C.c_int),
+                ("dx1", C.c_double), ("dx2", C.c_double), ("dx3", C.c_double),
+                ("x1min", C.c_double), ("x2min", C.c_double), ("x3min", C.c_double),
+                ("gamma", C.c_double),
+                ("d", dp), ("M1", dp), ("M2", dp), ("M3", dp), ("E", dp), ("s", dp),
+                ("grav", C.c_void_p)]
+
+
+class OrcIonPar(C.Structure):
+    _fields_ = [(n, C.c_double) for n in
+                ("sigma_ph", "m_H", "mu", "e_gamma", "alpha_C", "k_B", "time_unit", "max_de_iter",
+                 "max_de_therm_iter", "max_dx_iter", "max_de_step", "max_de_therm_step", "max_dx_step",
+                 "tfloor", "tceil")] + [("maxiter", C.c_int), ("min_area", C.c_double), ("d_nlo", C.c_double)]
+
+
+def build_oracle():
+    so = os.path.join(ROOT, "oracle", "_build", "libathena_oracle.so")
+    src = os.path.join(ROOT, "oracle", "athena_oracle.c")
+    if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "build_ref.py"), "--oracle-only"], check=True)
+    return so
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(build_oracle())
+        gp = C.POINTER(OrcGrid)
+        L.orc_bvals.argtypes = [gp, C.POINTER(C.c_int)]
+        L.orc_max_speeds.argtypes = [gp, dp]
+        L.orc_new_dt.argtypes = [gp, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double]
+        L.orc_new_dt.restype = C.c_double
+        L.orc_integrate_3d_ctu.argtypes = [gp, C.c_double]
+        L.orc_lr_states.argtypes = [dp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, dp, dp]
+        L.orc_roe_flux.argtypes = [dp, dp, dp, dp, C.c_int, C.c_double, C.c_double, dp]
+        L.orc_cons_to_prim.argtypes = [dp, C.c_int, C.c_double, dp]
+        L.orc_prim_to_cons.argtypes = [dp, C.c_int, C.c_double, dp]
+        L.orc_bvals_ionrad.argtypes = [gp, C.c_double, dp]
+        L.orc_roe_flux_batch.argtypes = [C.c_int, dp, dp, dp, dp, C.c_int, C.c_double, dp, dp]
+        L.orc_prim_to_cons_batch.argtypes = [C.c_int, dp, C.c_int, C.c_double, dp]
+        L.orc_cons_to_prim_batch.argtypes = [C.c_int, dp, C.c_int, C.c_double, dp]
+        L.orc_ion_derived.argtypes = [C.POINTER(OrcIonPar), C.c_double, C.c_double, C.c_double]
+        L.orc_ion_entering_flux.argtypes = [C.c_double, C.c_double]
+        L.orc_ion_entering_flux.restype = C.c_double
+        L.orc_ion_radtransfer.argtypes = [gp, C.POINTER(OrcIonPar), C.c_double, C.c_double, C.c_double,
+                                          dp, dp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.orc_ion_radtransfer.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def P(a):
+    return a.ctypes.data_as(dp)
+
+
+VARS = ("d", "M1", "M2", "M3", "E", "s")
+
+
+class OracleGrid:
+    """SoA state with ghosts + the scalars the reference keeps in MeshS/GridS."""
+
+    def __init__(self, nx, xmin, xmax, gamma, nscal, bc, grav=None):
+        self.nx = tuple(int(n) for n in nx)                     # (Nx1,Nx2,Nx3)
+        self.dx = tuple((xmax[a] - xmin[a]) / self.nx[a] for a in range(3))   # init_mesh.c: dx = (max-min)/Nx
+        self.xmin = tuple(xmin)
+        self.gamma, self.nscal = float(gamma), int(nscal)
+        self.bc = (C.c_int * 6)(*bc)
+        shp = (self.nx[2] + 2 * NG, self.nx[1] + 2 * NG, self.nx[0] + 2 * NG)
+        self.U = {v: np.zeros(shp) for v in VARS[:5 + self.nscal]}
+        self.grav = grav                                        # ctypes function pointer or None
+        self.g = OrcGrid(self.nx[0], self.nx[1], self.nx[2], self.nscal, *self.dx, *self.xmin, self.gamma,
+                         *[P(self.U[v]) if v in self.U else None for v in VARS],
+                         C.cast(grav, C.c_void_p) if grav is not None else None)
+        self.edgeflux = np.zeros((self.nx[2] + 1, self.nx[1] + 1, self.nx[0] + 1))
+        self.time, self.dt, self.nstep = 0.0, 0.0, 0
+
+    def active(self, v):
+        return self.U[v][NG:-NG, NG:-NG, NG:-NG]
+
+    def set_active(self, d):
+        for v in self.U:
+            self.active(v)[...] = d[v]
+
+    def bvals(self):
+        lib().orc_bvals(C.byref(self.g), self.bc)
+
+    def bvals_ionrad(self, flux_i):
+        lib().orc_bvals_ionrad(C.byref(self.g), flux_i, P(self.edgeflux))
+
+    def new_dt(self, cour_no, tlim):
+        self.dt = lib().orc_new_dt(C.byref(self.g), cour_no, self.dt, self.nstep, self.time, tlim)
+        return self.dt
+
+    def integrate(self):
+        lib().orc_integrate_3d_ctu(C.byref(self.g), self.dt)
+
+    def ion_radtransfer(self, ionpar, flux_i, cour_no):
+        dt = C.c_double(self.dt)
+        nchem, ntherm = C.c_int(0), C.c_int(0)
+        niter = lib().orc_ion_radtransfer(C.byref(self.g), C.byref(ionpar), flux_i, self.time, cour_no,
+                                          C.byref(dt), P(self.edgeflux), C.byref(nchem), C.byref(ntherm))
+        self.dt = dt.value
+        return niter, ntherm.value, nchem.value
+
+
+def ion_par_from(par, dx):
+    p = OrcIonPar()
+    for n, _ in OrcIonPar._fields_[:15]:
+        setattr(p, n, par.par_getd("ionradiation", n))
+    p.maxiter = int(par.par_getd("ionradiation", "maxiter"))   # ionrad_3d.c:757 assigns a double to an int
+    lib().orc_ion_derived(C.byref(p), *dx)
+    return p
+
+
+def run_main_loop(G, nsteps, cour_no, tlim, ionpar=None, flux_i=0.0, userwork=None, log=None):
+    """main.c:519-669 for one root Grid: [ion RT; bvals] -> integrate -> Userwork_in_loop -> time += dt ->
+    new_dt -> bvals.  G must already hold problem() data, ghost zones and the first dt (main.c:430-451)."""
+    for _ in range(nsteps):
+        if G.time >= tlim:
+            break
+        if ionpar is not None:
+            rad = G.ion_radtransfer(ionpar, flux_i, cour_no)
+            G.bvals()
+            if log is not None:
+                log.setdefault("rad", []).append(rad + (G.dt,))
+        G.integrate()
+        if userwork is not None:
+            userwork(G)
+        G.nstep += 1
+        G.time += G.dt
+        G.new_dt(cour_no, tlim)
+        G.bvals()
+        if log is not None:
+            log.setdefault("next_dt", []).append(G.dt)

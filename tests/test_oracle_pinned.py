@@ -1,0 +1,77 @@
+"""Pins the CPU oracle (oracle/athena_oracle.c) against the reference's own outputs:
+ * function level: reference lr_states()/fluxes()/Cons1D_to_Prim1D()/cfast() vectors (tests/golden/units_*.npz,
+   produced by oracle/_ref/<cfg>/libref_units.so = the reference's objects) -- bit-exact;
+ * run level: restart dumps of the reference binary after K steps (tests/golden/<case>_kK.npz) --
+   hydro bit-exact, ion RT bit-exact as well (oracle and reference share the host libm)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from cases import Case, load_golden, VARS
+
+
+@pytest.mark.parametrize("nscal", [0, 1])
+def test_units_bit_exact(nscal):
+    g = load_golden(f"units_nscal{nscal}")
+    L = ol.lib()
+    gam = float(g["gamma"])
+    n = len(g["Wl"])
+    c = lambda k: np.ascontiguousarray(g[k])
+    U = np.empty((n, 6)); F = np.empty((n, 6)); W = np.empty((n, 6))
+    L.orc_prim_to_cons_batch(n, ol.P(c("Wl")), nscal, gam, ol.P(U))
+    assert np.array_equal(U, g["Ul"])
+    L.orc_roe_flux_batch(n, ol.P(c("Ul")), ol.P(c("Ur")), ol.P(c("Wl")), ol.P(c("Wr")), nscal, gam, ol.P(c("eta")), ol.P(F))
+    assert np.array_equal(F, g["F"])
+    L.orc_cons_to_prim_batch(n, ol.P(c("Ul")), nscal, gam, ol.P(W))
+    assert np.array_equal(W, g["W_of_Ul"])
+    il, iu = int(g["pencil_il"]), int(g["pencil_iu"])
+    for t in range(len(g["pencil_W"])):
+        Wp = np.ascontiguousarray(g["pencil_W"][t])
+        n = len(Wp)
+        Wl = np.zeros((n, 6)); Wr = np.zeros((n, 6))
+        L.orc_lr_states(ol.P(Wp), nscal, gam, float(g["pencil_dt"]), float(g["pencil_dx"]), il, iu, ol.P(Wl), ol.P(Wr))
+        assert np.array_equal(Wl[il:iu + 2], g["pencil_Wl"][t][il:iu + 2])
+        assert np.array_equal(Wr[il - 1:iu + 1], g["pencil_Wr"][t][il - 1:iu + 1])
+
+
+def oracle_run(case, log=None):
+    grav = case.grav_fn()
+    G = ol.OracleGrid(case.nx, case.xmin, case.xmax, case.gamma, case.nscal, case.bc, grav=grav)
+    G.set_active(case.U0)
+    G.bvals()
+    if case.ion:
+        G.bvals_ionrad(case.flux_i)
+    G.new_dt(case.cour_no, case.tlim)
+    assert G.dt == float(case.gold["dt0"])
+    ionpar = ol.ion_par_from(case.par, G.dx) if case.ion else None
+    userwork = None
+    tab = case.reset_table()
+    if tab is not None:
+        cells, vals = tab
+
+        def userwork(G):
+            for n, v in enumerate(VARS):
+                G.U[v].reshape(-1)[cells] = vals[n]
+    ol.run_main_loop(G, case.nsteps, case.cour_no, case.tlim, ionpar, case.flux_i, userwork, log)
+    return G
+
+
+@pytest.mark.parametrize("name", ["blast16_k1", "blast16_k6", "blastmix_k5", "ifront32_k1", "ifront32_k4",
+                                  "ioniz24_k1", "ioniz24_k3"])
+def test_run_matches_reference_dump(name):
+    case = Case(name)
+    log = {}
+    G = oracle_run(case, log)
+    assert G.nstep == case.nsteps
+    assert np.array_equal(np.array(log["next_dt"]), case.gold["next_dt"][1:]) or \
+        np.allclose(np.array(log["next_dt"]), case.gold["next_dt"][1:], rtol=5e-7)   # stdout prints 7 digits
+    assert G.time == float(case.gold["time1"])
+    assert G.dt == float(case.gold["dt1"])
+    for v in case.U1:
+        assert np.array_equal(G.active(v), case.U1[v]), f"{name}: {v} differs, max abs {np.abs(G.active(v)-case.U1[v]).max()}"
+    if case.ion:
+        rad = case.gold["rad"]
+        assert [r[0] for r in log["rad"]] == [int(x) for x in rad[:, 0]]
+        assert np.array_equal(G.edgeflux, case.gold["U1_edgeflux"])
