@@ -1,0 +1,366 @@
+// api.cu -- the C ABI of libathena_b200.so (include/athena_b200.h): handle lifetime, host<->device
+// coherence, static-potential tabulation, and thin wrappers over hydro.cu / ion.cu.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <thread>
+#include <vector>
+#include "../../include/athena_b200.h"
+#include "engine.cuh"
+
+static thread_local std::string g_err;
+void ab2_set_error(const std::string& s) { g_err = s; }
+bool ab2_check(cudaError_t e, const char* what)
+{
+  if (e == cudaSuccess) return true;
+  g_err = std::string("[athena_b200] ") + what + ": " + cudaGetErrorString(e);
+  return false;
+}
+#define CK(call, what) do { if (!ab2_check((call), what)) return -1; } while (0)
+
+static double* dev_alloc(ab2_grid* h, size_t ndouble, bool zero = true)
+{
+  void* p = nullptr;
+  if (!ab2_check(cudaMalloc(&p, ndouble*sizeof(double)), "cudaMalloc")) return nullptr;
+  if (zero && !ab2_check(cudaMemsetAsync(p, 0, ndouble*sizeof(double), h->stream), "cudaMemset")) return nullptr;
+  h->allocs.push_back(p);
+  h->bytes_allocated += ndouble*sizeof(double);
+  return (double*)p;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// AoS (ConsS) <-> SoA transposition on the device
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_aos_to_soa(GridDev g, int nvar, long ncell, const double* aos)
+{
+  const long t = (long)blockIdx.x*blockDim.x + threadIdx.x;
+  if (t >= ncell) return;
+  for (int v=0; v<nvar; v++) g.U[v][t] = aos[t*nvar + v];
+}
+__global__ void k_soa_to_aos(GridDev g, int nvar, long ncell, double* aos)
+{
+  const long t = (long)blockIdx.x*blockDim.x + threadIdx.x;
+  if (t >= ncell) return;
+  for (int v=0; v<nvar; v++) aos[t*nvar + v] = g.U[v][t];
+}
+
+extern "C" {
+
+const char* ab2_last_error(void) { return g_err.c_str(); }
+const char* ab2_version(void) { return "athena_b200 0.1 (sm_100a, fp64, fmad=off)"; }
+
+int ab2_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+ab2_grid* ab2_grid_create(const ab2_grid_desc* d)
+{
+  if (!d || d->nx1 < 1 || d->nx2 < 1 || d->nx3 < 1 || d->nscal < 0 || d->nscal > 1) {
+    ab2_set_error("[ab2_grid_create]: bad descriptor"); return nullptr;
+  }
+  if (d->nx1 < 4 || d->nx2 < 4 || d->nx3 < 4) {
+    ab2_set_error("[ab2_grid_create]: the 3D CTU path needs at least 4 zones per direction"); return nullptr;
+  }
+  if (ab2_device_count() <= d->device) {
+    ab2_set_error("[ab2_grid_create]: no CUDA device (this engine has no CPU fallback)"); return nullptr;
+  }
+  if (!ab2_check(cudaSetDevice(d->device), "cudaSetDevice")) return nullptr;
+  ab2_grid* h = new ab2_grid();
+  memset(&h->g, 0, sizeof h->g);
+  h->nscal = d->nscal; h->device = d->device;
+  h->has_grav = false; h->has_ion = false; h->n_fixed = 0; h->d_fixed_cells = nullptr; h->d_fixed_vals = nullptr;
+  h->bytes_allocated = 0; h->launches = 0; h->maxiter = 0;
+  memset(&h->ion, 0, sizeof h->ion);
+  if (d->stream) { h->stream = (cudaStream_t)d->stream; h->own_stream = false; }
+  else {
+    if (!ab2_check(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), "cudaStreamCreate")) { delete h; return nullptr; }
+    h->own_stream = true;
+  }
+  GridDev& g = h->g;
+  g.nx[0] = d->nx1; g.nx[1] = d->nx2; g.nx[2] = d->nx3;
+  for (int a=0; a<3; a++) g.n[a] = g.nx[a] + 2*AB2_NG;
+  g.st[0] = 1; g.st[1] = g.n[0]; g.st[2] = (long)g.n[0]*g.n[1];
+  g.dx[0] = d->dx1; g.dx[1] = d->dx2; g.dx[2] = d->dx3;
+  g.Gamma = d->gamma; g.Gamma_1 = d->gamma - 1.0;
+  h->xmin[0] = d->x1min; h->xmin[1] = d->x2min; h->xmin[2] = d->x3min;
+  const size_t ncell = (size_t)g.n[0]*g.n[1]*g.n[2];
+  const int nvar = 5 + d->nscal;
+
+  h->own_U = (d->external_U[0] == nullptr);
+  for (int v=0; v<nvar; v++) {
+    g.U[v] = h->own_U ? dev_alloc(h, ncell) : d->external_U[v];
+    if (!g.U[v]) { ab2_set_error(h->own_U ? g_err : std::string("[ab2_grid_create]: external_U incomplete")); ab2_grid_destroy(h); return nullptr; }
+  }
+  // CTU scratch: 9 state arrays of nvar components in one slab (also the staging area of the AoS transposes)
+  double* slab = dev_alloc(h, (size_t)9*nvar*ncell);
+  if (!slab) { ab2_grid_destroy(h); return nullptr; }
+  size_t off = 0;
+  for (int dir=0; dir<3; dir++) for (int v=0; v<nvar; v++) { g.Ul[dir][v] = slab + off; off += ncell; }
+  for (int dir=0; dir<3; dir++) for (int v=0; v<nvar; v++) { g.Ur[dir][v] = slab + off; off += ncell; }
+  for (int dir=0; dir<3; dir++) for (int v=0; v<nvar; v++) { g.F[dir][v] = slab + off; off += ncell; }
+  for (int dir=0; dir<3; dir++) { g.eta[dir] = dev_alloc(h, ncell); if (!g.eta[dir]) { ab2_grid_destroy(h); return nullptr; } }
+
+  void* p = nullptr;
+  if (!ab2_check(cudaMalloc(&p, SC_N*sizeof(unsigned long long)), "cudaMalloc scalars")) { ab2_grid_destroy(h); return nullptr; }
+  h->d_scal = (unsigned long long*)p; h->allocs.push_back(p);
+  cudaMemsetAsync(h->d_scal, 0, SC_N*sizeof(unsigned long long), h->stream);
+  if (!ab2_check(cudaHostAlloc(&p, SC_N*sizeof(unsigned long long), cudaHostAllocDefault), "cudaHostAlloc")) { ab2_grid_destroy(h); return nullptr; }
+  h->h_scal = (unsigned long long*)p;
+  memset(h->h_scal, 0, SC_N*sizeof(unsigned long long));
+  if (!ab2_check(cudaStreamSynchronize(h->stream), "create sync")) { ab2_grid_destroy(h); return nullptr; }
+  return h;
+}
+
+void ab2_grid_destroy(ab2_grid* h)
+{
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  for (void* p : h->allocs) cudaFree(p);
+  if (h->h_scal) cudaFreeHost(h->h_scal);
+  if (h->own_stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+long long ab2_bytes_allocated(const ab2_grid* h) { return (long long)h->bytes_allocated; }
+long long ab2_kernel_launches(const ab2_grid* h) { return h->launches; }
+int ab2_synchronize(ab2_grid* h) { CK(cudaStreamSynchronize(h->stream), "synchronize"); return 0; }
+double* ab2_device_ptr(ab2_grid* h, int var) { return (var >= 0 && var < 5+h->nscal) ? h->g.U[var] : nullptr; }
+
+// ---- coherence ----------------------------------------------------------------------------------------
+int ab2_upload_cons_aos(ab2_grid* h, const double* U_aos)
+{
+  GridDev& g = h->g;
+  const long ncell = (long)g.n[0]*g.n[1]*g.n[2];
+  const int nvar = 5 + h->nscal;
+  double* stage = g.Ul[0][0];      // scratch slab is dead between steps
+  CK(cudaMemcpyAsync(stage, U_aos, (size_t)ncell*nvar*sizeof(double), cudaMemcpyHostToDevice, h->stream), "upload aos");
+  k_aos_to_soa<<<(unsigned)((ncell+255)/256), 256, 0, h->stream>>>(g, nvar, ncell, stage);
+  h->launches++;
+  CK(cudaStreamSynchronize(h->stream), "upload aos sync");
+  return 0;
+}
+
+int ab2_download_cons_aos(ab2_grid* h, double* U_aos)
+{
+  GridDev& g = h->g;
+  const long ncell = (long)g.n[0]*g.n[1]*g.n[2];
+  const int nvar = 5 + h->nscal;
+  double* stage = g.Ul[0][0];
+  k_soa_to_aos<<<(unsigned)((ncell+255)/256), 256, 0, h->stream>>>(g, nvar, ncell, stage);
+  h->launches++;
+  CK(cudaMemcpyAsync(U_aos, stage, (size_t)ncell*nvar*sizeof(double), cudaMemcpyDeviceToHost, h->stream), "download aos");
+  CK(cudaStreamSynchronize(h->stream), "download aos sync");
+  return 0;
+}
+
+int ab2_upload_cons_soa(ab2_grid* h, const double* const vars[6])
+{
+  const size_t nb = (size_t)h->g.n[0]*h->g.n[1]*h->g.n[2]*sizeof(double);
+  for (int v=0; v<5+h->nscal; v++) CK(cudaMemcpyAsync(h->g.U[v], vars[v], nb, cudaMemcpyHostToDevice, h->stream), "upload soa");
+  CK(cudaStreamSynchronize(h->stream), "upload soa sync");
+  return 0;
+}
+
+int ab2_download_cons_soa(ab2_grid* h, double* const vars[6])
+{
+  const size_t nb = (size_t)h->g.n[0]*h->g.n[1]*h->g.n[2]*sizeof(double);
+  for (int v=0; v<5+h->nscal; v++) CK(cudaMemcpyAsync(vars[v], h->g.U[v], nb, cudaMemcpyDeviceToHost, h->stream), "download soa");
+  CK(cudaStreamSynchronize(h->stream), "download soa sync");
+  return 0;
+}
+
+static size_t edge_count(const ab2_grid* h) { return (size_t)(h->g.nx[0]+1)*(h->g.nx[1]+1)*(h->g.nx[2]+1); }
+
+int ab2_upload_edgeflux(ab2_grid* h, const double* ef)
+{
+  if (!h->has_ion) { ab2_set_error("[ab2_upload_edgeflux]: ab2_ion_init not called"); return -1; }
+  CK(cudaMemcpyAsync(h->ion.edgeflux, ef, edge_count(h)*sizeof(double), cudaMemcpyHostToDevice, h->stream), "upload edgeflux");
+  CK(cudaStreamSynchronize(h->stream), "upload edgeflux sync");
+  return 0;
+}
+
+int ab2_download_edgeflux(ab2_grid* h, double* ef)
+{
+  if (!h->has_ion) { ab2_set_error("[ab2_download_edgeflux]: ab2_ion_init not called"); return -1; }
+  CK(cudaMemcpyAsync(ef, h->ion.edgeflux, edge_count(h)*sizeof(double), cudaMemcpyDeviceToHost, h->stream), "download edgeflux");
+  CK(cudaStreamSynchronize(h->stream), "download edgeflux sync");
+  return 0;
+}
+
+// ---- hydro -----------------------------------------------------------------------------------------------
+int ab2_bvals_mhd(ab2_grid* h, const int bc[6]) { return hydro_bvals(h, bc); }
+int ab2_max_wave_speeds(ab2_grid* h, double out[3]) { return hydro_max_speeds(h, out); }
+
+int ab2_new_dt(ab2_grid* h, double cour_no, double dt_old, int nstep, double time, double tlim,
+               ab2_reduce_fn reduce, void* ctx, double* dt_out)
+{ // new_dt.c:155-185
+  double v[3];
+  if (hydro_max_speeds(h, v) != 0) return -1;
+  double max_dti = 0.0;
+  for (int d=0; d<3; d++) if (h->g.nx[d] > 1) { const double x = v[d]/h->g.dx[d]; max_dti = (max_dti > x) ? max_dti : x; }
+  double dt;
+  if (nstep == 0) dt = cour_no/max_dti;
+  else { const double a = 2.0*dt_old, b = cour_no/max_dti; dt = (a < b) ? a : b; }
+  if (reduce) reduce(&dt, 1, 0, ctx);                 // new_dt.c:175-179 MPI_Allreduce(MIN)
+  if ((time < tlim) && ((tlim - time) < dt)) dt = tlim - time;
+  *dt_out = dt;
+  return 0;
+}
+
+int ab2_integrate_3d_ctu(ab2_grid* h, double dt) { return hydro_integrate(h, dt); }
+
+int ab2_set_fixed_cells(ab2_grid* h, long n, const long* cells, const double* vals)
+{
+  h->n_fixed = 0;
+  if (n <= 0) return 0;
+  void* p = nullptr;
+  CK(cudaMalloc(&p, n*sizeof(long)), "cudaMalloc fixed cells"); h->allocs.push_back(p); h->d_fixed_cells = (long*)p;
+  CK(cudaMalloc(&p, (size_t)6*n*sizeof(double)), "cudaMalloc fixed vals"); h->allocs.push_back(p); h->d_fixed_vals = (double*)p;
+  CK(cudaMemcpyAsync(h->d_fixed_cells, cells, n*sizeof(long), cudaMemcpyHostToDevice, h->stream), "fixed cells H2D");
+  CK(cudaMemcpyAsync(h->d_fixed_vals, vals, (size_t)6*n*sizeof(double), cudaMemcpyHostToDevice, h->stream), "fixed vals H2D");
+  CK(cudaStreamSynchronize(h->stream), "fixed sync");
+  h->n_fixed = n;
+  return 0;
+}
+
+int ab2_apply_fixed_cells(ab2_grid* h) { return hydro_apply_fixed(h); }
+
+// ---- static potential -------------------------------------------------------------------------------------
+// 1-D coordinate kinds per direction: the four argument forms the reference uses
+enum { CK_C = 0, CK_M = 1, CK_MH = 2, CK_PH = 3 };
+
+int ab2_set_static_grav_pot(ab2_grid* h, ab2_grav_pot_fn phi)
+{
+  GridDev& g = h->g;
+  if (!phi) { h->has_grav = false; return 0; }
+  const size_t ncell = (size_t)g.n[0]*g.n[1]*g.n[2];
+  // coordinates exactly as cc_pos() and the call sites form them
+  std::vector<double> X[3][4];
+  bool alias_m[3], alias_mh[3];
+  for (int d=0; d<3; d++) {
+    const int n = g.n[d];
+    const double x0 = h->xmin[d], dx = g.dx[d];
+    for (int kd=0; kd<4; kd++) X[d][kd].resize(n);
+    for (int i=0; i<n; i++) {
+      const double xc = x0 + ((double)(i - AB2_NG) + 0.5)*dx;      // cc_pos.c
+      X[d][CK_C][i] = xc;
+      X[d][CK_M][i] = (xc - dx);
+      X[d][CK_MH][i] = (xc - 0.5*dx);
+      X[d][CK_PH][i] = (xc + 0.5*dx);
+    }
+    alias_m[d] = true; alias_mh[d] = true;
+    for (int i=1; i<n; i++) {
+      if (X[d][CK_M][i] != X[d][CK_C][i-1]) alias_m[d] = false;
+      if (X[d][CK_MH][i] != X[d][CK_PH][i-1]) alias_mh[d] = false;
+    }
+  }
+  std::vector<double> host(ncell);
+  auto build = [&](int k0, int k1, int k2) -> double* {
+    const int kinds[3] = {k0,k1,k2};
+    const int n1 = g.n[0], n2 = g.n[1], n3 = g.n[2];
+    unsigned nthr = std::thread::hardware_concurrency(); if (nthr < 1) nthr = 1; if (nthr > 32) nthr = 32;
+    const char* env = getenv("AB2_GRAV_THREADS"); if (env) { int v = atoi(env); if (v >= 1) nthr = (unsigned)v; }
+    std::vector<std::thread> pool;
+    for (unsigned t=0; t<nthr; t++) pool.emplace_back([&, t]() {
+      for (int k=(int)t; k<n3; k+=(int)nthr) for (int j=0; j<n2; j++) {
+        double* rowp = host.data() + ((size_t)k*n2 + j)*n1;
+        const double x2 = X[1][kinds[1]][j], x3 = X[2][kinds[2]][k];
+        for (int i=0; i<n1; i++) rowp[i] = phi(X[0][kinds[0]][i], x2, x3);
+      }
+    });
+    for (auto& th : pool) th.join();
+    double* dptr = dev_alloc(h, ncell, false);
+    if (!dptr) return nullptr;
+    if (!ab2_check(cudaMemcpyAsync(dptr, host.data(), ncell*sizeof(double), cudaMemcpyHostToDevice, h->stream), "phi H2D")) return nullptr;
+    if (!ab2_check(cudaStreamSynchronize(h->stream), "phi sync")) return nullptr;
+    return dptr;
+  };
+  auto kinds_for = [](int d, int kind, int out[3]) { out[0] = out[1] = out[2] = CK_C; out[d] = kind; };
+
+  const double* T[PHI_NTAB];
+  int kk[3];
+  if (!(T[PHI_C] = build(CK_C,CK_C,CK_C))) return -1;
+  for (int d=0; d<3; d++) { kinds_for(d, CK_PH, kk); if (!(T[PHI_PH0+d] = build(kk[0],kk[1],kk[2]))) return -1; }
+  for (int d=0; d<3; d++) {
+    if (alias_mh[d]) T[PHI_MH0+d] = T[PHI_PH0+d] - g.st[d];
+    else { kinds_for(d, CK_MH, kk); if (!(T[PHI_MH0+d] = build(kk[0],kk[1],kk[2]))) return -1; }
+    if (alias_m[d]) T[PHI_M0+d] = T[PHI_C] - g.st[d];
+    else { kinds_for(d, CK_M, kk); if (!(T[PHI_M0+d] = build(kk[0],kk[1],kk[2]))) return -1; }
+  }
+  for (int d=0; d<3; d++) for (int t=0; t<3; t++) {
+    if (t == d) continue;
+    for (int plus=0; plus<2; plus++) {
+      const int id = phi_mix(d,t,plus);
+      if (alias_m[d]) T[id] = T[(plus ? PHI_PH0 : PHI_MH0) + t] - g.st[d];
+      else { kk[0] = kk[1] = kk[2] = CK_C; kk[d] = CK_M; kk[t] = plus ? CK_PH : CK_MH; if (!(T[id] = build(kk[0],kk[1],kk[2]))) return -1; }
+    }
+  }
+  for (int n=0; n<PHI_NTAB; n++) g.phi[n] = T[n];
+  if (!g.dhalf) { g.dhalf = dev_alloc(h, ncell); if (!g.dhalf) return -1; }
+  CK(cudaStreamSynchronize(h->stream), "grav sync");
+  h->has_grav = true;
+  return 0;
+}
+
+// ---- ion ------------------------------------------------------------------------------------------------
+void ab2_ion_derived(ab2_ion_par* p, double dx1, double dx2, double dx3)
+{ // ionrad.c:115-131 (including the dx[1]-twice quirk of :129)
+  const double area1 = dx1*dx2, area2 = dx1*dx3, area3 = dx2*dx3;
+  if (area1 < area2) { if (area1 < area3) p->min_area = area1; else p->min_area = area3; }
+  else { if (area2 < area3) p->min_area = area2; else p->min_area = area3; }
+  double maxdx = dx1 > dx2 ? dx1 : dx2;
+  maxdx = maxdx > dx3 ? maxdx : dx2;
+  p->d_nlo = 1.0e-4 * p->m_H / (p->sigma_ph * maxdx);        // MINOPTDEPTH, ionrad.h:29
+}
+
+double ab2_ion_entering_flux(double flux_i, double time)
+{ // ionradplane_3d.c:265
+  return flux_i*(5.*(erf((time - 1.2e5)/8e4)+1)+0.1);
+}
+
+int ab2_ion_init(ab2_grid* h, const ab2_ion_par* par)
+{
+  if (h->nscal < 1) { ab2_set_error("[ab2_ion_init]: ion radiation needs NSCALARS >= 1"); return -1; }
+  IonParDev& p = h->ionpar;
+  p.sigma_ph = par->sigma_ph; p.m_H = par->m_H; p.mu = par->mu; p.e_gamma = par->e_gamma; p.alpha_C = par->alpha_C;
+  p.k_B = par->k_B; p.time_unit = par->time_unit; p.max_de_iter = par->max_de_iter;
+  p.max_de_therm_iter = par->max_de_therm_iter; p.max_dx_iter = par->max_dx_iter; p.max_de_step = par->max_de_step;
+  p.max_de_therm_step = par->max_de_therm_step; p.max_dx_step = par->max_dx_step; p.tfloor = par->tfloor; p.tceil = par->tceil;
+  p.min_area = par->min_area; p.d_nlo = par->d_nlo;
+  h->maxiter = par->maxiter;
+  if (!(par->max_de_therm_step > 0)) { ab2_set_error("[ab2_ion_init]: max_de_therm_step must be > 0 (check_range reads an unset value otherwise, ionrad_3d.c:227-241)"); return -1; }
+  if (!h->has_ion) {
+    const size_t ncell = (size_t)h->g.n[0]*h->g.n[1]*h->g.n[2];
+    IonDev& I = h->ion;
+    if (!(I.ph_rate = dev_alloc(h, ncell)) || !(I.edot = dev_alloc(h, ncell)) || !(I.nHdot = dev_alloc(h, ncell)) ||
+        !(I.e_init = dev_alloc(h, ncell)) || !(I.e_th_init = dev_alloc(h, ncell)) || !(I.x_init = dev_alloc(h, ncell)) ||
+        !(I.edgeflux = dev_alloc(h, edge_count(h)))) return -1;
+    double* s = dev_alloc(h, (ncell+1)/2);
+    if (!s) return -1;
+    I.sign_state = (int*)s;
+    CK(cudaStreamSynchronize(h->stream), "ion init sync");
+    h->has_ion = true;
+  }
+  return 0;
+}
+
+int ab2_bvals_ionrad(ab2_grid* h, double flux_i)
+{
+  if (!h->has_ion) { ab2_set_error("[ab2_bvals_ionrad]: ab2_ion_init not called"); return -1; }
+  return ion_bvals_ionrad(h, flux_i);
+}
+
+int ab2_ion_radtransfer_3d(ab2_grid* h, double flux_i, double time, double cour_no, double* dt,
+                           int* niter, int* nchem, int* ntherm, ab2_reduce_fn reduce, void* ctx)
+{
+  if (!h->has_ion) { ab2_set_error("[ab2_ion_radtransfer_3d]: ab2_ion_init not called"); return -1; }
+  return ion_radtransfer(h, ab2_ion_entering_flux(flux_i, time), cour_no, dt, niter, nchem, ntherm, reduce, ctx);
+}
+
+} // extern "C"

@@ -1,0 +1,104 @@
+// engine.cuh -- device-side grid descriptor shared by the kernels, and the host-side handle.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#define AB2_NG 4                 // nghost, defs.h.in:129-140
+#define AB2_NVAR 6               // d, M1, M2, M3, E, s0 (s0 unused when nscal == 0)
+
+// Static-potential tables.  Entry = Phi evaluated by the HOST callback at exactly the argument the
+// reference passes for cell (i,j,k) (integrate_3d_ctu.c:334-336, 1172-1215, 1468-1522, 1878-1933,
+// 2746-2777): offsets per direction are 0, -dx ("M"), -dx/2 ("MH"), +dx/2 ("PH").
+enum {
+  PHI_C = 0,
+  PHI_M0, PHI_M1, PHI_M2,          // (x_d - dx_d)
+  PHI_MH0, PHI_MH1, PHI_MH2,       // (x_d - dx_d/2)
+  PHI_PH0, PHI_PH1, PHI_PH2,       // (x_d + dx_d/2)
+  PHI_MIX0,                        // 12 tables: MIX(d,t,s): -dx_d in d and (s? +:-) dx_t/2 in t, t != d
+  PHI_NTAB = PHI_MIX0 + 12
+};
+// index of MIX(d,t,sign): d in 0..2, t = one of the two other directions in ascending order (slot 0/1), sign 0:-,1:+
+__host__ __device__ inline int phi_mix(int d, int t, int plus)
+{
+  int slot = (t > d) ? (t - 1) : t;           // position of t among the directions != d  (0 or 1)
+  return PHI_MIX0 + d*4 + slot*2 + plus;
+}
+
+struct GridDev {
+  int nx[3];                 // active zones
+  int n[3];                  // with ghosts
+  long st[3];                // element strides: st[0]=1, st[1]=n1, st[2]=n1*n2
+  double dx[3];
+  double Gamma, Gamma_1;
+  double* U[AB2_NVAR];       // conserved state, SoA [n3][n2][n1]
+  double* Ul[3][AB2_NVAR];   // face states, PHYSICAL component order (d,M1,M2,M3,E,s), one set per face direction
+  double* Ur[3][AB2_NVAR];
+  double* F[3][AB2_NVAR];    // fluxes, physical component order
+  double* eta[3];
+  double* dhalf;
+  const double* phi[PHI_NTAB];
+};
+
+// scalars block in device memory (mirrored to pinned host memory on demand)
+enum {
+  SC_MAXV1 = 0, SC_MAXV2, SC_MAXV3,   // new_dt: max |v|+a per direction (bit patterns, atomicMax on u64)
+  SC_DT_CHEM, SC_DT_THERM,            // ion: min over cells (atomicMin on u64 patterns)
+  SC_MAX_DTI,                         // ion: compute_dt_hydro max (atomicMax)
+  SC_COUNT,                           // ion: check_range cell count (u64)
+  SC_ERR,                             // sticky error flags
+  SC_N = 16
+};
+
+struct IonParDev {
+  double sigma_ph, m_H, mu, e_gamma, alpha_C, k_B, time_unit;
+  double max_de_iter, max_de_therm_iter, max_dx_iter;
+  double max_de_step, max_de_therm_step, max_dx_step;
+  double tfloor, tceil;
+  double min_area, d_nlo;
+};
+
+struct IonDev {
+  double *ph_rate, *edot, *nHdot, *e_init, *e_th_init, *x_init;
+  int* sign_state;            // (sign_count << 2) | (last_sign + 1)
+  double* edgeflux;           // [nx3+1][nx2+1][nx1+1]
+};
+
+typedef void (*ab2_reduce_fn_t)(double* vals, int n, int op, void* ctx);
+
+struct ab2_grid {
+  GridDev g;
+  int nscal;
+  int device;
+  double xmin[3];              // GridS.MinX
+  cudaStream_t stream;
+  bool own_stream, own_U;
+  std::vector<void*> allocs;
+  unsigned long long* d_scal;      // device scalars
+  unsigned long long* h_scal;      // pinned host mirror
+  bool has_grav;
+  bool has_ion;
+  IonParDev ionpar;
+  IonDev ion;
+  int maxiter;
+  long n_fixed;                    // Userwork_in_loop replay table
+  long* d_fixed_cells;
+  double* d_fixed_vals;
+  size_t bytes_allocated;
+  long long launches;              // kernels launched so far (bench.py's gpu_launches)
+};
+
+// error plumbing (api.cu)
+void ab2_set_error(const std::string& s);
+bool ab2_check(cudaError_t e, const char* what);
+
+// hydro.cu
+int hydro_bvals(ab2_grid* h, const int bc[6]);
+int hydro_max_speeds(ab2_grid* h, double out[3]);
+int hydro_integrate(ab2_grid* h, double dt);
+int hydro_apply_fixed(ab2_grid* h);
+// ion.cu
+int ion_bvals_ionrad(ab2_grid* h, double flux_i);
+int ion_radtransfer(ab2_grid* h, double flux_in, double cour_no, double* dt_io, int* niter, int* nchem, int* ntherm,
+                    ab2_reduce_fn_t reduce, void* ctx);

@@ -1,0 +1,486 @@
+// hydro.cu -- FP64 CUDA kernels (sm_100a) for the hydro half of the hot path:
+//   bvals_mhd   (bvals_mhd.c:174-508, physical BCs :959-1949)
+//   new_dt      (new_dt.c:69-139)
+//   integrate_3d_ctu (integrators/integrate_3d_ctu.c:110-3368; PLM lr_states_plm.c, Roe roe.c/hlle.c)
+//
+// Layout: SoA, one double[n3][n2][n1] per variable, x1 fastest.  Face states and fluxes are kept in
+// PHYSICAL component order (d,M1,M2,M3,E,s) so the reference's (x,y,z)->(z,x,y) permutations between
+// sweeps reduce to component-wise operations; the sweep order (Mx,My,Mz) is only
+// formed in registers when a pencil routine (PLM / Roe / cfast) needs it.
+//
+// Pass structure of one step (HBM round trips):
+//   A  k_first_x1 / k_first_march<1|2> : U -> first-pass face states Ul,Ur + fluxes F     (steps 1-3)
+//   B  k_dhalf                         : d^{n+1/2} from first-pass fluxes (static potential only, step 8a)
+//   C  k_correct<0|1|2>                : transverse flux-gradient + gravity corrections of Ul,Ur, eta (steps 5-7, 9a)
+//   D  k_final<0|1|2>                  : etah = max of 9 etas, Roe flux from corrected states (step 9b-d)
+//   E  k_update                        : gravity source (11a) + three ordered flux-difference updates (12a-c)
+#include "engine.cuh"
+#include "physics.cuh"
+
+#define NG AB2_NG
+
+// ---------------------------------------------------------------------------------------------------
+// sweep-order <-> physical-order register shuffles
+// ---------------------------------------------------------------------------------------------------
+template <int DIR, int NS> __device__ __forceinline__ S6 load_sweep(double* const* A, long c)
+{
+  S6 r;
+  r.d = A[0][c];
+  r.x = A[1+DIR][c];
+  r.y = A[1+(DIR+1)%3][c];
+  r.z = A[1+(DIR+2)%3][c];
+  r.e = A[4][c];
+  r.s = NS ? A[5][c] : 0.0;
+  return r;
+}
+template <int DIR, int NS> __device__ __forceinline__ void store_sweep(double* const* A, long c, const S6& r)
+{
+  A[0][c] = r.d;
+  A[1+DIR][c] = r.x;
+  A[1+(DIR+1)%3][c] = r.y;
+  A[1+(DIR+2)%3][c] = r.z;
+  A[4][c] = r.e;
+  if (NS) A[5][c] = r.s;
+}
+template <int DIR, int NS> __device__ __forceinline__ S6 sweep_from_phys(const double* P)
+{
+  S6 r; r.d = P[0]; r.x = P[1+DIR]; r.y = P[1+(DIR+1)%3]; r.z = P[1+(DIR+2)%3]; r.e = P[4]; r.s = NS ? P[5] : 0.0;
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Pass A, x1: one block = 128 consecutive cells of one (j,k) row -> 125 faces.  Primitive states and the
+// left states travel between neighbouring threads through shared memory.
+// ---------------------------------------------------------------------------------------------------
+#define A1_T 128
+#define A1_F (A1_T-3)
+template <int NS, bool GRAV>
+__global__ void __launch_bounds__(A1_T) k_first_x1(GridDev g, double dt)
+{
+  __shared__ double sW[6][A1_T];
+  __shared__ double sL[6][A1_T];
+  const int t = threadIdx.x;
+  const int il = NG-2, iu = g.nx[0]+NG+1;
+  const int f0 = il+1 + blockIdx.x*A1_F;
+  const int c = f0 - 2 + t;
+  const int j = NG-2 + blockIdx.y, k = NG-2 + blockIdx.z;
+  const long row = (long)k*g.st[2] + (long)j*g.st[1];
+  const double dtodx = dt/g.dx[0];
+
+  S6 W0;
+  if (c <= iu+1) {
+    S6 U = load_sweep<0,NS>(g.U, row+c);
+    W0 = cons_to_prim<NS>(U, g.Gamma_1);
+    sW[0][t] = W0.d; sW[1][t] = W0.x; sW[2][t] = W0.y; sW[3][t] = W0.z; sW[4][t] = W0.e; sW[5][t] = W0.s;
+  }
+  __syncthreads();
+  S6 Wl_next, Wr_this;
+  const bool do_plm = (t >= 1) && (t <= A1_T-2) && (c <= iu);
+  if (do_plm) {
+    S6 Wm, Wp;
+    Wm.d = sW[0][t-1]; Wm.x = sW[1][t-1]; Wm.y = sW[2][t-1]; Wm.z = sW[3][t-1]; Wm.e = sW[4][t-1]; Wm.s = sW[5][t-1];
+    Wp.d = sW[0][t+1]; Wp.x = sW[1][t+1]; Wp.y = sW[2][t+1]; Wp.z = sW[3][t+1]; Wp.e = sW[4][t+1]; Wp.s = sW[5][t+1];
+    plm_cell<NS>(Wm, W0, Wp, dtodx, g.Gamma, Wl_next, Wr_this);
+    if (GRAV) {   // integrate_3d_ctu.c:318-342
+      const long cc = row + c;
+      Wl_next.x -= dtodx*(g.phi[PHI_MH0][cc+1] - g.phi[PHI_M0][cc+1]);
+      Wr_this.x -= dtodx*(g.phi[PHI_C][cc] - g.phi[PHI_MH0][cc]);
+    }
+    sL[0][t] = Wl_next.d; sL[1][t] = Wl_next.x; sL[2][t] = Wl_next.y; sL[3][t] = Wl_next.z; sL[4][t] = Wl_next.e; sL[5][t] = Wl_next.s;
+  }
+  __syncthreads();
+  if ((t >= 2) && (t <= A1_T-2) && (c <= iu)) {
+    S6 Wl;
+    Wl.d = sL[0][t-1]; Wl.x = sL[1][t-1]; Wl.y = sL[2][t-1]; Wl.z = sL[3][t-1]; Wl.e = sL[4][t-1]; Wl.s = sL[5][t-1];
+    const S6 Ul = prim_to_cons<NS>(Wl, g.Gamma_1);
+    const S6 Ur = prim_to_cons<NS>(Wr_this, g.Gamma_1);
+    S6 F;
+    roe_flux<NS>(Ul, Ur, Wl, Wr_this, 0.0, g.Gamma, g.Gamma_1, F);
+    store_sweep<0,NS>(g.Ul[0], row+c, Ul);
+    store_sweep<0,NS>(g.Ur[0], row+c, Ur);
+    store_sweep<0,NS>(g.F[0], row+c, F);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Pass A, x2/x3: threads lie along x1 (coalesced rows), each marches `seg` faces along the sweep axis with a
+// 3-cell sliding window of primitives in registers; the left state of the next face is carried over.
+// ---------------------------------------------------------------------------------------------------
+template <int DIR, int NS, bool GRAV>
+__global__ void __launch_bounds__(128) k_first_march(GridDev g, double dt, int seg)
+{
+  const int il = NG-2, iu = g.nx[0]+NG+1;
+  const int i = il + blockIdx.x*blockDim.x + threadIdx.x;
+  if (i > iu) return;
+  constexpr int OTH = (DIR == 1) ? 2 : 1;                 // the transverse axis that is not x1
+  const int o = NG-2 + blockIdx.z;                        // range [l, u] of that axis
+  const int fl = NG-2+1, fu = g.nx[DIR]+NG+1;             // faces [l+1, u] along the sweep
+  const int fs = fl + blockIdx.y*seg;
+  int fe = fs + seg; if (fe > fu+1) fe = fu+1;
+  const long sd = g.st[DIR];
+  const long base = (long)i + (long)o*g.st[OTH];
+  const double dtodx = dt/g.dx[DIR];
+
+  S6 Wm = cons_to_prim<NS>(load_sweep<DIR,NS>(g.U, base + (long)(fs-2)*sd), g.Gamma_1);
+  S6 W0 = cons_to_prim<NS>(load_sweep<DIR,NS>(g.U, base + (long)(fs-1)*sd), g.Gamma_1);
+  S6 Wl_prev;
+  for (int c = fs-1; c < fe; c++) {
+    const long cc = base + (long)c*sd;
+    const S6 Wp = cons_to_prim<NS>(load_sweep<DIR,NS>(g.U, cc + sd), g.Gamma_1);
+    S6 Wl_next, Wr_this;
+    plm_cell<NS>(Wm, W0, Wp, dtodx, g.Gamma, Wl_next, Wr_this);
+    if (GRAV) {   // integrate_3d_ctu.c:635-645, 819-829
+      Wl_next.x -= dtodx*(g.phi[PHI_MH0+DIR][cc+sd] - g.phi[PHI_M0+DIR][cc+sd]);
+      Wr_this.x -= dtodx*(g.phi[PHI_C][cc] - g.phi[PHI_MH0+DIR][cc]);
+    }
+    if (c >= fs) {
+      const S6 Ul = prim_to_cons<NS>(Wl_prev, g.Gamma_1);
+      const S6 Ur = prim_to_cons<NS>(Wr_this, g.Gamma_1);
+      S6 F;
+      roe_flux<NS>(Ul, Ur, Wl_prev, Wr_this, 0.0, g.Gamma, g.Gamma_1, F);
+      store_sweep<DIR,NS>(g.Ul[DIR], cc, Ul);
+      store_sweep<DIR,NS>(g.Ur[DIR], cc, Ur);
+      store_sweep<DIR,NS>(g.F[DIR], cc, F);
+    }
+    Wl_prev = Wl_next; Wm = W0; W0 = Wp;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// thread -> (i,j,k) over a box [lo,hi] (inclusive); x-threads flatten (i,j), blockIdx.y is k
+// ---------------------------------------------------------------------------------------------------
+struct Box { int lo[3], hi[3]; };
+__device__ __forceinline__ bool box_cell(const Box& b, int& i, int& j, int& k)
+{
+  const int ni = b.hi[0]-b.lo[0]+1, nj = b.hi[1]-b.lo[1]+1;
+  const long t = (long)blockIdx.x*blockDim.x + threadIdx.x;
+  if (t >= (long)ni*nj) return false;
+  const int jj = (int)(t / ni);
+  i = b.lo[0] + (int)(t - (long)jj*ni);
+  j = b.lo[1] + jj;
+  k = b.lo[2] + blockIdx.y;
+  return true;
+}
+
+// Pass B: integrate_3d_ctu.c:2104-2125 (active zones are all the update needs)
+__global__ void k_dhalf(GridDev g, Box b, double dt)
+{
+  int i,j,k; if (!box_cell(b,i,j,k)) return;
+  const long c = (long)k*g.st[2] + (long)j*g.st[1] + i;
+  const double q1 = 0.5*(dt/g.dx[0]), q2 = 0.5*(dt/g.dx[1]), q3 = 0.5*(dt/g.dx[2]);
+  g.dhalf[c] = g.U[0][c]
+    - q1*(g.F[0][0][c+1]       - g.F[0][0][c])
+    - q2*(g.F[1][0][c+g.st[1]] - g.F[1][0][c])
+    - q3*(g.F[2][0][c+g.st[2]] - g.F[2][0][c]);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Pass C: correct the L/R states of DIR-faces with the transverse flux gradients (steps 5a-b/6a-b/7a-b),
+// add the static-potential source terms (5d/6d/7d), and evaluate eta (9a).  One thread per face.
+// ---------------------------------------------------------------------------------------------------
+template <int DIR, int NS, bool GRAV>
+__global__ void __launch_bounds__(128) k_correct(GridDev g, Box b, double dt)
+{
+  int i,j,k; if (!box_cell(b,i,j,k)) return;
+  const long cR = (long)k*g.st[2] + (long)j*g.st[1] + i;
+  const long cL = cR - g.st[DIR];
+  constexpr int T1 = (DIR == 0) ? 1 : 0;           // transverse directions in ascending order:
+  constexpr int T2 = (DIR == 2) ? 1 : 2;           // the order the reference applies them in
+  const double qT1 = 0.5*(dt/g.dx[T1]), qT2 = 0.5*(dt/g.dx[T2]);
+  const long s1 = g.st[T1], s2 = g.st[T2];
+
+  double UL[6], UR[6];
+#pragma unroll
+  for (int v=0; v<5+NS; v++) { UL[v] = g.Ul[DIR][v][cR]; UR[v] = g.Ur[DIR][v][cR]; }
+#pragma unroll
+  for (int v=0; v<5+NS; v++) {
+    UL[v] -= qT1*(g.F[T1][v][cL+s1] - g.F[T1][v][cL]);
+    UR[v] -= qT1*(g.F[T1][v][cR+s1] - g.F[T1][v][cR]);
+  }
+#pragma unroll
+  for (int v=0; v<5+NS; v++) {
+    UL[v] -= qT2*(g.F[T2][v][cL+s2] - g.F[T2][v][cL]);
+    UR[v] -= qT2*(g.F[T2][v][cR+s2] - g.F[T2][v][cR]);
+  }
+  if (GRAV) {
+    // right state: cell cR (integrate_3d_ctu.c:1171-1192 and cyclic)
+    double phic = g.phi[PHI_C][cR];
+    double phir = g.phi[PHI_PH0+T1][cR], phil = g.phi[PHI_MH0+T1][cR];
+    UR[1+T1] -= qT1*(phir-phil)*g.U[0][cR];
+    UR[4] -= qT1*(g.F[T1][0][cR]*(phic - phil) + g.F[T1][0][cR+s1]*(phir - phic));
+    phir = g.phi[PHI_PH0+T2][cR]; phil = g.phi[PHI_MH0+T2][cR];
+    UR[1+T2] -= qT2*(phir-phil)*g.U[0][cR];
+    UR[4] -= qT2*(g.F[T2][0][cR]*(phic - phil) + g.F[T2][0][cR+s2]*(phir - phic));
+    // left state: cell cL, potentials as seen from cell cR shifted by -dx_DIR (:1196-1215)
+    phic = g.phi[PHI_M0+DIR][cR];
+    phir = g.phi[phi_mix(DIR,T1,1)][cR]; phil = g.phi[phi_mix(DIR,T1,0)][cR];
+    UL[1+T1] -= qT1*(phir-phil)*g.U[0][cL];
+    UL[4] -= qT1*(g.F[T1][0][cL]*(phic - phil) + g.F[T1][0][cL+s1]*(phir - phic));
+    phir = g.phi[phi_mix(DIR,T2,1)][cR]; phil = g.phi[phi_mix(DIR,T2,0)][cR];
+    UL[1+T2] -= qT2*(phir-phil)*g.U[0][cL];
+    UL[4] -= qT2*(g.F[T2][0][cL]*(phic - phil) + g.F[T2][0][cL+s2]*(phir - phic));
+  }
+#pragma unroll
+  for (int v=0; v<5+NS; v++) { g.Ul[DIR][v][cR] = UL[v]; g.Ur[DIR][v][cR] = UR[v]; }
+  g.eta[DIR][cR] = eta_face(sweep_from_phys<DIR,NS>(UL), sweep_from_phys<DIR,NS>(UR), g.Gamma, g.Gamma_1);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Pass D: final fluxes with the H-correction (integrate_3d_ctu.c:2350-2437)
+// ---------------------------------------------------------------------------------------------------
+template <int DIR, int NS>
+__global__ void __launch_bounds__(128) k_final(GridDev g, Box b)
+{
+  int i,j,k; if (!box_cell(b,i,j,k)) return;
+  const long c = (long)k*g.st[2] + (long)j*g.st[1] + i;
+  constexpr int A = (DIR == 0) ? 1 : 0;
+  constexpr int B = (DIR == 2) ? 1 : 2;
+  const long sd = g.st[DIR], sa = g.st[A], sb = g.st[B];
+  double etah = AB2_MAX(g.eta[A][c-sd], g.eta[A][c]);
+  etah = AB2_MAX(etah, g.eta[A][c-sd+sa]);
+  etah = AB2_MAX(etah, g.eta[A][c+sa]);
+  etah = AB2_MAX(etah, g.eta[B][c-sd]);
+  etah = AB2_MAX(etah, g.eta[B][c]);
+  etah = AB2_MAX(etah, g.eta[B][c-sd+sb]);
+  etah = AB2_MAX(etah, g.eta[B][c+sb]);
+  etah = AB2_MAX(etah, g.eta[DIR][c]);
+  const S6 Ul = load_sweep<DIR,NS>(g.Ul[DIR], c);
+  const S6 Ur = load_sweep<DIR,NS>(g.Ur[DIR], c);
+  const S6 Wl = cons_to_prim<NS>(Ul, g.Gamma_1);
+  const S6 Wr = cons_to_prim<NS>(Ur, g.Gamma_1);
+  S6 F;
+  roe_flux<NS>(Ul, Ur, Wl, Wr, etah, g.Gamma, g.Gamma_1, F);
+  store_sweep<DIR,NS>(g.F[DIR], c, F);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Pass E: static-potential source for the full step (11a, :2741-2782) then U -= dt/dx dF in the reference's
+// three ordered passes (12a-c, :2981-3050), per active cell.
+// ---------------------------------------------------------------------------------------------------
+template <int NS, bool GRAV>
+__global__ void __launch_bounds__(128) k_update(GridDev g, Box b, double dt)
+{
+  int i,j,k; if (!box_cell(b,i,j,k)) return;
+  const long c = (long)k*g.st[2] + (long)j*g.st[1] + i;
+  const double dtodx[3] = { dt/g.dx[0], dt/g.dx[1], dt/g.dx[2] };
+  double U[6];
+#pragma unroll
+  for (int v=0; v<5+NS; v++) U[v] = g.U[v][c];
+  if (GRAV) {
+    const double phic = g.phi[PHI_C][c];
+    const double dh = g.dhalf[c];
+#pragma unroll
+    for (int d=0; d<3; d++) {
+      const double phir = g.phi[PHI_PH0+d][c], phil = g.phi[PHI_MH0+d][c];
+      U[1+d] -= dtodx[d]*(phir-phil)*dh;
+      U[4] -= dtodx[d]*(g.F[d][0][c]*(phic - phil) + g.F[d][0][c+g.st[d]]*(phir - phic));
+    }
+  }
+#pragma unroll
+  for (int d=0; d<3; d++) {
+#pragma unroll
+    for (int v=0; v<5+NS; v++) U[v] -= dtodx[d]*(g.F[d][v][c+g.st[d]] - g.F[d][v][c]);
+  }
+#pragma unroll
+  for (int v=0; v<5+NS; v++) g.U[v][c] = U[v];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// bvals_mhd: one kernel per face; threads over (ghost layer, transverse plane)
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_bvals(GridDev g, int nvar, int dir, int side, int flag, Box tr /* ranges of the two other axes in slots of their own axis */)
+{
+  // thread -> (a, b, layer) ; a = fastest transverse axis
+  const int A = (dir == 0) ? 1 : 0, B = (dir == 2) ? 1 : 2;
+  const int na = tr.hi[A]-tr.lo[A]+1, nb = tr.hi[B]-tr.lo[B]+1;
+  const long t = (long)blockIdx.x*blockDim.x + threadIdx.x;
+  if (t >= (long)na*nb*NG) return;
+  const int ia = (int)(t % na);
+  const long r = t / na;
+  const int layer = 1 + (int)(r % NG);
+  const int ib = (int)(r / NG);
+  const int s = NG, e = g.nx[dir]+NG-1;
+  int dst, src;
+  if (side == 0) {
+    dst = s - layer;
+    src = (flag == 2) ? s : (flag == 4) ? e-(layer-1) : s+(layer-1);
+  } else {
+    dst = e + layer;
+    src = (flag == 2) ? e : (flag == 4) ? s+(layer-1) : e-(layer-1);
+  }
+  const long off = (long)(tr.lo[A]+ia)*g.st[A] + (long)(tr.lo[B]+ib)*g.st[B];
+  const long cd = off + (long)dst*g.st[dir], cs = off + (long)src*g.st[dir];
+  const bool refl = (flag == 1 || flag == 5);
+  for (int v=0; v<nvar; v++) {
+    double x = g.U[v][cs];
+    if (refl && v == 1+dir) x = -x;
+    g.U[v][cd] = x;
+  }
+}
+
+int hydro_bvals(ab2_grid* h, const int bc[6])
+{
+  GridDev& g = h->g;
+  const int nvar = 5 + h->nscal;
+  for (int dir=0; dir<3; dir++) {
+    if (g.nx[dir] <= 1) continue;
+    Box tr;
+    for (int a=0; a<3; a++) { tr.lo[a] = 0; tr.hi[a] = 0; }
+    // x1: active j,k; x2: all i, active k; x3: all i,j   (bvals_mhd.c:969, 1087-1089, 1206-1208)
+    for (int a=0; a<3; a++) {
+      if (a == dir) continue;
+      if (a < dir) { tr.lo[a] = 0; tr.hi[a] = g.n[a]-1; }
+      else { tr.lo[a] = NG; tr.hi[a] = g.nx[a]+NG-1; }
+    }
+    const int A = (dir == 0) ? 1 : 0, B = (dir == 2) ? 1 : 2;
+    const long nt = (long)(tr.hi[A]-tr.lo[A]+1)*(tr.hi[B]-tr.lo[B]+1)*NG;
+    for (int side=0; side<2; side++) {
+      const int flag = bc[2*dir+side];
+      if (flag != 1 && flag != 2 && flag != 4 && flag != 5) continue;   // <=0: neighbouring Grid / prolongated face
+      k_bvals<<<(unsigned)((nt+255)/256), 256, 0, h->stream>>>(g, nvar, dir, side, flag, tr);
+      h->launches++;
+    }
+  }
+  return ab2_check(cudaGetLastError(), "bvals_mhd") ? 0 : -1;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// new_dt: max over active zones of |v_d| + sqrt(gamma P/d)  (new_dt.c:69-139)
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void atomic_max_pos(unsigned long long* p, double x)
+{ // MAX(cur, x) with the reference's ternary semantics: NaN never replaces; values are >= 0 so the bit pattern orders
+  if (x > 0.0) atomicMax(p, (unsigned long long)__double_as_longlong(x));
+}
+
+__global__ void __launch_bounds__(256) k_max_speeds(GridDev g, unsigned long long* scal)
+{
+  const long nact = (long)g.nx[0]*g.nx[1]*g.nx[2];
+  double m1 = 0.0, m2 = 0.0, m3 = 0.0;
+  for (long t = (long)blockIdx.x*blockDim.x + threadIdx.x; t < nact; t += (long)gridDim.x*blockDim.x) {
+    const int i = (int)(t % g.nx[0]);
+    const long r = t / g.nx[0];
+    const int j = (int)(r % g.nx[1]), k = (int)(r / g.nx[1]);
+    const long c = (long)(k+NG)*g.st[2] + (long)(j+NG)*g.st[1] + (i+NG);
+    const double d = g.U[0][c];
+    const double di = 1.0/d;
+    const double v1 = g.U[1][c]*di, v2 = g.U[2][c]*di, v3 = g.U[3][c]*di;
+    const double qsq = v1*v1 + v2*v2 + v3*v3;
+    const double p = AB2_MAX(g.Gamma_1*(g.U[4][c] - 0.5*d*qsq), AB2_TINY);
+    const double asq = g.Gamma*p*di;
+    const double a = sqrt(asq);
+    m1 = AB2_MAX(m1, fabs(v1)+a);
+    m2 = AB2_MAX(m2, fabs(v2)+a);
+    m3 = AB2_MAX(m3, fabs(v3)+a);
+  }
+  for (int o=16; o>0; o>>=1) {
+    double x;
+    x = __shfl_xor_sync(0xffffffffu, m1, o); m1 = AB2_MAX(m1, x);
+    x = __shfl_xor_sync(0xffffffffu, m2, o); m2 = AB2_MAX(m2, x);
+    x = __shfl_xor_sync(0xffffffffu, m3, o); m3 = AB2_MAX(m3, x);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomic_max_pos(&scal[SC_MAXV1], m1);
+    atomic_max_pos(&scal[SC_MAXV2], m2);
+    atomic_max_pos(&scal[SC_MAXV3], m3);
+  }
+}
+
+int hydro_max_speeds(ab2_grid* h, double out[3])
+{
+  GridDev& g = h->g;
+  if (!ab2_check(cudaMemsetAsync(h->d_scal + SC_MAXV1, 0, 3*sizeof(unsigned long long), h->stream), "new_dt memset")) return -1;
+  const long nact = (long)g.nx[0]*g.nx[1]*g.nx[2];
+  int blocks = (int)((nact + 255)/256); if (blocks > 148*8) blocks = 148*8;
+  k_max_speeds<<<blocks, 256, 0, h->stream>>>(g, h->d_scal);
+  h->launches++;
+  if (!ab2_check(cudaMemcpyAsync(h->h_scal + SC_MAXV1, h->d_scal + SC_MAXV1, 3*sizeof(unsigned long long),
+                                 cudaMemcpyDeviceToHost, h->stream), "new_dt D2H")) return -1;
+  if (!ab2_check(cudaStreamSynchronize(h->stream), "new_dt sync")) return -1;
+  for (int d=0; d<3; d++) {
+    long long bits = (long long)h->h_scal[SC_MAXV1+d];
+    double v; memcpy(&v, &bits, sizeof v);
+    out[d] = (g.nx[d] > 1) ? v : 0.0;
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Userwork_in_loop replay: overwrite a static list of cells with fixed values
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_apply_fixed(GridDev g, int nvar, long n, const long* cells, const double* vals)
+{
+  const long t = (long)blockIdx.x*blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const long c = cells[t];
+  for (int v=0; v<nvar; v++) g.U[v][c] = vals[(long)v*n + t];
+}
+
+int hydro_apply_fixed(ab2_grid* h)
+{
+  if (h->n_fixed <= 0) return 0;
+  k_apply_fixed<<<(unsigned)((h->n_fixed+255)/256), 256, 0, h->stream>>>(h->g, 5+h->nscal, h->n_fixed, h->d_fixed_cells, h->d_fixed_vals);
+  h->launches++;
+  return ab2_check(cudaGetLastError(), "apply_fixed") ? 0 : -1;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// integrate_3d_ctu driver
+// ---------------------------------------------------------------------------------------------------
+static inline dim3 box_grid(const Box& b, int threads)
+{
+  const long nij = (long)(b.hi[0]-b.lo[0]+1)*(b.hi[1]-b.lo[1]+1);
+  return dim3((unsigned)((nij + threads-1)/threads), (unsigned)(b.hi[2]-b.lo[2]+1), 1);
+}
+
+template <int NS, bool GRAV>
+static int integrate_impl(ab2_grid* h, double dt)
+{
+  GridDev& g = h->g;
+  cudaStream_t st = h->stream;
+  const int s[3] = {NG,NG,NG}, e[3] = {g.nx[0]+NG-1, g.nx[1]+NG-1, g.nx[2]+NG-1};
+  int l[3], u[3];
+  for (int a=0; a<3; a++) { l[a] = s[a]-2; u[a] = e[a]+2; }
+  const int seg = 32;
+
+  // Pass A
+  {
+    const int nf = g.nx[0]+4;
+    dim3 grid((nf + A1_F-1)/A1_F, u[1]-l[1]+1, u[2]-l[2]+1);
+    k_first_x1<NS,GRAV><<<grid, A1_T, 0, st>>>(g, dt);
+    const int ni = u[0]-l[0]+1;
+    dim3 g2((ni+127)/128, (g.nx[1]+4 + seg-1)/seg, u[2]-l[2]+1);
+    k_first_march<1,NS,GRAV><<<g2, 128, 0, st>>>(g, dt, seg);
+    dim3 g3((ni+127)/128, (g.nx[2]+4 + seg-1)/seg, u[1]-l[1]+1);
+    k_first_march<2,NS,GRAV><<<g3, 128, 0, st>>>(g, dt, seg);
+    h->launches += 3;
+  }
+  Box act; for (int a=0; a<3; a++) { act.lo[a] = s[a]; act.hi[a] = e[a]; }
+  // Pass B
+  if (GRAV) { k_dhalf<<<box_grid(act,128), 128, 0, st>>>(g, act, dt); h->launches++; }
+  // Pass C: faces of direction d over [l+1, u-1] transversally and [l+1, u] along d
+  for (int d=0; d<3; d++) {
+    Box b; for (int a=0; a<3; a++) { b.lo[a] = l[a]+1; b.hi[a] = (a == d) ? u[a] : u[a]-1; }
+    if (d == 0) k_correct<0,NS,GRAV><<<box_grid(b,128), 128, 0, st>>>(g, b, dt);
+    if (d == 1) k_correct<1,NS,GRAV><<<box_grid(b,128), 128, 0, st>>>(g, b, dt);
+    if (d == 2) k_correct<2,NS,GRAV><<<box_grid(b,128), 128, 0, st>>>(g, b, dt);
+    h->launches++;
+  }
+  // Pass D: faces [s, e+1] along d, active transversally (the +-1 transverse ring of the reference's loops feeds MHD only)
+  for (int d=0; d<3; d++) {
+    Box b; for (int a=0; a<3; a++) { b.lo[a] = s[a]; b.hi[a] = (a == d) ? e[a]+1 : e[a]; }
+    if (d == 0) k_final<0,NS><<<box_grid(b,128), 128, 0, st>>>(g, b);
+    if (d == 1) k_final<1,NS><<<box_grid(b,128), 128, 0, st>>>(g, b);
+    if (d == 2) k_final<2,NS><<<box_grid(b,128), 128, 0, st>>>(g, b);
+    h->launches++;
+  }
+  // Pass E
+  k_update<NS,GRAV><<<box_grid(act,128), 128, 0, st>>>(g, act, dt);
+  h->launches++;
+  return ab2_check(cudaGetLastError(), "integrate_3d_ctu") ? 0 : -1;
+}
+
+int hydro_integrate(ab2_grid* h, double dt)
+{
+  if (h->nscal) return h->has_grav ? integrate_impl<1,true>(h, dt) : integrate_impl<1,false>(h, dt);
+  return h->has_grav ? integrate_impl<0,true>(h, dt) : integrate_impl<0,false>(h, dt);
+}

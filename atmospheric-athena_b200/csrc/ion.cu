@@ -1,0 +1,407 @@
+// ion.cu -- FP64 CUDA kernels (sm_100a) for the ion-plane radiative transfer + photoionisation sub-cycle:
+//   ion_radtransfer_3d   (ionradiation/ionrad_3d.c:862-1047)
+//   get_ph_rate_plane    (ionradiation/ionradplane_3d.c:88-407, dir = -1 branch :253-322)
+//   compute_chem_rates / compute_therm_rates / ionization_update / floors / check_range / compute_dt_hydro
+//                        (ionrad_3d.c:288-409, 414-562, 565-590, 70-157, 206-283, 593-678)
+//   bvals_ionrad         (ionradiation/bvals_ionrad.c:63-146, 308-332)
+//
+// The reference makes nine full-grid sweeps per sub-cycle iteration; here an iteration is two kernels,
+// separated by the grid-wide min that chooses the sub-step:
+//   k_ion_rates  : one WARP per ray; 32 cells at a time, exp(-tau) in parallel, attenuation as a warp-level
+//                  prefix product with the reference's 1e-3 ray cut, then photo/chem/thermal rates and the
+//                  per-cell dt limits of those same cells while they are in registers.
+//   k_ion_update : E,s update, temperature and neutral floors, check_range count and the new hydro dt.
+// exp/pow come from the CUDA math library (<= 2 ulp) and the prefix product reassociates the flux
+// products, so this path agrees with the reference to ~1e-13 relative per iteration, not bit for bit.
+#include <float.h>
+#include <math.h>
+#include <string.h>
+#include "engine.cuh"
+#include "physics.cuh"
+
+#define NG AB2_NG
+#define MINFLUXFRAC 1.0e-3     // ionrad.h:26
+#define IONFRACFLOOR 1.0e-4    // ionrad.h:31
+#define CION 8.0e5             // ionrad.h:36
+#define MAXCELLCOUNT 20        // ionrad.h:38
+#define LARGE DBL_MAX          // ionrad.h:16
+#define KB 1.38e-16            // ionrad_chemistry.c:43
+#define MAXSIGNCOUNT 4         // ionrad_3d.c:286
+#define DAMPFACTOR 0.5         // ionrad_3d.c:287
+
+#define ERR_DT_CHEM_NEG 1ull
+
+__device__ __forceinline__ void atomic_min_double(unsigned long long* addr, double val)
+{ // `if (val < cur) cur = val` (NaN never wins), any sign
+  unsigned long long old = *addr, assumed;
+  do {
+    assumed = old;
+    if (!(val < __longlong_as_double((long long)assumed))) break;
+    old = atomicCAS(addr, assumed, (unsigned long long)__double_as_longlong(val));
+  } while (assumed != old);
+}
+__device__ __forceinline__ void atomic_max_double(unsigned long long* addr, double val)
+{ // MAX(cur,val) = cur > val ? cur : val  -> replace unless cur > val ... but keep cur when val is NaN
+  unsigned long long old = *addr, assumed;
+  do {
+    assumed = old;
+    if (!(val > __longlong_as_double((long long)assumed))) break;
+    old = atomicCAS(addr, assumed, (unsigned long long)__double_as_longlong(val));
+  } while (assumed != old);
+}
+
+struct CellChem { double n_H, n_Hplus, n_e, x, ke, e_thermal, T; };
+
+__device__ __forceinline__ double kinetic(double d, double M1, double M2, double M3)
+{ return 0.5 * (M1*M1 + M2*M2 + M3*M3) / d; }
+
+__device__ __forceinline__ CellChem chem_state(const IonParDev& p, double Gamma_1, double d, double M1, double M2, double M3, double E, double s)
+{ // ionrad_3d.c:82-101 == :313-330 == :438-456
+  CellChem c;
+  c.n_H = s / p.m_H;
+  c.n_Hplus = (d - s) / p.m_H;
+  c.n_e = c.n_Hplus + d * p.alpha_C / (14.0 * p.m_H);
+  c.x = c.n_e / (c.n_H + c.n_Hplus);
+  c.ke = kinetic(d,M1,M2,M3);
+  c.e_thermal = E - c.ke;
+  const double e_sp = c.e_thermal / d;
+  c.T = Gamma_1 * e_sp * (c.x*0.5*p.m_H+(1.0-c.x)*p.mu)/ p.k_B;
+  return c;
+}
+
+// apply_temp_floor (ionrad_3d.c:70-136) then apply_neutral_floor (:140-157) for one cell
+__device__ __forceinline__ void floors(const IonParDev& p, double Gamma_1, double d, double M1, double M2, double M3, double& E, double& s)
+{
+  const CellChem c = chem_state(p, Gamma_1, d, M1, M2, M3, E, s);
+  if (c.T < p.tfloor) {
+    const double e_sp = p.tfloor * p.k_B / ((c.x*0.5*p.m_H+(1.0-c.x)*p.mu) * Gamma_1);
+    E = kinetic(d,M1,M2,M3) + e_sp * d;
+  }
+  if ((c.T > p.tceil) && (p.tceil > 0)) {
+    const double e_sp = p.tceil * p.k_B / ((c.x*0.5*p.m_H+(1.0-c.x)*p.mu) * Gamma_1);
+    E = kinetic(d,M1,M2,M3) + e_sp * d;
+  }
+  double d_nlim = d*IONFRACFLOOR;
+  d_nlim = d_nlim < p.d_nlo ? d_nlim : p.d_nlo;
+  if (s < d_nlim) s = d_nlim;
+  else if (s > d) s = d;
+}
+
+// thread -> active cell
+__device__ __forceinline__ bool active_cell(const GridDev& g, long& c)
+{
+  const long nij = (long)g.nx[0]*g.nx[1];
+  const long t = (long)blockIdx.x*blockDim.x + threadIdx.x;
+  if (t >= nij) return false;
+  const int j = (int)(t / g.nx[0]);
+  const int i = (int)(t - (long)j*g.nx[0]);
+  c = (long)(blockIdx.y+NG)*g.st[2] + (long)(j+NG)*g.st[1] + (i+NG);
+  return true;
+}
+
+// ion_radtransfer_3d prologue (:896-905): floors + save_energy_and_x (:162-201)
+__global__ void __launch_bounds__(128) k_ion_prep(GridDev g, IonParDev p, IonDev ion)
+{
+  long c; if (!active_cell(g, c)) return;
+  const double d = g.U[0][c], M1 = g.U[1][c], M2 = g.U[2][c], M3 = g.U[3][c];
+  double E = g.U[4][c], s = g.U[5][c];
+  floors(p, g.Gamma_1, d, M1, M2, M3, E, s);
+  g.U[4][c] = E; g.U[5][c] = s;
+  const double e_thermal = E - kinetic(d,M1,M2,M3);
+  const double n_H = s / p.m_H;
+  const double n_Hplus = (d - s) / p.m_H;
+  const double n_e = n_Hplus + d * p.alpha_C / (14.0 * p.m_H);
+  ion.e_init[c] = E;
+  ion.e_th_init[c] = e_thermal;
+  ion.x_init[c] = n_e / (n_H + n_Hplus);
+  ion.sign_state[c] = 1;          // last_sign = 0, sign_count = 0
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k_ion_rates: ray trace (ionradplane_3d.c:254-310) + chem rates (ionrad_3d.c:307-394) + therm rates (:433-550)
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_ion_rates(GridDev g, IonParDev p, IonDev ion, double flux_in, unsigned long long* scal)
+{
+  const int lane = threadIdx.x & 31;
+  const long ray = (long)blockIdx.x*(blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long nrays = (long)g.nx[1]*g.nx[2];
+  if (ray >= nrays) return;
+  const int jj = (int)(ray % g.nx[1]), kk = (int)(ray / g.nx[1]);
+  const long row = (long)(kk+NG)*g.st[2] + (long)(jj+NG)*g.st[1] + NG;
+  double* ef = ion.edgeflux + ((long)kk*(g.nx[1]+1) + jj)*(g.nx[0]+1);
+  const double dx1 = g.dx[0];
+  const int nx1 = g.nx[0];
+
+  double carry = flux_in;         // flux entering the current chunk
+  bool alive = true;              // false once the ray has been cut
+  double dt_chem_min = LARGE, dt_therm_min = LARGE;
+  unsigned long long err = 0;
+
+  for (int c0 = 0; c0 < nx1; c0 += 32) {
+    const int ii = c0 + lane;
+    const bool valid = ii < nx1;
+    const long c = row + (valid ? ii : nx1-1);
+    const double d = g.U[0][c], M1 = g.U[1][c], M2 = g.U[2][c], M3 = g.U[3][c], E = g.U[4][c], s = g.U[5][c];
+
+    // --- ray: tau, attenuation, photoionisation rate
+    const double n_H = s / p.m_H;
+    const double tau = p.sigma_ph * n_H * dx1;
+    const double etau = valid ? exp(-tau) : 1.0;
+    double incl = etau;
+#pragma unroll
+    for (int o=1; o<32; o<<=1) {
+      const double y = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl *= y;
+    }
+    double excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) excl = 1.0;
+    const double flux_before = carry*excl;
+    const double flux_after = flux_before*etau;
+    const double flux_frac = flux_after / (flux_in + 1e-12);
+    const unsigned cutmask = __ballot_sync(0xffffffffu, valid && (flux_frac < MINFLUXFRAC));
+    const int first = cutmask ? (__ffs(cutmask) - 1) : 32;
+    const bool lit = alive && (lane <= first);
+    double ph = 0.0;
+    if (lit) ph = flux_before * (1.0-etau) / (n_H*dx1);
+    if (valid) {
+      ef[ii] = lit ? flux_before : 0.0;
+      ion.ph_rate[c] = ph;
+    }
+    carry = __shfl_sync(0xffffffffu, flux_after, 31);
+    if (first < 32) alive = false;
+
+    if (valid) {
+      // --- chemistry (ionrad_3d.c:313-391)
+      const CellChem cs = chem_state(p, g.Gamma_1, d, M1, M2, M3, E, s);
+      double T = cs.T;
+      if (T < p.tfloor) T = p.tfloor;
+      double nHdot = 2.59e-13*pow(T/1.0e4, -0.7) * p.time_unit * cs.n_e * cs.n_Hplus - ph * cs.n_H;
+      int st = ion.sign_state[c];
+      int last_sign = (st & 3) - 1, sign_count = st >> 2;
+      if (nHdot < 0.0) {
+        if (last_sign == 1) sign_count++;
+        else if (sign_count > 0) sign_count--;
+        last_sign = -1;
+      } else if (nHdot > 0.0) {
+        if (last_sign == -1) sign_count++;
+        else if (sign_count > 0) sign_count--;
+        last_sign = 1;
+      } else {
+        sign_count = last_sign = 0;
+      }
+      ion.sign_state[c] = (sign_count << 2) | (last_sign + 1);
+      for (int n=MAXSIGNCOUNT; n<sign_count; n++) nHdot *= DAMPFACTOR;
+      ion.nHdot[c] = nHdot;
+
+      double d_nlim = d*IONFRACFLOOR;
+      d_nlim = d_nlim < p.d_nlo ? d_nlim : p.d_nlo;
+      double dt1, dt2;
+      if (nHdot == 0.0) {
+        dt1 = dt2 = LARGE;
+      } else if (nHdot > 0.0) {
+        dt1 = p.max_dx_iter / (1+p.max_dx_iter) * cs.n_e / nHdot;
+        dt2 = p.max_dx_iter * cs.n_H / nHdot;
+      } else if (s > 1.0001*d_nlim) {
+        dt1 = -p.max_dx_iter * cs.n_e / nHdot;
+        dt2 = -p.max_dx_iter / (1+p.max_dx_iter) * cs.n_H / nHdot;
+      } else {
+        dt1 = dt2 = LARGE;
+      }
+      const double dt_chem = (dt1 < dt2) ? dt1 : dt2;
+      if (dt_chem < dt_chem_min) dt_chem_min = dt_chem;
+      if (dt_chem < 0) err |= ERR_DT_CHEM_NEG;
+
+      // --- thermal (ionrad_3d.c:438-547), unfloored T
+      double edot;
+      bool constrain = true;
+      if (cs.T < p.tfloor) { edot = 0.0; constrain = false; }
+      else if ((nHdot < 0) && (s < 1.0001*d_nlim)) { edot = 0.0; constrain = false; }
+      else {
+        const double rc = (cs.T < 100.0) ? 0.0 : 6.11e-10*pow(cs.T,-0.89)*KB*cs.T;
+        const double lya = -7.5e-19*cs.n_e*cs.n_H*exp(-118348/cs.T);
+        edot = ph * p.e_gamma * cs.n_H
+          - rc * p.time_unit * cs.n_Hplus * cs.n_e
+          + lya * p.time_unit;
+        if (edot == 0.0) {
+          dt1 = dt2 = LARGE;
+        } else if (edot > 0.0) {
+          dt1 = p.max_de_iter * E / edot;
+          dt2 = p.max_de_therm_iter * cs.e_thermal / edot;
+        } else {
+          const double e_sp_min = p.tfloor * p.k_B / ((cs.x*0.5*p.m_H+(1.0-cs.x)*p.mu) * g.Gamma_1);
+          const double e_th_min = e_sp_min * d;
+          const double e_min = kinetic(d,M1,M2,M3) + e_th_min;
+          if ((cs.e_thermal/(1.0+p.max_de_therm_iter) < e_th_min) && (E/(1.0+p.max_de_iter) < e_min)) constrain = false;
+          else {
+            dt1 = -p.max_de_iter / (1+p.max_de_iter) * E / edot;
+            dt2 = -p.max_de_therm_iter / (1+p.max_de_therm_iter) * cs.e_thermal / edot;
+          }
+        }
+      }
+      ion.edot[c] = edot;
+      if (constrain) {
+        const double dt_therm = (dt1 < dt2) ? dt1 : dt2;
+        if (dt_therm < dt_therm_min) dt_therm_min = dt_therm;
+      }
+    }
+  }
+  if (lane == 0) ef[nx1] = alive ? carry : 0.0;      // ionradplane_3d.c:308
+
+  for (int o=16; o>0; o>>=1) {
+    double y = __shfl_xor_sync(0xffffffffu, dt_chem_min, o); if (y < dt_chem_min) dt_chem_min = y;
+    y = __shfl_xor_sync(0xffffffffu, dt_therm_min, o); if (y < dt_therm_min) dt_therm_min = y;
+    err |= __shfl_xor_sync(0xffffffffu, err, o);
+  }
+  if (lane == 0) {
+    atomic_min_double(&scal[SC_DT_CHEM], dt_chem_min);
+    atomic_min_double(&scal[SC_DT_THERM], dt_therm_min);
+    if (err) atomicOr(&scal[SC_ERR], err);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k_ion_update: ionization_update (:565-590) + floors (:970-971) + check_range (:206-283) + compute_dt_hydro (:593-678)
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_ion_update(GridDev g, IonParDev p, IonDev ion, double dt, unsigned long long* scal)
+{
+  long c;
+  const bool act = active_cell(g, c);
+  unsigned long long count = 0;
+  double max_dti = 0.0;
+  if (act) {
+    const double d = g.U[0][c], M1 = g.U[1][c], M2 = g.U[2][c], M3 = g.U[3][c];
+    double E = g.U[4][c], s = g.U[5][c];
+    const double nHdot = ion.nHdot[c];
+    double d_nlim = d*IONFRACFLOOR;
+    d_nlim = d_nlim < p.d_nlo ? d_nlim : p.d_nlo;
+    if ((nHdot > 0) || (s > 1.0001*d_nlim)) {
+      E += ion.edot[c] * dt;
+      s += nHdot * dt * p.m_H;
+    }
+    floors(p, g.Gamma_1, d, M1, M2, M3, E, s);
+    g.U[4][c] = E; g.U[5][c] = s;
+
+    // check_range
+    const double n_H = s / p.m_H;
+    if (!(ion.ph_rate[c] / (p.min_area * n_H) > 2.0*CION)) {
+      const double e_thermal = E - kinetic(d,M1,M2,M3);
+      const double eth0 = ion.e_th_init[c], e0 = ion.e_init[c], x0 = ion.x_init[c];
+      if ((e_thermal / eth0 >= 1 + p.max_de_therm_step) || (eth0 / e_thermal >= 1 + p.max_de_therm_step)) count = 1;
+      else if ((p.max_de_step > 0) && ((E / e0 >= 1 + p.max_de_step) || (e0 / E >= 1 + p.max_de_step))) count = 1;
+      else if (p.max_dx_step > 0) {
+        const double n_Hplus = (d - s) / p.m_H;
+        const double n_e = n_Hplus + d * p.alpha_C / (14.0 * p.m_H);
+        const double x = n_e / (n_H + n_Hplus);
+        if ((x / x0 >= 1 + p.max_dx_step) || (x0 / x >= 1 + p.max_dx_step)) count = 1;
+      }
+    }
+    // compute_dt_hydro
+    const double di = 1.0/d;
+    const double v1 = M1*di, v2 = M2*di, v3 = M3*di;
+    const double qsq = v1*v1 + v2*v2 + v3*v3;
+    const double pr = AB2_MAX(g.Gamma_1*(E - 0.5*d*qsq), AB2_TINY);
+    const double asq = g.Gamma*pr*di;
+    const double a = sqrt(asq);
+    if (g.nx[0] > 1) max_dti = AB2_MAX(max_dti,(fabs(v1)+a)/g.dx[0]);
+    if (g.nx[1] > 1) max_dti = AB2_MAX(max_dti,(fabs(v2)+a)/g.dx[1]);
+    if (g.nx[2] > 1) max_dti = AB2_MAX(max_dti,(fabs(v3)+a)/g.dx[2]);
+  }
+  for (int o=16; o>0; o>>=1) {
+    count += __shfl_xor_sync(0xffffffffu, count, o);
+    const double y = __shfl_xor_sync(0xffffffffu, max_dti, o);
+    max_dti = AB2_MAX(max_dti, y);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (count) atomicAdd(&scal[SC_COUNT], count);
+    atomic_max_double(&scal[SC_MAX_DTI], max_dti);
+  }
+}
+
+__global__ void k_bvals_ionrad(IonDev ion, int nx1, int nx2, int nx3, double flux_i)
+{ // bvals_ionrad.c:308-332 outflow_flux_ix1
+  const long t = (long)blockIdx.x*blockDim.x + threadIdx.x;
+  if (t >= (long)(nx2+1)*(nx3+1)) return;
+  ion.edgeflux[t*(nx1+1)] = flux_i;
+}
+
+int ion_bvals_ionrad(ab2_grid* h, double flux_i)
+{
+  const GridDev& g = h->g;
+  const long n = (long)(g.nx[1]+1)*(g.nx[2]+1);
+  k_bvals_ionrad<<<(unsigned)((n+255)/256), 256, 0, h->stream>>>(h->ion, g.nx[0], g.nx[1], g.nx[2], flux_i);
+  h->launches++;
+  return ab2_check(cudaGetLastError(), "bvals_ionrad") ? 0 : -1;
+}
+
+static inline double bits_to_double(unsigned long long b) { double v; memcpy(&v, &b, sizeof v); return v; }
+static inline unsigned long long double_to_bits(double v) { unsigned long long b; memcpy(&b, &v, sizeof b); return b; }
+
+// ion_radtransfer_3d for a root-level Grid (ionrad_3d.c:862-1047).  flux_in = flux entering at the upstream
+// face (the caller evaluates the reference's time ramp, ionradplane_3d.c:265).  reduce(vals,n,op,ctx) combines
+// sub-cycle scalars across the Grids of a Domain (op 0 MIN, 1 MAX, 2 SUM): the MPI_Allreduce sites of
+// ionrad_3d.c:275,399,554,672; NULL for a single Grid.
+int ion_radtransfer(ab2_grid* h, double flux_in, double cour_no, double* dt_io, int* niter_out, int* nchem_out, int* ntherm_out,
+                    ab2_reduce_fn_t reduce, void* ctx)
+{
+  GridDev& g = h->g;
+  cudaStream_t st = h->stream;
+  const IonParDev& p = h->ionpar;
+  const long nij = (long)g.nx[0]*g.nx[1];
+  const dim3 cgrid((unsigned)((nij+127)/128), (unsigned)g.nx[2], 1);
+  const long nrays = (long)g.nx[1]*g.nx[2];
+  const unsigned rgrid = (unsigned)((nrays + 3)/4);
+
+  k_ion_prep<<<cgrid, 128, 0, st>>>(g, p, h->ion);
+  h->launches++;
+
+  double grid_dt = *dt_io, dt_done = 0.0, dt = 0.0, dt_chem = 0.0, dt_therm = 0.0, dt_hydro = 0.0;
+  int niter = 0, hydro_done = 0, nchem = 0, ntherm = 0;
+  while (!hydro_done) {
+    // rates + per-cell limits
+    h->h_scal[SC_DT_CHEM] = double_to_bits(LARGE); h->h_scal[SC_DT_THERM] = double_to_bits(LARGE);
+    h->h_scal[SC_MAX_DTI] = double_to_bits(0.0); h->h_scal[SC_COUNT] = 0;
+    if (!ab2_check(cudaMemcpyAsync(h->d_scal + SC_DT_CHEM, h->h_scal + SC_DT_CHEM, 4*sizeof(unsigned long long),
+                                   cudaMemcpyHostToDevice, st), "ion scalars H2D")) return -1;
+    k_ion_rates<<<rgrid, 128, 0, st>>>(g, p, h->ion, flux_in, h->d_scal);
+    h->launches++;
+    if (!ab2_check(cudaMemcpyAsync(h->h_scal + SC_DT_CHEM, h->d_scal + SC_DT_CHEM, 2*sizeof(unsigned long long),
+                                   cudaMemcpyDeviceToHost, st), "ion scalars D2H")) return -1;
+    if (!ab2_check(cudaMemcpyAsync(h->h_scal + SC_ERR, h->d_scal + SC_ERR, sizeof(unsigned long long),
+                                   cudaMemcpyDeviceToHost, st), "ion err D2H")) return -1;
+    if (!ab2_check(cudaStreamSynchronize(st), "ion rates sync")) return -1;
+    if (h->h_scal[SC_ERR] & ERR_DT_CHEM_NEG) { ab2_set_error("[compute_chem_rates]: dt_chem < 0"); return -2; }
+    double v[2] = { bits_to_double(h->h_scal[SC_DT_CHEM]), bits_to_double(h->h_scal[SC_DT_THERM]) };
+    if (reduce) reduce(v, 2, 0, ctx);
+    dt_chem = v[0]; dt_therm = v[1];
+
+    if (dt_chem < dt_therm) nchem++; else ntherm++;          // ionrad_3d.c:943-945
+    dt = AB2_MIN(dt_therm, dt_chem);
+    if (dt_done + dt > grid_dt) { dt = grid_dt - dt_done; hydro_done = 1; }
+
+    k_ion_update<<<cgrid, 128, 0, st>>>(g, p, h->ion, dt, h->d_scal);
+    h->launches++;
+    dt_done += dt;
+    niter++;
+    if (!ab2_check(cudaMemcpyAsync(h->h_scal + SC_MAX_DTI, h->d_scal + SC_MAX_DTI, 2*sizeof(unsigned long long),
+                                   cudaMemcpyDeviceToHost, st), "ion scalars D2H")) return -1;
+    if (!ab2_check(cudaStreamSynchronize(st), "ion update sync")) return -1;
+    double cnt = (double)h->h_scal[SC_COUNT];
+    double mx = bits_to_double(h->h_scal[SC_MAX_DTI]);
+    if (reduce) { reduce(&cnt, 1, 2, ctx); reduce(&mx, 1, 1, ctx); }
+
+    if (cnt > MAXCELLCOUNT) { grid_dt = dt_done; break; }      // check_range (:982)
+    if (hydro_done) break;                                     // :989
+    dt_hydro = cour_no/mx;                                     // :997
+    if (dt_hydro < dt_done) { grid_dt = dt_done; break; }
+  }
+  if (niter == h->maxiter) grid_dt = dt_done;                  // :1022
+  *dt_io = grid_dt;
+  if (niter_out) *niter_out = niter;
+  if (nchem_out) *nchem_out = nchem;
+  if (ntherm_out) *ntherm_out = ntherm;
+  if (grid_dt < 0) {                                           // :1044-1046
+    ab2_set_error("[ion_radtransfer_3d]: dt < 0");
+    return -3;
+  }
+  return 0;
+}

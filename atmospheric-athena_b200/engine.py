@@ -1,0 +1,282 @@
+"""ctypes binding of csrc/libathena_b200.so (include/athena_b200.h) -- the only way Python reaches the GPU here.
+
+There is no fallback: if the shared library is missing or no CUDA device is visible, construction raises.
+PyTorch is used for plumbing only (device memory that NCCL can address, streams): no torch op touches the state.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libathena_b200.so")
+NG = 4
+VARS = ("d", "M1", "M2", "M3", "E", "s")
+dp = C.POINTER(C.c_double)
+
+GRAV_FN = C.CFUNCTYPE(C.c_double, C.c_double, C.c_double, C.c_double)
+REDUCE_FN = C.CFUNCTYPE(None, dp, C.c_int, C.c_int, C.c_void_p)
+
+
+class EngineError(RuntimeError):
+    """What the C shim would hand to ath_error() (utils.c:118)."""
+
+
+class GridDesc(C.Structure):
+    _fields_ = [("nx1", C.c_int), ("nx2", C.c_int), ("nx3", C.c_int), ("nscal", C.c_int),
+                ("dx1", C.c_double), ("dx2", C.c_double), ("dx3", C.c_double),
+                ("x1min", C.c_double), ("x2min", C.c_double), ("x3min", C.c_double),
+                ("gamma", C.c_double), ("device", C.c_int), ("stream", C.c_void_p),
+                ("external_U", C.c_void_p * 6)]
+
+
+class IonPar(C.Structure):
+    _fields_ = [(n, C.c_double) for n in
+                ("sigma_ph", "m_H", "mu", "e_gamma", "alpha_C", "k_B", "time_unit", "max_de_iter",
+                 "max_de_therm_iter", "max_dx_iter", "max_de_step", "max_de_therm_step", "max_dx_step",
+                 "tfloor", "tceil")] + [("maxiter", C.c_int), ("min_area", C.c_double), ("d_nlo", C.c_double)]
+
+
+EXPORTS = ["ab2_last_error", "ab2_version", "ab2_device_count", "ab2_grid_create", "ab2_grid_destroy",
+           "ab2_bytes_allocated", "ab2_kernel_launches", "ab2_synchronize", "ab2_upload_cons_aos",
+           "ab2_download_cons_aos", "ab2_upload_cons_soa", "ab2_download_cons_soa", "ab2_upload_edgeflux",
+           "ab2_download_edgeflux", "ab2_device_ptr", "ab2_bvals_mhd", "ab2_max_wave_speeds", "ab2_new_dt",
+           "ab2_set_static_grav_pot", "ab2_integrate_3d_ctu", "ab2_set_fixed_cells", "ab2_apply_fixed_cells",
+           "ab2_ion_init", "ab2_ion_derived", "ab2_bvals_ionrad", "ab2_ion_entering_flux", "ab2_ion_radtransfer_3d",
+           "ab2_unit_roe_flux", "ab2_unit_convert", "ab2_unit_lr_states"]
+
+
+def build(verbose=False):
+    """Compile csrc/*.cu for sm_100a into csrc/libathena_b200.so (nvcc cross-compiles without a GPU)."""
+    r = subprocess.run(["bash", os.path.join(_HERE, "csrc", "build.sh")], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise EngineError("nvcc build failed:\n" + r.stdout + r.stderr)
+    if verbose:
+        print(r.stdout + r.stderr)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EngineError(f"{LIB_PATH} is missing: run __graft_entry__.build() (there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    L.ab2_last_error.restype = C.c_char_p
+    L.ab2_version.restype = C.c_char_p
+    L.ab2_grid_create.argtypes = [C.POINTER(GridDesc)]
+    L.ab2_grid_create.restype = vp
+    L.ab2_grid_destroy.argtypes = [vp]
+    L.ab2_grid_destroy.restype = None
+    L.ab2_bytes_allocated.argtypes = [vp]
+    L.ab2_bytes_allocated.restype = C.c_longlong
+    L.ab2_kernel_launches.argtypes = [vp]
+    L.ab2_kernel_launches.restype = C.c_longlong
+    L.ab2_synchronize.argtypes = [vp]
+    L.ab2_upload_cons_aos.argtypes = [vp, dp]
+    L.ab2_download_cons_aos.argtypes = [vp, dp]
+    L.ab2_upload_cons_soa.argtypes = [vp, C.POINTER(dp)]
+    L.ab2_download_cons_soa.argtypes = [vp, C.POINTER(dp)]
+    L.ab2_upload_edgeflux.argtypes = [vp, dp]
+    L.ab2_download_edgeflux.argtypes = [vp, dp]
+    L.ab2_device_ptr.argtypes = [vp, C.c_int]
+    L.ab2_device_ptr.restype = vp
+    L.ab2_bvals_mhd.argtypes = [vp, C.POINTER(C.c_int)]
+    L.ab2_max_wave_speeds.argtypes = [vp, dp]
+    L.ab2_new_dt.argtypes = [vp, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double, vp, vp, dp]
+    L.ab2_set_static_grav_pot.argtypes = [vp, vp]
+    L.ab2_integrate_3d_ctu.argtypes = [vp, C.c_double]
+    L.ab2_set_fixed_cells.argtypes = [vp, C.c_long, C.POINTER(C.c_long), dp]
+    L.ab2_apply_fixed_cells.argtypes = [vp]
+    L.ab2_ion_init.argtypes = [vp, C.POINTER(IonPar)]
+    L.ab2_ion_derived.argtypes = [C.POINTER(IonPar), C.c_double, C.c_double, C.c_double]
+    L.ab2_ion_derived.restype = None
+    L.ab2_bvals_ionrad.argtypes = [vp, C.c_double]
+    L.ab2_ion_entering_flux.argtypes = [C.c_double, C.c_double]
+    L.ab2_ion_entering_flux.restype = C.c_double
+    L.ab2_ion_radtransfer_3d.argtypes = [vp, C.c_double, C.c_double, C.c_double, dp,
+                                         C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), vp, vp]
+    L.ab2_unit_roe_flux.argtypes = [C.c_int, dp, dp, dp, dp, C.c_int, C.c_double, dp, dp]
+    L.ab2_unit_convert.argtypes = [C.c_int, dp, C.c_int, C.c_double, C.c_int, dp, dp]
+    L.ab2_unit_lr_states.argtypes = [C.c_int, C.c_int, dp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, dp, dp]
+    _lib = L
+    return L
+
+
+def ion_par_from(par, root_dx) -> IonPar:
+    """ion_radtransfer_init_3d's par_getd calls (ionrad_3d.c:742-757) + ionrad.c:115-131."""
+    p = IonPar()
+    for n, _ in IonPar._fields_[:15]:
+        setattr(p, n, par.par_getd("ionradiation", n))
+    p.maxiter = int(par.par_getd("ionradiation", "maxiter"))
+    lib().ab2_ion_derived(C.byref(p), *root_dx)
+    return p
+
+
+class Grid:
+    """One reference GridS mirrored on one GPU."""
+
+    def __init__(self, nx, dx, xmin, gamma, nscal, device=0, torch_memory=False):
+        L = lib()
+        self.nx = tuple(int(n) for n in nx)
+        self.dx = tuple(float(x) for x in dx)
+        self.xmin = tuple(float(x) for x in xmin)
+        self.nscal = int(nscal)
+        self.nvar = 5 + self.nscal
+        self.shape = (self.nx[2] + 2 * NG, self.nx[1] + 2 * NG, self.nx[0] + 2 * NG)
+        self.device = device
+        desc = GridDesc(self.nx[0], self.nx[1], self.nx[2], self.nscal, *self.dx, *self.xmin, float(gamma), device, None)
+        self.U_torch = None
+        if torch_memory:
+            import torch
+            torch.cuda.set_device(device)
+            self.U_torch = torch.zeros((self.nvar,) + self.shape, dtype=torch.float64, device=f"cuda:{device}")
+            desc.stream = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+            for v in range(self.nvar):
+                desc.external_U[v] = self.U_torch[v].data_ptr()
+            torch.cuda.synchronize(device)
+        self.h = L.ab2_grid_create(C.byref(desc))
+        if not self.h:
+            raise EngineError(L.ab2_last_error().decode())
+        self._keep = []          # callbacks that must outlive the handle
+
+    # -- helpers ---------------------------------------------------------------------------------
+    def _ck(self, rc):
+        if rc != 0:
+            raise EngineError(lib().ab2_last_error().decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().ab2_grid_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def bytes_allocated(self):
+        return lib().ab2_bytes_allocated(self.h)
+
+    @property
+    def kernel_launches(self):
+        return lib().ab2_kernel_launches(self.h)
+
+    def synchronize(self):
+        self._ck(lib().ab2_synchronize(self.h))
+
+    # -- coherence -------------------------------------------------------------------------------
+    def upload(self, U: dict):
+        """U: dict var -> float64 array [n3][n2][n1] incl. ghosts (SoA)."""
+        arrs = [np.ascontiguousarray(U[v], dtype=np.float64) for v in VARS[:self.nvar]]
+        for a in arrs:
+            assert a.shape == self.shape, (a.shape, self.shape)
+        ptrs = (dp * 6)(*[a.ctypes.data_as(dp) for a in arrs])
+        self._ck(lib().ab2_upload_cons_soa(self.h, ptrs))
+
+    def download(self) -> dict:
+        out = {v: np.empty(self.shape) for v in VARS[:self.nvar]}
+        ptrs = (dp * 6)(*[out[v].ctypes.data_as(dp) for v in VARS[:self.nvar]])
+        self._ck(lib().ab2_download_cons_soa(self.h, ptrs))
+        return out
+
+    def upload_aos(self, U_aos: np.ndarray):
+        a = np.ascontiguousarray(U_aos, dtype=np.float64)
+        assert a.shape == self.shape + (self.nvar,)
+        self._ck(lib().ab2_upload_cons_aos(self.h, a.ctypes.data_as(dp)))
+
+    def download_aos(self) -> np.ndarray:
+        a = np.empty(self.shape + (self.nvar,))
+        self._ck(lib().ab2_download_cons_aos(self.h, a.ctypes.data_as(dp)))
+        return a
+
+    def upload_active(self, U: dict):
+        full = {v: np.zeros(self.shape) for v in VARS[:self.nvar]}
+        for v in full:
+            full[v][NG:-NG, NG:-NG, NG:-NG] = U[v]
+        self.upload(full)
+
+    def download_active(self) -> dict:
+        return {v: a[NG:-NG, NG:-NG, NG:-NG].copy() for v, a in self.download().items()}
+
+    def download_edgeflux(self) -> np.ndarray:
+        ef = np.empty((self.nx[2] + 1, self.nx[1] + 1, self.nx[0] + 1))
+        self._ck(lib().ab2_download_edgeflux(self.h, ef.ctypes.data_as(dp)))
+        return ef
+
+    def upload_edgeflux(self, ef):
+        a = np.ascontiguousarray(ef, dtype=np.float64)
+        self._ck(lib().ab2_upload_edgeflux(self.h, a.ctypes.data_as(dp)))
+
+    # -- hot path --------------------------------------------------------------------------------
+    def bvals_mhd(self, bc):
+        self._ck(lib().ab2_bvals_mhd(self.h, (C.c_int * 6)(*bc)))
+
+    def max_wave_speeds(self):
+        out = (C.c_double * 3)()
+        self._ck(lib().ab2_max_wave_speeds(self.h, out))
+        return tuple(out)
+
+    def new_dt(self, cour_no, dt_old, nstep, time, tlim, reduce=None):
+        dt = C.c_double(0.0)
+        cb = self._reduce_cb(reduce)
+        self._ck(lib().ab2_new_dt(self.h, cour_no, dt_old, nstep, time, tlim, cb, None, C.byref(dt)))
+        return dt.value
+
+    def set_static_grav_pot(self, fn):
+        """fn: a C function pointer double(double,double,double) (ctypes function or CFUNCTYPE instance), or None."""
+        if fn is None:
+            self._ck(lib().ab2_set_static_grav_pot(self.h, None))
+            return
+        self._keep.append(fn)
+        self._ck(lib().ab2_set_static_grav_pot(self.h, C.cast(fn, C.c_void_p)))
+
+    def integrate_3d_ctu(self, dt):
+        self._ck(lib().ab2_integrate_3d_ctu(self.h, dt))
+
+    def set_fixed_cells(self, cells, vals):
+        cells = np.ascontiguousarray(cells, dtype=np.int64)
+        vals = np.ascontiguousarray(vals, dtype=np.float64)
+        assert vals.shape == (6, len(cells))
+        self._ck(lib().ab2_set_fixed_cells(self.h, len(cells), cells.ctypes.data_as(C.POINTER(C.c_long)), vals.ctypes.data_as(dp)))
+
+    def apply_fixed_cells(self):
+        self._ck(lib().ab2_apply_fixed_cells(self.h))
+
+    def ion_init(self, ionpar: IonPar):
+        self._ck(lib().ab2_ion_init(self.h, C.byref(ionpar)))
+
+    def bvals_ionrad(self, flux_i):
+        self._ck(lib().ab2_bvals_ionrad(self.h, flux_i))
+
+    def ion_radtransfer_3d(self, flux_i, time, cour_no, dt, reduce=None):
+        """Returns (new dt, niter, ntherm, nchem) -- the numbers of the reference's stderr line (ionrad_3d.c:1041)."""
+        dtc = C.c_double(dt)
+        ni, nc, nt = C.c_int(0), C.c_int(0), C.c_int(0)
+        cb = self._reduce_cb(reduce)
+        self._ck(lib().ab2_ion_radtransfer_3d(self.h, flux_i, time, cour_no, C.byref(dtc), C.byref(ni), C.byref(nc), C.byref(nt), cb, None))
+        return dtc.value, ni.value, nt.value, nc.value
+
+    def _reduce_cb(self, reduce):
+        if reduce is None:
+            return None
+        if getattr(self, "_reduce_src", None) is reduce:
+            return self._reduce_ptr
+
+        def _cb(vals, n, op, ctx):
+            arr = np.ctypeslib.as_array(vals, shape=(n,))
+            arr[:] = reduce(arr.copy(), op)
+        cb = REDUCE_FN(_cb)
+        self._keep.append(cb)
+        self._reduce_src, self._reduce_ptr = reduce, C.cast(cb, C.c_void_p)
+        return self._reduce_ptr

@@ -1,0 +1,132 @@
+/* athena_b200.h -- C ABI of libathena_b200.so: the B200-native engine for Atmospheric Athena's
+ * per-timestep hot path (3D CTU hydro + ion-plane radiative transfer), FP64 CUDA for sm_100a.
+ *
+ * The reference has no plugin ABI: its "operator API" is link-time symbol substitution of
+ *   new_dt(), bvals_mhd(), integrate_init()->integrate_3d_ctu(), ion_radtransfer_init()->ion_radtransfer_3d(),
+ *   bvals_ionrad(), RestrictCorrect()/Prolongate()   (src/prototypes.h:75-77,147,224-228)
+ * all taking MeshS* / DomainS*.  Those structs belong to the reference's headers, so this library takes
+ * plain pointers and sizes instead; `atmospheric-athena_b200/shim/athena_shim.c` is the ~200-line C file a
+ * maintainer compiles against the reference's own athena.h to bind the reference symbols to these entry
+ * points (INTEGRATION.md shows the link line).  Every entry point below names the reference function it
+ * replaces (paths relative to /root/reference/src).
+ *
+ * Conventions
+ *  - One ab2_grid per reference GridS, owned by the caller through an opaque handle; one CUDA device and
+ *    one stream per handle.  Not thread-safe per handle (neither is the reference, SURVEY 8b "Threading").
+ *  - Arrays with ghosts have extents [Nx3+8][Nx2+8][Nx1+8], x1 fastest, exactly GridS.U (athena.h:289-348,
+ *    ath_array.c:78-120).  "aos" = the reference's ConsS layout, nvar = 5+nscal doubles per cell
+ *    (d,M1,M2,M3,E[,s0]); "soa" = one array per variable (the device layout).
+ *  - Every function returns 0 on success and a negative code on failure; ab2_last_error() then holds the
+ *    message the shim passes to ath_error() (utils.c:118).  There is NO CPU fallback: without a CUDA device
+ *    ab2_grid_create fails.
+ */
+#ifndef ATHENA_B200_H
+#define ATHENA_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AB2_NGHOST 4
+
+typedef struct ab2_grid ab2_grid;
+
+typedef struct ab2_grid_desc {
+  int nx1, nx2, nx3;              /* GridS.Nx[0..2]: active zones on this Grid                              */
+  int nscal;                      /* NSCALARS: 0 (hydro only) or 1 (ion builds, s[0] = neutral density)      */
+  double dx1, dx2, dx3;           /* GridS.dx1..3                                                            */
+  double x1min, x2min, x3min;     /* GridS.MinX[0..2] (cc_pos.c)                                             */
+  double gamma;                   /* globals.h: Gamma                                                        */
+  int device;                     /* CUDA device ordinal                                                     */
+  void* stream;                   /* cudaStream_t to run on, or NULL: the library creates its own            */
+  double* external_U[6];          /* optional caller-owned DEVICE arrays for d,M1,M2,M3,E,s (all or none):    */
+                                  /* lets a host framework (torch / NCCL) exchange ghost slabs in place        */
+} ab2_grid_desc;
+
+/* <ionradiation> block as read by ion_radtransfer_init_3d (ionradiation/ionrad_3d.c:742-757), plus the two
+ * values ion_radtransfer_init derives from the ROOT mesh spacing (ionradiation/ionrad.c:115-131). */
+typedef struct ab2_ion_par {
+  double sigma_ph, m_H, mu, e_gamma, alpha_C, k_B, time_unit;
+  double max_de_iter, max_de_therm_iter, max_dx_iter;
+  double max_de_step, max_de_therm_step, max_dx_step;
+  double tfloor, tceil;
+  int maxiter;
+  double min_area, d_nlo;
+} ab2_ion_par;
+
+/* StaticGravPot: athena.h:503 GravPotFun_t, globals.h:24 */
+typedef double (*ab2_grav_pot_fn)(double x1, double x2, double x3);
+/* Combines sub-cycle scalars over the Grids of one Domain; op: 0 MIN, 1 MAX, 2 SUM.  Stands where the reference
+ * calls MPI_Allreduce (new_dt.c:175-179; ionrad_3d.c:275,399,554,672). */
+typedef void (*ab2_reduce_fn)(double* vals, int n, int op, void* ctx);
+
+/* ---- lifetime ------------------------------------------------------------------------------------ */
+const char* ab2_last_error(void);
+const char* ab2_version(void);
+int  ab2_device_count(void);
+/* integrate_init / integrate_init_3d (integrators/integrate.c:24-88, integrate_3d_ctu.c:3374-3492): allocates
+ * the device mirror of U and all CTU scratch. */
+ab2_grid* ab2_grid_create(const ab2_grid_desc* desc);
+/* integrate_destruct (integrate_3d_ctu.c:3498-3550) */
+void ab2_grid_destroy(ab2_grid* g);
+long long ab2_bytes_allocated(const ab2_grid* g);
+long long ab2_kernel_launches(const ab2_grid* g);
+int  ab2_synchronize(ab2_grid* g);
+
+/* ---- coherence points: host U <-> device mirror ---------------------------------------- */
+int ab2_upload_cons_aos(ab2_grid* g, const double* U_aos);      /* after problem() / restart_grids()          */
+int ab2_download_cons_aos(ab2_grid* g, double* U_aos);          /* before a dump fires / Userwork_after_loop  */
+int ab2_upload_cons_soa(ab2_grid* g, const double* const vars[6]);
+int ab2_download_cons_soa(ab2_grid* g, double* const vars[6]);
+int ab2_upload_edgeflux(ab2_grid* g, const double* edgeflux);   /* GridS.EdgeFlux [Nx3+1][Nx2+1][Nx1+1]        */
+int ab2_download_edgeflux(ab2_grid* g, double* edgeflux);
+double* ab2_device_ptr(ab2_grid* g, int var);                   /* device array of variable 0..5               */
+
+/* ---- hot path -------------------------------------------------------------------------------------- */
+/* bvals_mhd (bvals_mhd.c:174-508).  bc[6] = bc_ix1,bc_ox1,bc_ix2,bc_ox2,bc_ix3,bc_ox3 with the reference's flag
+ * values (1 reflect, 2 outflow, 4 periodic, 5 conductor); a value <= 0 marks a face owned by a neighbouring Grid
+ * (MPI in the reference, NCCL slab exchange here) or prolongated later, and is left untouched. */
+int ab2_bvals_mhd(ab2_grid* g, const int bc[6]);
+/* new_dt (new_dt.c:69-139): out[3] = max over active zones of |v_d| + sqrt(gamma P/d). */
+int ab2_max_wave_speeds(ab2_grid* g, double out[3]);
+/* new_dt (new_dt.c:32-198) for a single-Grid mesh: CFL, 2x growth limit, tlim clip.  reduce may be NULL. */
+int ab2_new_dt(ab2_grid* g, double cour_no, double dt_old, int nstep, double time, double tlim,
+               ab2_reduce_fn reduce, void* ctx, double* dt_out);
+/* StaticGravPot enrolment: tabulates the user's potential on the host at exactly the arguments the reference
+ * passes (integrate_3d_ctu.c:334-336,1172-1215,1468-1522,1878-1933,2746-2777) and uploads the tables. NULL clears. */
+int ab2_set_static_grav_pot(ab2_grid* g, ab2_grav_pot_fn phi);
+/* integrate_3d_ctu (integrators/integrate_3d_ctu.c:110-3368) with GridS.dt = dt. */
+int ab2_integrate_3d_ctu(ab2_grid* g, double dt);
+/* Userwork_in_loop replay: a static list of cells (flat indices incl. ghosts) reset to fixed values
+ * vals[6][n] every step, e.g. prob/ioniz_sphere.c:255-306. */
+int ab2_set_fixed_cells(ab2_grid* g, long n, const long* cells, const double* vals);
+int ab2_apply_fixed_cells(ab2_grid* g);
+
+/* ion_radtransfer_init (ionradiation/ionrad.c:64-149, ionrad_3d.c:739-814) */
+int ab2_ion_init(ab2_grid* g, const ab2_ion_par* par);
+/* ionrad.c:115-131: fills min_area and d_nlo from the root mesh spacing */
+void ab2_ion_derived(ab2_ion_par* par, double dx1, double dx2, double dx3);
+/* bvals_ionrad (ionradiation/bvals_ionrad.c:63-146, outflow_flux_ix1 :308-332) */
+int ab2_bvals_ionrad(ab2_grid* g, double flux_i);
+/* entering flux at the root upstream face at mesh time t (ionradplane_3d.c:265) */
+double ab2_ion_entering_flux(double flux_i, double time);
+/* ion_radtransfer_3d (ionradiation/ionrad_3d.c:862-1047) for a root-level Grid and one plane with dir = -1.
+ * *dt is GridS.dt on entry and on exit (the routine may shorten it).  niter/nchem/ntherm are the numbers of the
+ * reference's stderr line (:1041). */
+int ab2_ion_radtransfer_3d(ab2_grid* g, double flux_i, double time, double cour_no, double* dt,
+                           int* niter, int* nchem, int* ntherm, ab2_reduce_fn reduce, void* ctx);
+
+/* ---- function-level entry points (parity tests): rows of 6 doubles, host arrays ------------------------- */
+/* fluxes() of rsolvers/roe.c:59-336 (+ hlle.c fallback) on n independent interfaces */
+int ab2_unit_roe_flux(int n, const double* Ul, const double* Ur, const double* Wl, const double* Wr,
+                      int nscal, double gamma, const double* etah, double* F);
+/* Cons1D_to_Prim1D / Prim1D_to_Cons1D / cfast (convert_var.c:389-499); cfast_out may be NULL */
+int ab2_unit_convert(int n, const double* in, int nscal, double gamma, int to_prim, double* out, double* cfast_out);
+/* lr_states() of reconstruction/lr_states_plm.c:62-374 on npencil pencils of n cells */
+int ab2_unit_lr_states(int npencil, int n, const double* W, int nscal, double gamma, double dt, double dx,
+                       int il, int iu, double* Wl, double* Wr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
