@@ -46,7 +46,49 @@ __global__ void k_soa_to_aos(GridDev g, int nvar, long ncell, double* aos)
   for (int v=0; v<nvar; v++) aos[t*nvar + v] = g.U[v][t];
 }
 
+static const char* KERNEL_NAMES[KID_N] = {
+  "k_bvals", "k_max_speeds", "k_first_x1", "k_first_march<1>", "k_first_march<2>", "k_dhalf",
+  "k_correct<0>", "k_correct<1>", "k_correct<2>", "k_final<0>", "k_final<1>", "k_final<2>", "k_update",
+  "k_apply_fixed", "k_ion_prep", "k_ion_rates", "k_ion_update", "k_bvals_ionrad", "k_transpose" };
+
+cudaEvent_t ab2_prof_event(ab2_grid* h)
+{
+  cudaEvent_t e;
+  if (!h->prof_pool.empty()) { e = h->prof_pool.back(); h->prof_pool.pop_back(); return e; }
+  cudaEventCreate(&e);
+  return e;
+}
+
+static void prof_drain(ab2_grid* h)
+{
+  cudaStreamSynchronize(h->stream);
+  for (auto& p : h->prof_pending) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) { h->prof_ms[p.id] += ms; h->prof_cnt[p.id]++; }
+    h->prof_pool.push_back(p.a); h->prof_pool.push_back(p.b);
+  }
+  h->prof_pending.clear();
+}
+
 extern "C" {
+
+int ab2_profile_enable(ab2_grid* h, int on)
+{
+  prof_drain(h);
+  h->prof_on = (on != 0);
+  return 0;
+}
+
+int ab2_profile_kernels(void) { return KID_N; }
+const char* ab2_profile_kernel_name(int id) { return (id >= 0 && id < KID_N) ? KERNEL_NAMES[id] : ""; }
+
+int ab2_profile_read(ab2_grid* h, double* ms, long long* counts, int reset)
+{
+  prof_drain(h);
+  for (int n=0; n<KID_N; n++) { ms[n] = h->prof_ms[n]; counts[n] = h->prof_cnt[n]; }
+  if (reset) for (int n=0; n<KID_N; n++) { h->prof_ms[n] = 0.0; h->prof_cnt[n] = 0; }
+  return 0;
+}
 
 const char* ab2_last_error(void) { return g_err.c_str(); }
 const char* ab2_version(void) { return "athena_b200 0.1 (sm_100a, fp64, fmad=off)"; }
@@ -75,6 +117,8 @@ ab2_grid* ab2_grid_create(const ab2_grid_desc* d)
   h->nscal = d->nscal; h->device = d->device;
   h->has_grav = false; h->has_ion = false; h->n_fixed = 0; h->d_fixed_cells = nullptr; h->d_fixed_vals = nullptr;
   h->bytes_allocated = 0; h->launches = 0; h->maxiter = 0;
+  h->prof_on = false;
+  for (int n=0; n<KID_N; n++) { h->prof_ms[n] = 0.0; h->prof_cnt[n] = 0; }
   memset(&h->ion, 0, sizeof h->ion);
   if (d->stream) { h->stream = (cudaStream_t)d->stream; h->own_stream = false; }
   else {
@@ -120,7 +164,8 @@ void ab2_grid_destroy(ab2_grid* h)
 {
   if (!h) return;
   cudaSetDevice(h->device);
-  cudaStreamSynchronize(h->stream);
+  prof_drain(h);
+  for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
   for (void* p : h->allocs) cudaFree(p);
   if (h->h_scal) cudaFreeHost(h->h_scal);
   if (h->own_stream) cudaStreamDestroy(h->stream);
@@ -140,8 +185,7 @@ int ab2_upload_cons_aos(ab2_grid* h, const double* U_aos)
   const int nvar = 5 + h->nscal;
   double* stage = g.Ul[0][0];      // scratch slab is dead between steps
   CK(cudaMemcpyAsync(stage, U_aos, (size_t)ncell*nvar*sizeof(double), cudaMemcpyHostToDevice, h->stream), "upload aos");
-  k_aos_to_soa<<<(unsigned)((ncell+255)/256), 256, 0, h->stream>>>(g, nvar, ncell, stage);
-  h->launches++;
+  AB2_LAUNCH(h, KID_TRANSPOSE, (k_aos_to_soa<<<(unsigned)((ncell+255)/256), 256, 0, h->stream>>>(g, nvar, ncell, stage)));
   CK(cudaStreamSynchronize(h->stream), "upload aos sync");
   return 0;
 }
@@ -152,8 +196,7 @@ int ab2_download_cons_aos(ab2_grid* h, double* U_aos)
   const long ncell = (long)g.n[0]*g.n[1]*g.n[2];
   const int nvar = 5 + h->nscal;
   double* stage = g.Ul[0][0];
-  k_soa_to_aos<<<(unsigned)((ncell+255)/256), 256, 0, h->stream>>>(g, nvar, ncell, stage);
-  h->launches++;
+  AB2_LAUNCH(h, KID_TRANSPOSE, (k_soa_to_aos<<<(unsigned)((ncell+255)/256), 256, 0, h->stream>>>(g, nvar, ncell, stage)));
   CK(cudaMemcpyAsync(U_aos, stage, (size_t)ncell*nvar*sizeof(double), cudaMemcpyDeviceToHost, h->stream), "download aos");
   CK(cudaStreamSynchronize(h->stream), "download aos sync");
   return 0;

@@ -67,6 +67,14 @@ struct IonDev {
 
 typedef void (*ab2_reduce_fn_t)(double* vals, int n, int op, void* ctx);
 
+// per-kernel CUDA-event timing (bench.py's roofline): ids index KERNEL_NAMES in api.cu
+enum {
+  KID_BVALS = 0, KID_MAX_SPEEDS, KID_FIRST_X1, KID_FIRST_X2, KID_FIRST_X3, KID_DHALF,
+  KID_CORRECT_X1, KID_CORRECT_X2, KID_CORRECT_X3, KID_FINAL_X1, KID_FINAL_X2, KID_FINAL_X3, KID_UPDATE,
+  KID_APPLY_FIXED, KID_ION_PREP, KID_ION_RATES, KID_ION_UPDATE, KID_BVALS_IONRAD, KID_TRANSPOSE, KID_N
+};
+struct ProfPending { int id; cudaEvent_t a, b; };
+
 struct ab2_grid {
   GridDev g;
   int nscal;
@@ -87,7 +95,22 @@ struct ab2_grid {
   double* d_fixed_vals;
   size_t bytes_allocated;
   long long launches;              // kernels launched so far (bench.py's gpu_launches)
+  bool prof_on;
+  std::vector<ProfPending> prof_pending;
+  std::vector<cudaEvent_t> prof_pool;
+  double prof_ms[KID_N];
+  long long prof_cnt[KID_N];
 };
+
+// launch bookkeeping: counts every kernel; with profiling on, brackets it with events on the launching stream
+cudaEvent_t ab2_prof_event(ab2_grid* h);
+#define AB2_LAUNCH(h, id, ...) do { \
+    cudaEvent_t _a = nullptr, _b = nullptr; \
+    if ((h)->prof_on) { _a = ab2_prof_event(h); _b = ab2_prof_event(h); cudaEventRecord(_a, (h)->stream); } \
+    __VA_ARGS__; \
+    if ((h)->prof_on) { cudaEventRecord(_b, (h)->stream); (h)->prof_pending.push_back(ProfPending{(id), _a, _b}); } \
+    (h)->launches++; \
+  } while (0)
 
 // error plumbing (api.cu)
 void ab2_set_error(const std::string& s);

@@ -337,8 +337,7 @@ int hydro_bvals(ab2_grid* h, const int bc[6])
     for (int side=0; side<2; side++) {
       const int flag = bc[2*dir+side];
       if (flag != 1 && flag != 2 && flag != 4 && flag != 5) continue;   // <=0: neighbouring Grid / prolongated face
-      k_bvals<<<(unsigned)((nt+255)/256), 256, 0, h->stream>>>(g, nvar, dir, side, flag, tr);
-      h->launches++;
+      AB2_LAUNCH(h, KID_BVALS, (k_bvals<<<(unsigned)((nt+255)/256), 256, 0, h->stream>>>(g, nvar, dir, side, flag, tr)));
     }
   }
   return ab2_check(cudaGetLastError(), "bvals_mhd") ? 0 : -1;
@@ -391,8 +390,7 @@ int hydro_max_speeds(ab2_grid* h, double out[3])
   if (!ab2_check(cudaMemsetAsync(h->d_scal + SC_MAXV1, 0, 3*sizeof(unsigned long long), h->stream), "new_dt memset")) return -1;
   const long nact = (long)g.nx[0]*g.nx[1]*g.nx[2];
   int blocks = (int)((nact + 255)/256); if (blocks > 148*8) blocks = 148*8;
-  k_max_speeds<<<blocks, 256, 0, h->stream>>>(g, h->d_scal);
-  h->launches++;
+  AB2_LAUNCH(h, KID_MAX_SPEEDS, (k_max_speeds<<<blocks, 256, 0, h->stream>>>(g, h->d_scal)));
   if (!ab2_check(cudaMemcpyAsync(h->h_scal + SC_MAXV1, h->d_scal + SC_MAXV1, 3*sizeof(unsigned long long),
                                  cudaMemcpyDeviceToHost, h->stream), "new_dt D2H")) return -1;
   if (!ab2_check(cudaStreamSynchronize(h->stream), "new_dt sync")) return -1;
@@ -418,8 +416,7 @@ __global__ void k_apply_fixed(GridDev g, int nvar, long n, const long* cells, co
 int hydro_apply_fixed(ab2_grid* h)
 {
   if (h->n_fixed <= 0) return 0;
-  k_apply_fixed<<<(unsigned)((h->n_fixed+255)/256), 256, 0, h->stream>>>(h->g, 5+h->nscal, h->n_fixed, h->d_fixed_cells, h->d_fixed_vals);
-  h->launches++;
+  AB2_LAUNCH(h, KID_APPLY_FIXED, (k_apply_fixed<<<(unsigned)((h->n_fixed+255)/256), 256, 0, h->stream>>>(h->g, 5+h->nscal, h->n_fixed, h->d_fixed_cells, h->d_fixed_vals)));
   return ab2_check(cudaGetLastError(), "apply_fixed") ? 0 : -1;
 }
 
@@ -446,36 +443,32 @@ static int integrate_impl(ab2_grid* h, double dt)
   {
     const int nf = g.nx[0]+4;
     dim3 grid((nf + A1_F-1)/A1_F, u[1]-l[1]+1, u[2]-l[2]+1);
-    k_first_x1<NS,GRAV><<<grid, A1_T, 0, st>>>(g, dt);
+    AB2_LAUNCH(h, KID_FIRST_X1, (k_first_x1<NS,GRAV><<<grid, A1_T, 0, st>>>(g, dt)));
     const int ni = u[0]-l[0]+1;
     dim3 g2((ni+127)/128, (g.nx[1]+4 + seg-1)/seg, u[2]-l[2]+1);
-    k_first_march<1,NS,GRAV><<<g2, 128, 0, st>>>(g, dt, seg);
+    AB2_LAUNCH(h, KID_FIRST_X2, (k_first_march<1,NS,GRAV><<<g2, 128, 0, st>>>(g, dt, seg)));
     dim3 g3((ni+127)/128, (g.nx[2]+4 + seg-1)/seg, u[1]-l[1]+1);
-    k_first_march<2,NS,GRAV><<<g3, 128, 0, st>>>(g, dt, seg);
-    h->launches += 3;
+    AB2_LAUNCH(h, KID_FIRST_X3, (k_first_march<2,NS,GRAV><<<g3, 128, 0, st>>>(g, dt, seg)));
   }
   Box act; for (int a=0; a<3; a++) { act.lo[a] = s[a]; act.hi[a] = e[a]; }
   // Pass B
-  if (GRAV) { k_dhalf<<<box_grid(act,128), 128, 0, st>>>(g, act, dt); h->launches++; }
+  if (GRAV) AB2_LAUNCH(h, KID_DHALF, (k_dhalf<<<box_grid(act,128), 128, 0, st>>>(g, act, dt)));
   // Pass C: faces of direction d over [l+1, u-1] transversally and [l+1, u] along d
   for (int d=0; d<3; d++) {
     Box b; for (int a=0; a<3; a++) { b.lo[a] = l[a]+1; b.hi[a] = (a == d) ? u[a] : u[a]-1; }
-    if (d == 0) k_correct<0,NS,GRAV><<<box_grid(b,128), 128, 0, st>>>(g, b, dt);
-    if (d == 1) k_correct<1,NS,GRAV><<<box_grid(b,128), 128, 0, st>>>(g, b, dt);
-    if (d == 2) k_correct<2,NS,GRAV><<<box_grid(b,128), 128, 0, st>>>(g, b, dt);
-    h->launches++;
+    if (d == 0) AB2_LAUNCH(h, KID_CORRECT_X1+0, (k_correct<0,NS,GRAV><<<box_grid(b,128), 128, 0, st>>>(g, b, dt)));
+    if (d == 1) AB2_LAUNCH(h, KID_CORRECT_X1+1, (k_correct<1,NS,GRAV><<<box_grid(b,128), 128, 0, st>>>(g, b, dt)));
+    if (d == 2) AB2_LAUNCH(h, KID_CORRECT_X1+2, (k_correct<2,NS,GRAV><<<box_grid(b,128), 128, 0, st>>>(g, b, dt)));
   }
   // Pass D: faces [s, e+1] along d, active transversally (the +-1 transverse ring of the reference's loops feeds MHD only)
   for (int d=0; d<3; d++) {
     Box b; for (int a=0; a<3; a++) { b.lo[a] = s[a]; b.hi[a] = (a == d) ? e[a]+1 : e[a]; }
-    if (d == 0) k_final<0,NS><<<box_grid(b,128), 128, 0, st>>>(g, b);
-    if (d == 1) k_final<1,NS><<<box_grid(b,128), 128, 0, st>>>(g, b);
-    if (d == 2) k_final<2,NS><<<box_grid(b,128), 128, 0, st>>>(g, b);
-    h->launches++;
+    if (d == 0) AB2_LAUNCH(h, KID_FINAL_X1+0, (k_final<0,NS><<<box_grid(b,128), 128, 0, st>>>(g, b)));
+    if (d == 1) AB2_LAUNCH(h, KID_FINAL_X1+1, (k_final<1,NS><<<box_grid(b,128), 128, 0, st>>>(g, b)));
+    if (d == 2) AB2_LAUNCH(h, KID_FINAL_X1+2, (k_final<2,NS><<<box_grid(b,128), 128, 0, st>>>(g, b)));
   }
   // Pass E
-  k_update<NS,GRAV><<<box_grid(act,128), 128, 0, st>>>(g, act, dt);
-  h->launches++;
+  AB2_LAUNCH(h, KID_UPDATE, (k_update<NS,GRAV><<<box_grid(act,128), 128, 0, st>>>(g, act, dt)));
   return ab2_check(cudaGetLastError(), "integrate_3d_ctu") ? 0 : -1;
 }
 

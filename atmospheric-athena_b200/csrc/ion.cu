@@ -328,8 +328,7 @@ int ion_bvals_ionrad(ab2_grid* h, double flux_i)
 {
   const GridDev& g = h->g;
   const long n = (long)(g.nx[1]+1)*(g.nx[2]+1);
-  k_bvals_ionrad<<<(unsigned)((n+255)/256), 256, 0, h->stream>>>(h->ion, g.nx[0], g.nx[1], g.nx[2], flux_i);
-  h->launches++;
+  AB2_LAUNCH(h, KID_BVALS_IONRAD, (k_bvals_ionrad<<<(unsigned)((n+255)/256), 256, 0, h->stream>>>(h->ion, g.nx[0], g.nx[1], g.nx[2], flux_i)));
   return ab2_check(cudaGetLastError(), "bvals_ionrad") ? 0 : -1;
 }
 
@@ -351,8 +350,7 @@ int ion_radtransfer(ab2_grid* h, double flux_in, double cour_no, double* dt_io, 
   const long nrays = (long)g.nx[1]*g.nx[2];
   const unsigned rgrid = (unsigned)((nrays + 3)/4);
 
-  k_ion_prep<<<cgrid, 128, 0, st>>>(g, p, h->ion);
-  h->launches++;
+  AB2_LAUNCH(h, KID_ION_PREP, (k_ion_prep<<<cgrid, 128, 0, st>>>(g, p, h->ion)));
 
   double grid_dt = *dt_io, dt_done = 0.0, dt = 0.0, dt_chem = 0.0, dt_therm = 0.0, dt_hydro = 0.0;
   int niter = 0, hydro_done = 0, nchem = 0, ntherm = 0;
@@ -362,8 +360,7 @@ int ion_radtransfer(ab2_grid* h, double flux_in, double cour_no, double* dt_io, 
     h->h_scal[SC_MAX_DTI] = double_to_bits(0.0); h->h_scal[SC_COUNT] = 0;
     if (!ab2_check(cudaMemcpyAsync(h->d_scal + SC_DT_CHEM, h->h_scal + SC_DT_CHEM, 4*sizeof(unsigned long long),
                                    cudaMemcpyHostToDevice, st), "ion scalars H2D")) return -1;
-    k_ion_rates<<<rgrid, 128, 0, st>>>(g, p, h->ion, flux_in, h->d_scal);
-    h->launches++;
+    AB2_LAUNCH(h, KID_ION_RATES, (k_ion_rates<<<rgrid, 128, 0, st>>>(g, p, h->ion, flux_in, h->d_scal)));
     if (!ab2_check(cudaMemcpyAsync(h->h_scal + SC_DT_CHEM, h->d_scal + SC_DT_CHEM, 2*sizeof(unsigned long long),
                                    cudaMemcpyDeviceToHost, st), "ion scalars D2H")) return -1;
     if (!ab2_check(cudaMemcpyAsync(h->h_scal + SC_ERR, h->d_scal + SC_ERR, sizeof(unsigned long long),
@@ -378,8 +375,7 @@ int ion_radtransfer(ab2_grid* h, double flux_in, double cour_no, double* dt_io, 
     dt = AB2_MIN(dt_therm, dt_chem);
     if (dt_done + dt > grid_dt) { dt = grid_dt - dt_done; hydro_done = 1; }
 
-    k_ion_update<<<cgrid, 128, 0, st>>>(g, p, h->ion, dt, h->d_scal);
-    h->launches++;
+    AB2_LAUNCH(h, KID_ION_UPDATE, (k_ion_update<<<cgrid, 128, 0, st>>>(g, p, h->ion, dt, h->d_scal)));
     dt_done += dt;
     niter++;
     if (!ab2_check(cudaMemcpyAsync(h->h_scal + SC_MAX_DTI, h->d_scal + SC_MAX_DTI, 2*sizeof(unsigned long long),

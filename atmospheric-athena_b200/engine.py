@@ -46,7 +46,8 @@ EXPORTS = ["ab2_last_error", "ab2_version", "ab2_device_count", "ab2_grid_create
            "ab2_download_edgeflux", "ab2_device_ptr", "ab2_bvals_mhd", "ab2_max_wave_speeds", "ab2_new_dt",
            "ab2_set_static_grav_pot", "ab2_integrate_3d_ctu", "ab2_set_fixed_cells", "ab2_apply_fixed_cells",
            "ab2_ion_init", "ab2_ion_derived", "ab2_bvals_ionrad", "ab2_ion_entering_flux", "ab2_ion_radtransfer_3d",
-           "ab2_unit_roe_flux", "ab2_unit_convert", "ab2_unit_lr_states"]
+           "ab2_unit_roe_flux", "ab2_unit_convert", "ab2_unit_lr_states",
+           "ab2_profile_enable", "ab2_profile_kernels", "ab2_profile_kernel_name", "ab2_profile_read"]
 
 
 def build(verbose=False):
@@ -104,6 +105,10 @@ def lib():
     L.ab2_ion_entering_flux.restype = C.c_double
     L.ab2_ion_radtransfer_3d.argtypes = [vp, C.c_double, C.c_double, C.c_double, dp,
                                          C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), vp, vp]
+    L.ab2_profile_enable.argtypes = [vp, C.c_int]
+    L.ab2_profile_kernel_name.argtypes = [C.c_int]
+    L.ab2_profile_kernel_name.restype = C.c_char_p
+    L.ab2_profile_read.argtypes = [vp, dp, C.POINTER(C.c_longlong), C.c_int]
     L.ab2_unit_roe_flux.argtypes = [C.c_int, dp, dp, dp, dp, C.c_int, C.c_double, dp, dp]
     L.ab2_unit_convert.argtypes = [C.c_int, dp, C.c_int, C.c_double, C.c_int, dp, dp]
     L.ab2_unit_lr_states.argtypes = [C.c_int, C.c_int, dp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, dp, dp]
@@ -174,6 +179,17 @@ class Grid:
 
     def synchronize(self):
         self._ck(lib().ab2_synchronize(self.h))
+
+    def profile_enable(self, on=True):
+        self._ck(lib().ab2_profile_enable(self.h, 1 if on else 0))
+
+    def profile_read(self, reset=True) -> dict:
+        """{kernel name: (total ms, launches)} measured with CUDA events on the launching stream."""
+        n = lib().ab2_profile_kernels()
+        ms = (C.c_double * n)()
+        cnt = (C.c_longlong * n)()
+        self._ck(lib().ab2_profile_read(self.h, ms, cnt, 1 if reset else 0))
+        return {lib().ab2_profile_kernel_name(i).decode(): (ms[i], cnt[i]) for i in range(n) if cnt[i]}
 
     # -- coherence -------------------------------------------------------------------------------
     def upload(self, U: dict):

@@ -1,0 +1,379 @@
+#!/usr/bin/env python3
+"""bench.py -- zone-updates/s of one full hydro + ion-RT step (BASELINE.json metric) on N B200s.
+
+A "step" is one pass of the reference's main-loop body (main.c:519-669) over the whole grid:
+[ion_radtransfer_3d sub-cycle; bvals_mhd] -> integrate_3d_ctu -> Userwork_in_loop -> new_dt -> bvals_mhd,
+driven through the C ABI of libathena_b200.so.  Default workload: ioniz_sphere unigrid 256^3 (BASELINE.json
+configs[2], the north-star target config: hydro + ion RT + static potential); `--workload blast` is configs[1]
+(hydro-only isolation), `--workload ifront` is configs[0].  With --gpus N the grid is x3-slab decomposed, one
+256x256x256 slab per GPU (weak scaling), ghost slabs over NCCL, timestep/sub-cycle scalars over all_reduce.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload ioniz_sphere|blast|ifront] [--n 256]
+    python bench.py --impl reference ...      # the reference's own CPU build (oracle/_ref) on the host cores
+
+Prints ONE JSON line (rank 0).  `value` = zones of all ranks x K / max-over-ranks device time with the state
+resident in HBM; `e2e` = the same through host buffers (ConsS AoS upload + step + download per step);
+`roofline` = the dominant kernel of the timed region, CUDA-event timed on its stream, against MEASURED_PEAKS.json.
+"""
+import argparse
+import json
+import os
+import re
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+from __graft_entry__ import load_package  # noqa: E402
+
+load_package()
+from athena_b200.athinput import ParFile  # noqa: E402
+
+DECKS = os.path.join(ROOT, "tests", "decks")
+WORKLOADS = {
+    # name: (deck, problem/reference build, BASELINE.json config it corresponds to)
+    "ioniz_sphere": ("ioniz_sphere.athinput", "ioniz_sphere", "configs[2] ioniz_sphere unigrid"),
+    "blast": ("blast.athinput", "blast", "configs[1] 3D hydro blast, hydro-only"),
+    "ifront": ("ifront.athinput", "ifront", "configs[0] ifront"),
+}
+
+# Compulsory HBM bytes per zone of each kernel given the pass structure (DESIGN.md "Kernels"), as
+# (doubles with nvar multiplier, plain doubles, doubles only present with a static potential); x 8 B.
+KERNEL_BYTES = {
+    "k_first_x1": (4, 0, 2), "k_first_march<1>": (4, 0, 2), "k_first_march<2>": (4, 0, 2),
+    "k_dhalf": (0, 5, 0),
+    "k_correct<0>": (6, 1, 4), "k_correct<1>": (6, 1, 4), "k_correct<2>": (6, 1, 4),
+    "k_final<0>": (3, 3, 0), "k_final<1>": (3, 3, 0), "k_final<2>": (3, 3, 0),
+    "k_update": (5, 0, 5),
+    "k_ion_prep": (0, 11.5, 0), "k_ion_rates": (0, 11, 0), "k_ion_update": (0, 14, 0),
+    "k_max_speeds": (0, 5, 0),
+}
+
+
+def kernel_bytes_per_zone(name, nvar, grav):
+    if name not in KERNEL_BYTES:
+        return None
+    a, b, c = KERNEL_BYTES[name]
+    return 8.0 * (a * nvar + b + (c if grav else 0))
+
+
+def step_algorithmic_bytes(workload, n_iter):
+    """B_alg = B_hydro + n_iter*B_ion per zone-update (compulsory traffic, FP64, SoA)."""
+    b_hydro = {"blast": 80.0, "ifront": 96.0, "ioniz_sphere": 128.0}[workload]
+    return b_hydro + (n_iter * 112.0 if workload != "blast" else 0.0)
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def make_par(workload, n, nx3):
+    deck, _, _ = WORKLOADS[workload]
+    par = ParFile.par_open(os.path.join(DECKS, deck))
+    par.par_cmdline(["job/num_domains=1", f"domain1/Nx1={n}", f"domain1/Nx2={n}", f"domain1/Nx3={nx3}"])
+    if nx3 != n:    # weak scaling: the box grows along x3 with the GPU count, zones stay cubic
+        x3min, x3max = par.par_getd("domain1", "x3min"), par.par_getd("domain1", "x3max")
+        c, h = 0.5 * (x3min + x3max), 0.5 * (x3max - x3min) * nx3 / n
+        par.par_cmdline([f"domain1/x3min={c - h!r}", f"domain1/x3max={c + h!r}"])
+    return par
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.lines = []
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(index)],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def summary(self, t0, t1):
+        if self.p is not None:
+            self.p.terminate()
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.lines:
+            if ts < t0 or ts > t1 + 0.3:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0])); mx = max(mx, float(f[1]))
+            except Exception:
+                continue
+            for nme, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the reference's own binary (oracle/_ref/<cfg>/athena), serial (no MPI here)
+# ---------------------------------------------------------------------------------------------------------
+def reference_exe(workload):
+    return os.path.join(ROOT, "oracle", "_ref", WORKLOADS[workload][1], "athena")
+
+
+def run_reference_cpu(workload, n, nsteps, instances):
+    """`instances` concurrent serial runs of the reference binary on an n^3 grid for nsteps steps.
+    Returns (sum of zone-cycles/wall-second over instances, wall seconds, kind)."""
+    exe = reference_exe(workload)
+    deck = os.path.join(DECKS, WORKLOADS[workload][0])
+    if not os.path.exists(exe):
+        return run_port_cpu(workload, min(n, 32), max(2, min(nsteps, 3)))
+    procs, tmps = [], []
+    t0 = time.time()
+    for _ in range(instances):
+        tmp = tempfile.mkdtemp(prefix="ath_ref_")
+        tmps.append(tmp)
+        cmd = [exe, "-i", deck, "job/maxout=0", "job/num_domains=1", f"domain1/Nx1={n}", f"domain1/Nx2={n}", f"domain1/Nx3={n}", f"time/nlim={nsteps}"]
+        procs.append(subprocess.Popen(cmd, cwd=tmp, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True))
+    total = 0.0
+    for p in procs:
+        out, _ = p.communicate()
+        m = re.search(r"zone-cycles/wall-second = (\S+)", out)
+        if m:
+            total += float(m.group(1))
+    wall = time.time() - t0
+    for tmp in tmps:
+        subprocess.run(["rm", "-rf", tmp])
+    return total, wall, "reference"
+
+
+def run_port_cpu(workload, n, nsteps):
+    """Fallback when oracle/_ref is absent: the oracle port (oracle/athena_oracle.c), 1 thread."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    from athena_b200 import problems
+    par = make_par(workload, n, n)
+    nx = (n, n, n)
+    xmin = tuple(par.par_getd("domain1", f"x{a}min") for a in (1, 2, 3))
+    xmax = tuple(par.par_getd("domain1", f"x{a}max") for a in (1, 2, 3))
+    bc = tuple(par.par_geti("domain1", k) for k in ("bc_ix1", "bc_ox1", "bc_ix2", "bc_ox2", "bc_ix3", "bc_ox3"))
+    prob = WORKLOADS[workload][1]
+    ion = prob != "blast"
+    grav = None
+    if prob == "ioniz_sphere":
+        problems.ioniz_sphere_setup(par)
+        grav = problems.lib().ab2_planet_pot
+    G = ol.OracleGrid(nx, xmin, xmax, par.par_getd("problem", "gamma"), 1 if ion else 0, bc, grav=grav)
+    U = problems.problem(prob, par, nx, xmin, G.dx)
+    for v in G.U:
+        G.U[v][...] = U[v]
+    G.bvals()
+    flux = par.par_getd("problem", "flux") if ion else 0.0
+    if ion:
+        G.bvals_ionrad(flux)
+    cour, tlim = par.par_getd("time", "cour_no"), par.par_getd("time", "tlim")
+    G.new_dt(cour, tlim)
+    t0 = time.time()
+    ol.run_main_loop(G, nsteps, cour, tlim, ol.ion_par_from(par, G.dx) if ion else None, flux)
+    wall = time.time() - t0
+    return n ** 3 * nsteps / wall, wall, "port"
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    n = args.cpu_n
+    nsteps = args.steps + args.warmup
+    value, wall, kind = run_reference_cpu(args.workload, n, nsteps, cores)
+    used = cores if kind == "reference" else 1
+    line = {
+        "impl": "reference", "metric": "zone-updates/s per hydro+ion-RT step", "value": value, "unit": "zone-updates/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / nsteps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{WORKLOADS[args.workload][2]}; CPU sample {n}^3 per instance, {nsteps} steps from t=0"},
+        "cpu_baseline": {"value": value, "unit": "zone-updates/s", "cores": used, "kind": kind,
+                         "sample": f"{used} concurrent serial runs of the reference binary (no MPI in this image; ideal-scaling proxy), "
+                                   f"{n}^3 zones each, {nsteps} steps, sum of zone-cycles/wall-second (main.c:722)"},
+        "e2e": {"value": value, "unit": "zone-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------
+def gpu_arm(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from athena_b200 import engine
+    from athena_b200.driver import Run
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this engine has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    d = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+        d = dist
+    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+
+    n = args.n
+    par = make_par(args.workload, n, n * world)
+    prob = WORKLOADS[args.workload][1]
+    t_setup = time.time()
+    R = Run(par, prob, device=local, dist=d, torch_memory=True)
+    t_setup = time.time() - t_setup
+    G = R.G
+    zones_local = R.zones
+    zones_total = zones_local * world
+    nvar, grav = G.nvar, (prob == "ioniz_sphere")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        R.step()
+    barrier()
+
+    # ---- timed region: K steps, state resident in HBM ----
+    sampler = ClockSampler(local) if rank == 0 else None
+    G.profile_enable(True)
+    G.profile_read(reset=True)
+    l0 = G.kernel_launches
+    it0 = len(R.rad_log)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    w0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        R.step()
+    e1.record()
+    barrier()
+    w1 = time.time()
+    ms = e0.elapsed_time(e1)
+    prof = G.profile_read(reset=True)
+    G.profile_enable(False)
+    launches = G.kernel_launches - l0
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clocks = sampler.summary(w0, w1) if sampler else None
+    n_iter = (sum(r[0] for r in R.rad_log[it0:]) / max(1, len(R.rad_log) - it0)) if R.ion else 0.0
+    value = zones_total * args.steps / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel ----
+    peak, peak_src = measured_peaks()
+    ktab = {}
+    tot_ms = sum(v[0] for v in prof.values())
+    for name, (kms, cnt) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
+        bpz = kernel_bytes_per_zone(name, nvar, grav)
+        ent = {"ms_total": round(kms, 4), "launches": cnt, "share": round(kms / tot_ms, 4) if tot_ms else None}
+        if bpz:
+            ent["alg_bytes_per_launch"] = bpz * zones_local
+            ent["gbs"] = round(bpz * zones_local / (kms / cnt * 1e-3) / 1e9, 1)
+        ktab[name] = ent
+    dom = next(iter(ktab)) if ktab else None
+    roof = None
+    if dom and "gbs" in ktab[dom]:
+        roof = {"bound": "hbm", "kernel": dom, "achieved": ktab[dom]["gbs"], "peak": peak, "unit": "GB/s",
+                "frac": round(ktab[dom]["gbs"] / peak, 4), "traffic": None, "peak_source": peak_src,
+                "alg_bytes_per_launch": ktab[dom]["alg_bytes_per_launch"], "avg_launch_ms": round(ktab[dom]["ms_total"] / ktab[dom]["launches"], 4),
+                "share_of_kernel_time": ktab[dom]["share"]}
+        b_alg = step_algorithmic_bytes(args.workload, n_iter)
+        roof["step"] = {"alg_bytes_per_zone_update": b_alg, "achieved": round(value / world * b_alg / 1e9, 1),
+                        "frac": round(value / world * b_alg / 1e9 / peak, 4),
+                        "note": "whole step at SURVEY 8(d) compulsory bytes per GPU; the hydro sweep is FP64-pipe bound at this traffic"}
+        prof_json = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(prof_json):
+            try:
+                roof["traffic"] = json.load(open(prof_json)).get(dom, {}).get("dram_bytes_per_launch")
+            except Exception:
+                pass
+
+    # ---- e2e: host buffers in and out every step (the per-call coherence mode of the drop-in shim) ----
+    e2e_steps = min(args.steps, args.e2e_steps)
+    host = torch.empty(G.shape + (nvar,), dtype=torch.float64, pin_memory=True).numpy()
+    host[...] = G.download_aos()
+    barrier()
+    e0.record()
+    for _ in range(e2e_steps):
+        G.upload_aos(host)
+        R.step()
+        engine.lib().ab2_download_cons_aos(G.h, host.ctypes.data_as(engine.dp))
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item())
+    e2e = {"value": zones_total * e2e_steps / (ms_e2e * 1e-3), "unit": "zone-updates/s",
+           "h2d_bytes_per_step": int(host.nbytes), "d2h_bytes_per_step": int(host.nbytes), "steps": e2e_steps,
+           "path": "ab2_upload_cons_aos(pinned host ConsS) -> step -> ab2_download_cons_aos, per step"}
+
+    # ---- CPU baseline beside it (rank 0, N=1): the reference's own binary on a bounded sample ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, wall, kind = run_reference_cpu(args.workload, args.cpu_n, args.cpu_steps, 1)
+        cpu = {"value": v, "unit": "zone-updates/s", "cores": 1, "kind": kind,
+               "sample": f"{args.cpu_n}^3 zones, {args.cpu_steps} steps from t=0, serial reference build (gcc -O3, no MPI in this image), {wall:.1f} s"}
+
+    if rank == 0:
+        line = {
+            "metric": "zone-updates/s per hydro+ion-RT step", "value": value, "unit": "zone-updates/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{WORKLOADS[args.workload][2]} {n}x{n}x{n * world}, steps {args.warmup}..{args.warmup + args.steps} from t=0",
+                       "zones_per_gpu": zones_local, "parallelism": f"x3-slabs x{world}",
+                       "ion_iterations_per_step": round(n_iter, 2), "l2": "working set >> L2 (state + scratch = "
+                       f"{G.bytes_allocated / 2**30:.1f} GiB per GPU), no flush needed", "setup_s": round(t_setup, 1)},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "kernels": ktab,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="ioniz_sphere", choices=sorted(WORKLOADS))
+    ap.add_argument("--n", type=int, default=256, help="zones per direction per GPU")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--cpu-n", type=int, default=64, help="grid of the bounded CPU sample")
+    ap.add_argument("--cpu-steps", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        print("bench.py: note: fewer than 3 warm-up steps", file=sys.stderr)
+    return reference_arm(args) if args.impl == "reference" else gpu_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

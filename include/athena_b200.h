@@ -116,6 +116,14 @@ double ab2_ion_entering_flux(double flux_i, double time);
 int ab2_ion_radtransfer_3d(ab2_grid* g, double flux_i, double time, double cour_no, double* dt,
                            int* niter, int* nchem, int* ntherm, ab2_reduce_fn reduce, void* ctx);
 
+/* ---- per-kernel device timing (bench.py's roofline) ------------------------------------------------------ */
+/* When enabled every kernel launch is bracketed by CUDA events on the launching stream; ab2_profile_read drains
+ * them into ms[id] / counts[id] (id < ab2_profile_kernels(), names from ab2_profile_kernel_name). */
+int ab2_profile_enable(ab2_grid* g, int on);
+int ab2_profile_kernels(void);
+const char* ab2_profile_kernel_name(int id);
+int ab2_profile_read(ab2_grid* g, double* ms, long long* counts, int reset);
+
 /* ---- function-level entry points (parity tests): rows of 6 doubles, host arrays ------------------------- */
 /* fluxes() of rsolvers/roe.c:59-336 (+ hlle.c fallback) on n independent interfaces */
 int ab2_unit_roe_flux(int n, const double* Ul, const double* Ur, const double* Wl, const double* Wr,
