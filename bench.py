@@ -94,7 +94,7 @@ class ClockSampler:
         self.lines = []
         self.p = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(index)],
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -252,12 +252,12 @@ def gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local) if rank == 0 else None     # started early: nvidia-smi takes ~1 s to emit its first sample
     for _ in range(args.warmup):
         R.step()
     barrier()
 
     # ---- timed region: K steps, state resident in HBM ----
-    sampler = ClockSampler(local) if rank == 0 else None
     G.profile_enable(True)
     G.profile_read(reset=True)
     l0 = G.kernel_launches
@@ -360,8 +360,8 @@ def gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="ioniz_sphere", choices=sorted(WORKLOADS))
     ap.add_argument("--n", type=int, default=256, help="zones per direction per GPU")

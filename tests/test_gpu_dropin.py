@@ -1,0 +1,52 @@
+"""Drop-in test: the reference's UNMODIFIED driver (main.c loop, par.c, problem file, restart dumps) linked
+against shim/athena_shim.c + libathena_b200.so (build/dropin/<cfg>/athena, built by shim/build_dropin.py in the
+container) runs the golden decks on the GPU; its restart dumps are compared with the reference's own."""
+import os
+import re
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from cases import Case, ROOT, DECKS
+from athena_b200.restart import read_restart
+
+pytestmark = pytest.mark.gpu
+
+
+def run_dropin(case):
+    exe = os.path.join(ROOT, "build", "dropin", case.build, "athena")
+    if not os.path.exists(exe):
+        pytest.skip("build/dropin not built (needs the reference sources: shim/build_dropin.py)")
+    with tempfile.TemporaryDirectory() as tmp:
+        cmd = [exe, "-i", os.path.join(DECKS, str(case.gold["deck"])), f"time/nlim={case.nsteps}"] + [str(x) for x in case.gold["overrides"]]
+        r = subprocess.run(cmd, cwd=tmp, capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        rst = sorted(f for f in os.listdir(tmp) if f.endswith(".rst"))
+        d1 = read_restart(os.path.join(tmp, rst[-1]))
+    rad = [int(a) for a in re.findall(r"Radiation done in (\d+) iterations", r.stderr)]
+    return d1, rad, r
+
+
+@pytest.mark.parametrize("name", ["blast16_k6", "blastmix_k5"])
+def test_dropin_hydro_bit_exact(name):
+    case = Case(name)
+    d1, _, _ = run_dropin(case)
+    assert d1["nstep"] == case.nsteps and d1["time"] == float(case.gold["time1"]) and d1["dt"] == float(case.gold["dt1"])
+    for v in case.U1:
+        assert np.array_equal(d1["grids"][0][v], case.U1[v]), v
+
+
+@pytest.mark.parametrize("name", ["ifront32_k4", "ioniz24_k3"])
+def test_dropin_ion(name):
+    case = Case(name)
+    d1, rad, r = run_dropin(case)
+    assert rad == [int(x) for x in case.gold["rad"][:, 0]]
+    assert abs(d1["time"] - float(case.gold["time1"])) <= 1e-9 * float(case.gold["time1"])
+    g = d1["grids"][0]
+    for v in ("d", "E", "s"):
+        assert np.allclose(g[v], case.U1[v], rtol=1e-9, atol=0), v
+    assert np.allclose(g["edgeflux"], case.gold["U1_edgeflux"], rtol=1e-9, atol=0)
+    if name.startswith("ioniz"):
+        assert "Userwork_in_loop replayed on the device" in r.stdout
