@@ -120,7 +120,7 @@ ab2_grid* ab2_grid_create(const ab2_grid_desc* d)
   h->prof_on = false;
   for (int n=0; n<KID_N; n++) { h->prof_ms[n] = 0.0; h->prof_cnt[n] = 0; }
   memset(&h->ion, 0, sizeof h->ion);
-  if (d->stream) { h->stream = (cudaStream_t)d->stream; h->own_stream = false; }
+  if (d->use_external_stream) { h->stream = (cudaStream_t)d->stream; h->own_stream = false; }
   else {
     if (!ab2_check(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), "cudaStreamCreate")) { delete h; return nullptr; }
     h->own_stream = true;

@@ -44,13 +44,19 @@ def exchange_x3_ghosts(U, rank: int, world: int, bc_ix3: int, bc_ox3: int, dist=
     hi = rank + 1 if rank < world - 1 else (0 if bc_ox3 == 4 else None)
     ops = []
     nvar = U.shape[0]
+    # Upward transfers first (send top active layers to hi / receive bottom ghosts from lo), then downward ones.
+    # With a 2-slab periodic ring both messages travel between the same pair of ranks and NCCL matches
+    # point-to-point calls by order, so every rank must post them in the same global order.
     for v in range(nvar):
         if hi is not None:
             ops.append(dist.P2POp(dist.isend, U[v, n3 - 2 * NG:n3 - NG], hi, group))
-            ops.append(dist.P2POp(dist.irecv, U[v, n3 - NG:n3], hi, group))
+        if lo is not None:
+            ops.append(dist.P2POp(dist.irecv, U[v, 0:NG], lo, group))
+    for v in range(nvar):
         if lo is not None:
             ops.append(dist.P2POp(dist.isend, U[v, NG:2 * NG], lo, group))
-            ops.append(dist.P2POp(dist.irecv, U[v, 0:NG], lo, group))
+        if hi is not None:
+            ops.append(dist.P2POp(dist.irecv, U[v, n3 - NG:n3], hi, group))
     if ops:
         for w in dist.batch_isend_irecv(ops):
             w.wait()

@@ -30,7 +30,7 @@ class GridDesc(C.Structure):
                 ("dx1", C.c_double), ("dx2", C.c_double), ("dx3", C.c_double),
                 ("x1min", C.c_double), ("x2min", C.c_double), ("x3min", C.c_double),
                 ("gamma", C.c_double), ("device", C.c_int), ("stream", C.c_void_p),
-                ("external_U", C.c_void_p * 6)]
+                ("use_external_stream", C.c_int), ("external_U", C.c_void_p * 6)]
 
 
 class IonPar(C.Structure):
@@ -138,13 +138,14 @@ class Grid:
         self.nvar = 5 + self.nscal
         self.shape = (self.nx[2] + 2 * NG, self.nx[1] + 2 * NG, self.nx[0] + 2 * NG)
         self.device = device
-        desc = GridDesc(self.nx[0], self.nx[1], self.nx[2], self.nscal, *self.dx, *self.xmin, float(gamma), device, None)
+        desc = GridDesc(self.nx[0], self.nx[1], self.nx[2], self.nscal, *self.dx, *self.xmin, float(gamma), device, None, 0)
         self.U_torch = None
         if torch_memory:
             import torch
             torch.cuda.set_device(device)
             self.U_torch = torch.zeros((self.nvar,) + self.shape, dtype=torch.float64, device=f"cuda:{device}")
             desc.stream = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+            desc.use_external_stream = 1
             for v in range(self.nvar):
                 desc.external_U[v] = self.U_torch[v].data_ptr()
             torch.cuda.synchronize(device)

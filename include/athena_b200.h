@@ -38,7 +38,9 @@ typedef struct ab2_grid_desc {
   double x1min, x2min, x3min;     /* GridS.MinX[0..2] (cc_pos.c)                                             */
   double gamma;                   /* globals.h: Gamma                                                        */
   int device;                     /* CUDA device ordinal                                                     */
-  void* stream;                   /* cudaStream_t to run on, or NULL: the library creates its own            */
+  void* stream;                   /* cudaStream_t to run on when use_external_stream != 0 (NULL is then the    */
+                                  /* legacy default stream, which is what torch hands out); otherwise ignored   */
+  int use_external_stream;        /* 0: the library creates its own non-blocking stream                        */
   double* external_U[6];          /* optional caller-owned DEVICE arrays for d,M1,M2,M3,E,s (all or none):    */
                                   /* lets a host framework (torch / NCCL) exchange ghost slabs in place        */
 } ab2_grid_desc;
