@@ -54,8 +54,18 @@ template <int DIR, int NS> __device__ __forceinline__ S6 sweep_from_phys(const d
 // ---------------------------------------------------------------------------------------------------
 #define A1_T 128
 #define A1_F (A1_T-3)
+// minimum resident blocks per SM (register caps), tuned on B200 at 256^3 (profiles/r1_tuning.md)
+#ifndef AB2_LB_FIRST
+#define AB2_LB_FIRST 4
+#endif
+#ifndef AB2_LB_FIRST_X1
+#define AB2_LB_FIRST_X1 5
+#endif
+#ifndef AB2_LB_FINAL
+#define AB2_LB_FINAL 5
+#endif
 template <int NS, bool GRAV>
-__global__ void __launch_bounds__(A1_T) k_first_x1(GridDev g, double dt)
+__global__ void __launch_bounds__(A1_T, AB2_LB_FIRST_X1) k_first_x1(GridDev g, double dt)
 {
   __shared__ double sW[6][A1_T];
   __shared__ double sL[6][A1_T];
@@ -107,7 +117,7 @@ __global__ void __launch_bounds__(A1_T) k_first_x1(GridDev g, double dt)
 // 3-cell sliding window of primitives in registers; the left state of the next face is carried over.
 // ---------------------------------------------------------------------------------------------------
 template <int DIR, int NS, bool GRAV>
-__global__ void __launch_bounds__(128) k_first_march(GridDev g, double dt, int seg)
+__global__ void __launch_bounds__(128, AB2_LB_FIRST) k_first_march(GridDev g, double dt, int seg)
 {
   const int il = NG-2, iu = g.nx[0]+NG+1;
   const int i = il + blockIdx.x*blockDim.x + threadIdx.x;
@@ -229,7 +239,7 @@ __global__ void __launch_bounds__(128) k_correct(GridDev g, Box b, double dt)
 // Pass D: final fluxes with the H-correction (integrate_3d_ctu.c:2350-2437)
 // ---------------------------------------------------------------------------------------------------
 template <int DIR, int NS>
-__global__ void __launch_bounds__(128) k_final(GridDev g, Box b)
+__global__ void __launch_bounds__(128, AB2_LB_FINAL) k_final(GridDev g, Box b)
 {
   int i,j,k; if (!box_cell(b,i,j,k)) return;
   const long c = (long)k*g.st[2] + (long)j*g.st[1] + i;

@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(128) k_ion_update(GridDev g, IonParDev p, IonD
   long c;
   const bool act = active_cell(g, c);
   unsigned long long count = 0;
-  double max_dti = 0.0;
+  double m1 = 0.0, m2 = 0.0, m3 = 0.0;
   if (act) {
     const double d = g.U[0][c], M1 = g.U[1][c], M2 = g.U[2][c], M3 = g.U[3][c];
     double E = g.U[4][c], s = g.U[5][c];
@@ -278,42 +278,54 @@ __global__ void __launch_bounds__(128) k_ion_update(GridDev g, IonParDev p, IonD
       E += ion.edot[c] * dt;
       s += nHdot * dt * p.m_H;
     }
-    floors(p, g.Gamma_1, d, M1, M2, M3, E, s);
-    g.U[4][c] = E; g.U[5][c] = s;
-
-    // check_range
-    const double n_H = s / p.m_H;
-    if (!(ion.ph_rate[c] / (p.min_area * n_H) > 2.0*CION)) {
-      const double e_thermal = E - kinetic(d,M1,M2,M3);
-      const double eth0 = ion.e_th_init[c], e0 = ion.e_init[c], x0 = ion.x_init[c];
-      if ((e_thermal / eth0 >= 1 + p.max_de_therm_step) || (eth0 / e_thermal >= 1 + p.max_de_therm_step)) count = 1;
-      else if ((p.max_de_step > 0) && ((E / e0 >= 1 + p.max_de_step) || (e0 / E >= 1 + p.max_de_step))) count = 1;
-      else if (p.max_dx_step > 0) {
-        const double n_Hplus = (d - s) / p.m_H;
-        const double n_e = n_Hplus + d * p.alpha_C / (14.0 * p.m_H);
-        const double x = n_e / (n_H + n_Hplus);
-        if ((x / x0 >= 1 + p.max_dx_step) || (x0 / x >= 1 + p.max_dx_step)) count = 1;
-      }
+    // floors (apply_temp_floor :70-136, apply_neutral_floor :140-157), keeping the cell's chemistry state: when no
+    // floor fires (the common case) check_range below re-evaluates the very same expressions on the same values,
+    // so the seven divisions are shared; when one fires they are recomputed from the floored E,s as the reference does
+    CellChem cs = chem_state(p, g.Gamma_1, d, M1, M2, M3, E, s);
+    bool changed = false;
+    if (cs.T < p.tfloor) {
+      const double e_sp = p.tfloor * p.k_B / ((cs.x*0.5*p.m_H+(1.0-cs.x)*p.mu) * g.Gamma_1);
+      E = kinetic(d,M1,M2,M3) + e_sp * d; changed = true;
     }
-    // compute_dt_hydro
+    if ((cs.T > p.tceil) && (p.tceil > 0)) {
+      const double e_sp = p.tceil * p.k_B / ((cs.x*0.5*p.m_H+(1.0-cs.x)*p.mu) * g.Gamma_1);
+      E = kinetic(d,M1,M2,M3) + e_sp * d; changed = true;
+    }
+    if (s < d_nlim) { s = d_nlim; changed = true; }
+    else if (s > d) { s = d; changed = true; }
+    g.U[4][c] = E; g.U[5][c] = s;
+    if (changed) cs = chem_state(p, g.Gamma_1, d, M1, M2, M3, E, s);
+
+    // check_range (ionrad_3d.c:222-264)
+    if (!(ion.ph_rate[c] / (p.min_area * cs.n_H) > 2.0*CION)) {
+      const double eth0 = ion.e_th_init[c], e0 = ion.e_init[c], x0 = ion.x_init[c];
+      if ((cs.e_thermal / eth0 >= 1 + p.max_de_therm_step) || (eth0 / cs.e_thermal >= 1 + p.max_de_therm_step)) count = 1;
+      else if ((p.max_de_step > 0) && ((E / e0 >= 1 + p.max_de_step) || (e0 / E >= 1 + p.max_de_step))) count = 1;
+      else if ((p.max_dx_step > 0) && ((cs.x / x0 >= 1 + p.max_dx_step) || (x0 / cs.x >= 1 + p.max_dx_step))) count = 1;
+    }
+    // compute_dt_hydro (:609-663): max over cells of (|v_d|+a)/dx_d.  Division by the positive constant dx_d is
+    // monotone under rounding, so max_c fl(x_c/dx) == fl((max_c x_c)/dx): keep three per-direction maxima here and
+    // divide once on the host (new_dt.c:126-161 has this very form).
     const double di = 1.0/d;
     const double v1 = M1*di, v2 = M2*di, v3 = M3*di;
     const double qsq = v1*v1 + v2*v2 + v3*v3;
     const double pr = AB2_MAX(g.Gamma_1*(E - 0.5*d*qsq), AB2_TINY);
     const double asq = g.Gamma*pr*di;
     const double a = sqrt(asq);
-    if (g.nx[0] > 1) max_dti = AB2_MAX(max_dti,(fabs(v1)+a)/g.dx[0]);
-    if (g.nx[1] > 1) max_dti = AB2_MAX(max_dti,(fabs(v2)+a)/g.dx[1]);
-    if (g.nx[2] > 1) max_dti = AB2_MAX(max_dti,(fabs(v3)+a)/g.dx[2]);
+    m1 = fabs(v1)+a; m2 = fabs(v2)+a; m3 = fabs(v3)+a;
   }
   for (int o=16; o>0; o>>=1) {
     count += __shfl_xor_sync(0xffffffffu, count, o);
-    const double y = __shfl_xor_sync(0xffffffffu, max_dti, o);
-    max_dti = AB2_MAX(max_dti, y);
+    double y;
+    y = __shfl_xor_sync(0xffffffffu, m1, o); m1 = AB2_MAX(m1, y);
+    y = __shfl_xor_sync(0xffffffffu, m2, o); m2 = AB2_MAX(m2, y);
+    y = __shfl_xor_sync(0xffffffffu, m3, o); m3 = AB2_MAX(m3, y);
   }
   if ((threadIdx.x & 31) == 0) {
     if (count) atomicAdd(&scal[SC_COUNT], count);
-    atomic_max_double(&scal[SC_MAX_DTI], max_dti);
+    atomic_max_double(&scal[SC_MAXV1], m1);
+    atomic_max_double(&scal[SC_MAXV2], m2);
+    atomic_max_double(&scal[SC_MAXV3], m3);
   }
 }
 
@@ -356,9 +368,10 @@ int ion_radtransfer(ab2_grid* h, double flux_in, double cour_no, double* dt_io, 
   int niter = 0, hydro_done = 0, nchem = 0, ntherm = 0;
   while (!hydro_done) {
     // rates + per-cell limits
+    h->h_scal[SC_MAXV1] = h->h_scal[SC_MAXV2] = h->h_scal[SC_MAXV3] = double_to_bits(0.0);
     h->h_scal[SC_DT_CHEM] = double_to_bits(LARGE); h->h_scal[SC_DT_THERM] = double_to_bits(LARGE);
     h->h_scal[SC_MAX_DTI] = double_to_bits(0.0); h->h_scal[SC_COUNT] = 0;
-    if (!ab2_check(cudaMemcpyAsync(h->d_scal + SC_DT_CHEM, h->h_scal + SC_DT_CHEM, 4*sizeof(unsigned long long),
+    if (!ab2_check(cudaMemcpyAsync(h->d_scal + SC_MAXV1, h->h_scal + SC_MAXV1, 7*sizeof(unsigned long long),
                                    cudaMemcpyHostToDevice, st), "ion scalars H2D")) return -1;
     AB2_LAUNCH(h, KID_ION_RATES, (k_ion_rates<<<rgrid, 128, 0, st>>>(g, p, h->ion, flux_in, h->d_scal)));
     if (!ab2_check(cudaMemcpyAsync(h->h_scal + SC_DT_CHEM, h->d_scal + SC_DT_CHEM, 2*sizeof(unsigned long long),
@@ -378,11 +391,12 @@ int ion_radtransfer(ab2_grid* h, double flux_in, double cour_no, double* dt_io, 
     AB2_LAUNCH(h, KID_ION_UPDATE, (k_ion_update<<<cgrid, 128, 0, st>>>(g, p, h->ion, dt, h->d_scal)));
     dt_done += dt;
     niter++;
-    if (!ab2_check(cudaMemcpyAsync(h->h_scal + SC_MAX_DTI, h->d_scal + SC_MAX_DTI, 2*sizeof(unsigned long long),
+    if (!ab2_check(cudaMemcpyAsync(h->h_scal + SC_MAXV1, h->d_scal + SC_MAXV1, 7*sizeof(unsigned long long),
                                    cudaMemcpyDeviceToHost, st), "ion scalars D2H")) return -1;
     if (!ab2_check(cudaStreamSynchronize(st), "ion update sync")) return -1;
     double cnt = (double)h->h_scal[SC_COUNT];
-    double mx = bits_to_double(h->h_scal[SC_MAX_DTI]);
+    double mx = 0.0;
+    for (int dd=0; dd<3; dd++) if (g.nx[dd] > 1) { const double x = bits_to_double(h->h_scal[SC_MAXV1+dd])/g.dx[dd]; mx = AB2_MAX(mx, x); }
     if (reduce) { reduce(&cnt, 1, 2, ctx); reduce(&mx, 1, 1, ctx); }
 
     if (cnt > MAXCELLCOUNT) { grid_dt = dt_done; break; }      // check_range (:982)

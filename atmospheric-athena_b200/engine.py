@@ -12,7 +12,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libathena_b200.so")
+LIB_PATH = os.environ.get("AB2_LIB") or os.path.join(_HERE, "csrc", "libathena_b200.so")   # AB2_LIB: tuning variants of the same library
 NG = 4
 VARS = ("d", "M1", "M2", "M3", "E", "s")
 dp = C.POINTER(C.c_double)
