@@ -833,6 +833,22 @@ void orc_integrate_3d_ctu(OrcGrid *g, double dt)
     fluxes(Ul3[c],Ur3[c],wl,wr,nscal,Gamma,Gamma_1,etah,&F3[c]);
   }
 
+  /*=== STEP 12e (SMR): keep the final fluxes, physical component order (:3076-3364) ===*/
+  {
+    int dir;
+    for (dir=0; dir<3; dir++) if (g->Fsave[dir] != NULL) {
+      const C1 *F = (dir == 0) ? F1 : (dir == 1) ? F2 : F3;
+      size_t c;
+      for (c=0; c<ncell; c++) {
+        double *o = g->Fsave[dir] + 6*c;
+        o[0] = F[c].d; o[4] = F[c].E; o[5] = F[c].s;
+        if (dir == 0) { o[1] = F[c].Mx; o[2] = F[c].My; o[3] = F[c].Mz; }
+        if (dir == 1) { o[1] = F[c].Mz; o[2] = F[c].Mx; o[3] = F[c].My; }
+        if (dir == 2) { o[1] = F[c].My; o[2] = F[c].Mz; o[3] = F[c].Mx; }
+      }
+    }
+  }
+
   /*=== STEP 11a: static gravity, full step (:2741-2782) ===*/
   if (Phi != NULL) {
     for (k=ks; k<=ke; k++) for (j=js; j<=je; j++) for (i=is; i<=ie; i++) {
@@ -1147,7 +1163,7 @@ static double compute_dt_hydro(IonCtx *c, double cour_no)                  /* :5
 }
 
 /* ionradplane_3d.c:88-407, dir = -1 branch (:253-322), root level */
-static void get_ph_rate_plane(IonCtx *c, double flux0, double *edgeflux)
+static void get_ph_rate_plane(IonCtx *c, double flux0, double *edgeflux, int finegrid)
 {
   OrcGrid *g = c->g; const OrcIonPar *p = c->p;
   const int e1 = g->nx1+1, e2 = g->nx2+1;
@@ -1156,7 +1172,7 @@ static void get_ph_rate_plane(IonCtx *c, double flux0, double *edgeflux)
   int i,j,k,ii;
   for (k=c->ks; k<=c->ke; k++) for (j=c->js; j<=c->je; j++) {
     double *ef = edgeflux + ((size_t)(k-c->ks)*e2 + (size_t)(j-c->js))*e1;
-    double flux = flux0, flux_frac = 0.0;
+    double flux = finegrid ? ef[fixed] : flux0, flux_frac = 0.0;      /* ionradplane_3d.c:263-272 */
     for (i=s; i<=e; i++) {
       size_t x = IDX(g,k,j,i);
       double n_H, tau, etau, kph;
@@ -1180,6 +1196,12 @@ static void get_ph_rate_plane(IonCtx *c, double flux0, double *edgeflux)
 int orc_ion_radtransfer(OrcGrid *g, const OrcIonPar *p, double flux_i, double time, double cour_no,
                         double *dt_io, double *edgeflux, int *nchem_out, int *ntherm_out)
 {
+  return orc_ion_radtransfer_root(g, p, flux_i, time, cour_no, dt_io, edgeflux, nchem_out, ntherm_out, NULL);
+}
+
+int orc_ion_radtransfer_root(OrcGrid *g, const OrcIonPar *p, double flux_i, double time, double cour_no,
+                             double *dt_io, double *edgeflux, int *nchem_out, int *ntherm_out, double *tcoarse_out)
+{
   IonCtx ctx, *c = &ctx;
   const size_t ncell = (size_t)N1(g)*N2(g)*N3(g);
   double dt_chem, dt_therm, dt_hydro, dt, dt_done, grid_dt = *dt_io;
@@ -1199,7 +1221,7 @@ int orc_ion_radtransfer(OrcGrid *g, const OrcIonPar *p, double flux_i, double ti
   dt_done = 0.0; hydro_done = 0; nchem = ntherm = 0;
   while (!hydro_done) {                                                    /* :919, root level */
     IONLOOP(c) c->ph_rate[IDX(g,k,j,i)] = 0.0;                             /* :922 */
-    get_ph_rate_plane(c, orc_ion_entering_flux(flux_i, time), edgeflux);   /* :929 */
+    get_ph_rate_plane(c, orc_ion_entering_flux(flux_i, time), edgeflux, 0);   /* :929 */
     dt_chem = compute_chem_rates(c);                                       /* :935 */
     dt_therm = compute_therm_rates(c);                                     /* :938 */
     if (dt_chem < dt_therm) nchem++; else ntherm++;
@@ -1216,6 +1238,7 @@ int orc_ion_radtransfer(OrcGrid *g, const OrcIonPar *p, double flux_i, double ti
     if (dt_hydro < dt_done) { grid_dt = dt_done; break; }
   }
   if (niter == p->maxiter) grid_dt = dt_done;                              /* :1022 */
+  if (tcoarse_out) *tcoarse_out = dt_done;                                 /* :1028 tcoarse = dt_done */
 
   free(c->ph_rate); free(c->edot); free(c->nHdot); free(c->e_init); free(c->e_th_init); free(c->x_init);
   free(c->last_sign); free(c->sign_count);
@@ -1223,4 +1246,208 @@ int orc_ion_radtransfer(OrcGrid *g, const OrcIonPar *p, double flux_i, double ti
   if (nchem_out) *nchem_out = nchem;
   if (ntherm_out) *ntherm_out = ntherm;
   return niter;
+}
+
+int orc_ion_radtransfer_fine(OrcGrid *g, const OrcIonPar *p, double tcoarse, double *dt_io, double *edgeflux,
+                             int *nchem_out, int *ntherm_out)
+{
+  IonCtx ctx, *c = &ctx;
+  const size_t ncell = (size_t)N1(g)*N2(g)*N3(g);
+  double dt_chem, dt_therm, dt, dt_done, grid_dt = *dt_io;
+  int niter = 0, coarsetime_done = 0, nchem = 0, ntherm = 0, i, j, k;
+
+  c->g = g; c->p = p; c->Gamma_1 = g->gamma - 1.0;
+  c->is = NG; c->ie = g->nx1+NG-1; c->js = NG; c->je = g->nx2+NG-1; c->ks = NG; c->ke = g->nx3+NG-1;
+  c->ph_rate = calloc(ncell,sizeof(double)); c->edot = calloc(ncell,sizeof(double));
+  c->nHdot = calloc(ncell,sizeof(double)); c->e_init = calloc(ncell,sizeof(double));
+  c->e_th_init = calloc(ncell,sizeof(double)); c->x_init = calloc(ncell,sizeof(double));
+  c->last_sign = calloc(ncell,sizeof(int)); c->sign_count = calloc(ncell,sizeof(int));
+
+  apply_temp_floor(c);
+  apply_neutral_floor(c);
+  save_energy_and_x(c);
+  dt_done = 0.0;
+  while (1) {                                                              /* :919 finegrid */
+    IONLOOP(c) c->ph_rate[IDX(g,k,j,i)] = 0.0;
+    get_ph_rate_plane(c, 0.0, edgeflux, 1);
+    dt_chem = compute_chem_rates(c);
+    dt_therm = compute_therm_rates(c);
+    if (dt_chem < dt_therm) nchem++; else ntherm++;
+    dt = MIN(dt_therm, dt_chem);
+    if (dt_done + dt > tcoarse) { dt = tcoarse - dt_done; coarsetime_done = 1; }   /* :958-961 */
+    ionization_update(c, dt);
+    dt_done += dt;
+    niter++;
+    apply_temp_floor(c);
+    apply_neutral_floor(c);
+    if (coarsetime_done) { grid_dt = dt_done; break; }                     /* :1008-1012 */
+  }
+  free(c->ph_rate); free(c->edot); free(c->nHdot); free(c->e_init); free(c->e_th_init); free(c->x_init);
+  free(c->last_sign); free(c->sign_count);
+  *dt_io = grid_dt;
+  if (nchem_out) *nchem_out = nchem;
+  if (ntherm_out) *ntherm_out = ntherm;
+  return niter;
+}
+
+/* ================================================================================================
+ * SMR: smr.c, ionrad_smr.c (one parent Grid, one child Grid, same process)
+ * ============================================================================================== */
+static double *var_of(const OrcGrid *g, int v)
+{
+  switch (v) { case 0: return g->d; case 1: return g->M1; case 2: return g->M2; case 3: return g->M3; case 4: return g->E; default: return g->s; }
+}
+
+/* 8-cell conservative average of variable v at child cells (k,j,i)..(+1): smr.c:1874-1964 summation order */
+static double restrict8(const OrcGrid *ch, int v, int k, int j, int i)
+{
+  const double *a = var_of(ch, v);
+  double sum = a[IDX(ch,k,j,i)] + a[IDX(ch,k,j,i+1)];
+  sum += a[IDX(ch,k,j+1,i)] + a[IDX(ch,k,j+1,i+1)];
+  sum += a[IDX(ch,k+1,j,i)] + a[IDX(ch,k+1,j,i+1)] + a[IDX(ch,k+1,j+1,i)] + a[IDX(ch,k+1,j+1,i+1)];
+  return sum*0.125;
+}
+
+static void restrict_inject(OrcGrid *pa, const OrcGrid *ch, const OrcOverlap *o, int v)
+{
+  int k,j,i,kk,jj,ii;
+  double *dst = var_of(pa, v);
+  for (k=o->cs[2], kk=NG; k<=o->ce[2]; k++, kk+=2)
+    for (j=o->cs[1], jj=NG; j<=o->ce[1]; j++, jj+=2)
+      for (i=o->cs[0], ii=NG; i<=o->ce[0]; i++, ii+=2)
+        dst[IDX(pa,k,j,i)] = restrict8(ch, v, kk, jj, ii);
+}
+
+void orc_ion_restrict(OrcGrid *pa, const OrcGrid *ch, const OrcOverlap *o)        /* smr.c:85-1205 */
+{
+  restrict_inject(pa, ch, o, 4);
+  restrict_inject(pa, ch, o, 5);
+}
+
+void orc_restrict_correct(OrcGrid *pa, const OrcGrid *ch, const OrcOverlap *o, double dt_parent)
+{
+  const int nvar = 5 + pa->nscal;
+  int v, dim, a, b;
+  for (v=0; v<nvar; v++) restrict_inject(pa, ch, o, v);                            /* Steps 3a, 1b */
+  /* Step 2a with Step 3c: flux correction of the coarse cells just outside the child (smr.c:1497-1577, 2019-2227) */
+  for (dim=0; dim<6; dim++) {
+    const int d = dim/2, side = dim%2;
+    const int t1 = (d == 0) ? 1 : 0, t2 = (d == 2) ? 1 : 2;      /* the two transverse axes, ascending */
+    const double dx = (d == 0) ? pa->dx1 : (d == 1) ? pa->dx2 : pa->dx3;
+    const double q = side ? (dt_parent/dx) : -(dt_parent/dx);
+    const int nch[3] = { ch->nx1, ch->nx2, ch->nx3 };
+    if (!o->face[dim]) continue;
+    for (b=o->cs[t2]; b<=o->ce[t2]; b++) for (a=o->cs[t1]; a<=o->ce[t1]; a++) {
+      int pc[3], pf[3], cf[3];                   /* parent cell to correct, parent face cell, child face cell (first of 2x2) */
+      size_t xc, xf, c00, c01, c10, c11;
+      pc[t1] = a; pc[t2] = b; pc[d] = side ? o->ce[d]+1 : o->cs[d]-1;
+      pf[t1] = a; pf[t2] = b; pf[d] = side ? o->ce[d]+1 : o->cs[d];
+      cf[t1] = NG + 2*(a - o->cs[t1]); cf[t2] = NG + 2*(b - o->cs[t2]); cf[d] = side ? NG + nch[d] : NG;
+      xc = IDX(pa,pc[2],pc[1],pc[0]); xf = IDX(pa,pf[2],pf[1],pf[0]);
+      c00 = IDX(ch,cf[2],cf[1],cf[0]);
+      { int e1[3] = {cf[0],cf[1],cf[2]}; e1[t1]++; c01 = IDX(ch,e1[2],e1[1],e1[0]); }
+      { int e2[3] = {cf[0],cf[1],cf[2]}; e2[t2]++; c10 = IDX(ch,e2[2],e2[1],e2[0]); }
+      { int e3[3] = {cf[0],cf[1],cf[2]}; e3[t1]++; e3[t2]++; c11 = IDX(ch,e3[2],e3[1],e3[0]); }
+      for (v=0; v<nvar; v++) {
+        const double *Fc = ch->Fsave[d], *Fp = pa->Fsave[d];
+        /* (f[b][a] + f[b][a+1]) + (f[b+1][a] + f[b+1][a+1]), x 0.25: smr.c:2046-2097 and the x2/x3 analogues */
+        double r = Fc[6*c00+v] + Fc[6*c01+v];
+        r += Fc[6*c10+v] + Fc[6*c11+v];
+        r *= 0.25;
+        var_of(pa,v)[xc] -= q*(Fp[6*xf+v] - r);
+      }
+    }
+  }
+}
+
+static double mcd_slope(double vl, double vc, double vr)                           /* smr.c:3478-3495 */
+{
+  double dvl = (vc - vl), dvr = (vr - vc), dv, dvm;
+  if (dvl > 0.0 && dvr > 0.0) {
+    dv = 2.0*(dvl < dvr ? dvl : dvr);
+    dvm = 0.5*(dvl + dvr);
+    return (dvm < dv ? dvm : dv);
+  } else if (dvl < 0.0 && dvr < 0.0) {
+    dv = 2.0*(dvl > dvr ? dvl : dvr);
+    dvm = 0.5*(dvl + dvr);
+    return (dvm > dv ? dvm : dv);
+  }
+  return 0.0;
+}
+
+static double pres_like(const OrcGrid *g, size_t x)                                /* smr.c:3209: E - KE (not x Gamma_1) */
+{
+  return g->E[x] - 0.5*(SQR(g->M1[x]) + SQR(g->M2[x]) + SQR(g->M3[x]))/g->d[x];
+}
+
+/* ProCon (smr.c:3068-3325) for the coarse cell (pk,pj,pi) of the parent, written to the 2x2x2 child cells at (ck,cj,ci) */
+static void procon(const OrcGrid *pa, int pk, int pj, int pi, OrcGrid *ch, int ck, int cj, int ci)
+{
+  const size_t x0 = IDX(pa,pk,pj,pi), xim = IDX(pa,pk,pj,pi-1), xip = IDX(pa,pk,pj,pi+1);
+  const size_t xjm = IDX(pa,pk,pj-1,pi), xjp = IDX(pa,pk,pj+1,pi), xkm = IDX(pa,pk-1,pj,pi), xkp = IDX(pa,pk+1,pj,pi);
+  const int nvar = 5 + pa->nscal;
+  int v, i, j, k;
+  double PC[2][2][2][6];
+  for (v=0; v<nvar; v++) {
+    double dq1, dq2, dq3, base;
+    if (v == 4) {
+      const double Pi = pres_like(pa,x0);
+      dq1 = mcd_slope(pres_like(pa,xim), Pi, pres_like(pa,xip));
+      dq2 = mcd_slope(pres_like(pa,xjm), Pi, pres_like(pa,xjp));
+      dq3 = mcd_slope(pres_like(pa,xkm), Pi, pres_like(pa,xkp));
+      base = Pi;
+    } else {
+      const double *a = var_of(pa, v);
+      dq1 = mcd_slope(a[xim], a[x0], a[xip]);
+      dq2 = mcd_slope(a[xjm], a[x0], a[xjp]);
+      dq3 = mcd_slope(a[xkm], a[x0], a[xkp]);
+      base = a[x0];
+    }
+    for (k=0; k<2; k++) for (j=0; j<2; j++) for (i=0; i<2; i++)
+      PC[k][j][i][v] = base + (0.5*i - 0.25)*dq1 + (0.5*j - 0.25)*dq2 + (0.5*k - 0.25)*dq3;
+  }
+  for (k=0; k<2; k++) for (j=0; j<2; j++) for (i=0; i<2; i++) {
+    double *c = PC[k][j][i];
+    c[4] += 0.5*(SQR(c[1]) + SQR(c[2]) + SQR(c[3]))/c[0];                          /* :3240 */
+    for (v=0; v<nvar; v++) var_of(ch,v)[IDX(ch,ck+k,cj+j,ci+i)] = c[v];
+  }
+}
+
+void orc_prolongate(const OrcGrid *pa, OrcGrid *ch, const OrcOverlap *o)           /* smr.c:2359-2923 */
+{
+  const int ps0[3] = { NG, NG, NG }, pe0[3] = { ch->nx1+NG-1, ch->nx2+NG-1, ch->nx3+NG-1 };   /* PGrid.ijks/ijke on the child */
+  int dim, a;
+  for (dim=0; dim<6; dim++) {
+    int cs[3], ps[3], pe[3], k, j, i, kk, jj, ii;
+    if (!o->face[dim]) continue;
+    for (a=0; a<3; a++) {
+      cs[a] = o->cs[a] - (NG/2) - 1;             /* parent slab start (:2442-2463) */
+      ps[a] = ps0[a] - NG; pe[a] = pe0[a] + NG;  /* child ghost box (:2667-2688) */
+    }
+    if (dim%2 == 0) pe[dim/2] = ps0[dim/2] - 1;
+    else { ps[dim/2] = pe0[dim/2] + 1; cs[dim/2] = o->ce[dim/2]; }
+    for (k=ps[2], kk=1; k<=pe[2]; k+=2, kk++)
+      for (j=ps[1], jj=1; j<=pe[1]; j+=2, jj++)
+        for (i=ps[0], ii=1; i<=pe[0]; i+=2, ii++)
+          procon(pa, cs[2]+kk, cs[1]+jj, cs[0]+ii, ch, k, j, i);
+  }
+}
+
+void orc_ion_prolong(const OrcGrid *pa, const double *efp, const OrcGrid *ch, double *efc, const OrcOverlap *o)
+{ /* ionrad_smr.c:345-459 (snd, dim 0) + :34-343 (rcv, serial branch: indices valid for a root-level parent) */
+  const int pe1 = pa->nx1+1, pe2 = pa->nx2+1, ce1 = ch->nx1+1, ce2 = ch->nx2+1;
+  const int fixed_p = o->cs[0] - NG, fixed_c = 0;
+  int k, j;
+  if (!o->face[0]) return;
+  for (k=o->cs[2]-NG; k<=o->ce[2]+1-NG; k++) for (j=o->cs[1]-NG; j<=o->ce[1]+1-NG; j++) {
+    const double val = efp[((size_t)k*pe2 + j)*pe1 + fixed_p];
+    const int ks = k*2 - o->cdisp[2], js = j*2 - o->cdisp[1];
+#define EFC(kk,jj) efc[((size_t)(kk)*ce2 + (jj))*ce1 + fixed_c]
+    EFC(ks,js) = val;
+    if (j < (o->ce[1]+1-NG)) {
+      if (k < (o->ce[2]+1-NG)) { EFC(ks+1,js+1) = val; EFC(ks,js+1) = val; EFC(ks+1,js) = val; }
+      else EFC(ks,js+1) = val;
+    } else if (k < (o->ce[2]+1-NG)) EFC(ks+1,js) = val;
+#undef EFC
+  }
 }

@@ -33,7 +33,20 @@ typedef struct OrcGrid {
   double gamma;        /* ratio of specific heats (globals.h: Gamma)     */
   double *d, *M1, *M2, *M3, *E, *s; /* [n3][n2][n1] with ghosts          */
   OrcGravPot grav;     /* StaticGravPot (globals.h:24) or NULL           */
+  double *Fsave[3];    /* optional: final x1/x2/x3 fluxes of the last orc_integrate_3d_ctu call, [cell][6] in
+                        * PHYSICAL component order (d,M1,M2,M3,E,s) -- what step 12e (integrate_3d_ctu.c:3076-3364)
+                        * copies into CGrid/PGrid[].myFlx for SMR.  NULL: not kept.                             */
 } OrcGrid;
+
+/* Overlap of ONE child Grid with ONE parent Grid (GridOvrlpS, athena.h:258-275; built by init_grid.c:300-1180),
+ * single Grid per Domain: cs/ce = CGrid.ijks/ijke on the PARENT (local indices incl. ghosts); the child's own
+ * overlap is its whole active region.  face[6]: 1 where the fine/coarse boundary is interior to the root Domain
+ * (myFlx[dim] != NULL, init_grid.c:508-510, 624-626).  cdisp = child Domain Disp (child-level cells). */
+typedef struct OrcOverlap {
+  int cs[3], ce[3];
+  int face[6];
+  int cdisp[3];
+} OrcOverlap;
 
 typedef struct OrcIonPar {           /* <ionradiation> block, ionrad_3d.c:742-757 */
   double sigma_ph, m_H, mu, e_gamma, alpha_C, k_B, time_unit;
@@ -85,6 +98,26 @@ double orc_ion_entering_flux(double flux_i, double time);
  * edgeflux: [nx3+1][nx2+1][nx1+1].  *dt is pGrid->dt on entry and on exit.  Returns niter. */
 int orc_ion_radtransfer(OrcGrid *g, const OrcIonPar *p, double flux_i, double time, double cour_no,
                         double *dt, double *edgeflux, int *nchem, int *ntherm);
+
+/* as orc_ion_radtransfer, also returning tcoarse = dt_done (ionrad_3d.c:1028) for the finer levels */
+int orc_ion_radtransfer_root(OrcGrid *g, const OrcIonPar *p, double flux_i, double time, double cour_no,
+                             double *dt, double *edgeflux, int *nchem, int *ntherm, double *tcoarse);
+
+/* ---- SMR (smr.c, ionrad_smr.c), one parent + one child on the same process --------------------------- */
+/* RestrictCorrect (smr.c:1207-2352): restrict child solution + boundary fluxes, inject, flux-correct the parent.
+ * Needs Fsave on both grids (zeros before the first step, as the reference's calloc'ed myFlx). */
+void orc_restrict_correct(OrcGrid *parent, const OrcGrid *child, const OrcOverlap *o, double dt_parent);
+/* ionradRestrictCorrect (smr.c:85-1205): E and s[0] only, no flux correction */
+void orc_ion_restrict(OrcGrid *parent, const OrcGrid *child, const OrcOverlap *o);
+/* Prolongate (smr.c:2359-2923) with ProCon (:3068-3325), mcd_slope (:3478-3495) */
+void orc_prolongate(const OrcGrid *parent, OrcGrid *child, const OrcOverlap *o);
+/* ionrad_prolong_snd + ionrad_prolong_rcv (ionrad_smr.c:345-459, 34-343, serial branch), dim = 0 */
+void orc_ion_prolong(const OrcGrid *parent, const double *edgeflux_parent, const OrcGrid *child,
+                     double *edgeflux_child, const OrcOverlap *o);
+/* ion_radtransfer_3d on a fine level (ionrad_3d.c:919-1014 with finegrid = 1): sub-cycles to tcoarse with the
+ * entering flux of each ray taken from edgeflux[k][j][0].  *dt returns GridS.dt = dt_done.  Returns niter. */
+int orc_ion_radtransfer_fine(OrcGrid *g, const OrcIonPar *p, double tcoarse, double *dt, double *edgeflux,
+                             int *nchem, int *ntherm);
 
 #ifdef __cplusplus
 }

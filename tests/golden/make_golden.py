@@ -44,6 +44,13 @@ CASES = {
                  ["domain1/Nx1=32", "domain1/Nx2=16", "domain1/Nx3=16"], [1, 4]),
     "ioniz24": ("ioniz_sphere", "ioniz_sphere.athinput",
                 ["domain1/Nx1=24", "domain1/Nx2=24", "domain1/Nx3=24"], [1, 3]),
+    # two-level SMR (root + one level-1 Domain, both single Grid); builds configured with --enable-smr
+    "blastsmr": ("blast_smr", "blast.athinput",
+                 ["job/num_domains=2", "domain1/Nx1=16", "domain1/Nx2=16", "domain1/Nx3=16", "problem/radius=0.25",
+                  "domain2/Nx1=16", "domain2/Nx2=12", "domain2/Nx3=8", "domain2/iDisp=8", "domain2/jDisp=10", "domain2/kDisp=12"], [1, 4]),
+    "ifrontsmr": ("ifront_smr", "ifront.athinput",
+                  ["job/num_domains=2", "domain1/Nx1=32", "domain1/Nx2=16", "domain1/Nx3=16",
+                   "domain2/Nx1=24", "domain2/Nx2=16", "domain2/Nx3=16", "domain2/iDisp=8", "domain2/jDisp=8", "domain2/kDisp=8"], [1, 3]),
 }
 
 
@@ -74,6 +81,9 @@ def make_runs():
             out = {}
             pack("U0", d0["grids"][0], out)
             pack("U1", d1["grids"][0], out)
+            for lev in range(1, len(d0["grids"])):
+                pack(f"U0L{lev}", d0["grids"][lev], out)
+                pack(f"U1L{lev}", d1["grids"][lev], out)
             out["dt0"] = d0["dt"]; out["time0"] = d0["time"]
             out["dt1"] = d1["dt"]; out["time1"] = d1["time"]; out["nstep1"] = d1["nstep"]
             out["next_dt"] = np.array(next_dt)
@@ -137,9 +147,14 @@ if __name__ == "__main__":
     spec = importlib.util.spec_from_file_location("build_ref", os.path.join(ROOT, "oracle", "build_ref.py"))
     br = importlib.util.module_from_spec(spec); spec.loader.exec_module(br)
     if os.path.isdir(os.path.join(br.REF, "src")):
-        for c in ("ifront", "ioniz_sphere", "blast"):
+        for c in ("ifront", "ioniz_sphere", "blast", "ifront_smr", "blast_smr"):
             br.build(c)
         for c in ("ifront", "blast"):
             br.build_units(c)
+    only = sys.argv[1:]
+    if only:
+        CASES = {k: v for k, v in CASES.items() if k in only}
+        globals()["CASES"] = CASES
     make_runs()
-    make_units()
+    if not only:
+        make_units()

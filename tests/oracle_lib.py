@@ -20,7 +20,11 @@ class OrcGrid(C.Structure):
                 ("x1min", C.c_double), ("x2min", C.c_double), ("x3min", C.c_double),
                 ("gamma", C.c_double),
                 ("d", dp), ("M1", dp), ("M2", dp), ("M3", dp), ("E", dp), ("s", dp),
-                ("grav", C.c_void_p)]
+                ("grav", C.c_void_p), ("Fsave", dp * 3)]
+
+
+class OrcOverlap(C.Structure):
+    _fields_ = [("cs", C.c_int * 3), ("ce", C.c_int * 3), ("face", C.c_int * 6), ("cdisp", C.c_int * 3)]
 
 
 class OrcIonPar(C.Structure):
@@ -65,6 +69,15 @@ def lib():
         L.orc_ion_radtransfer.argtypes = [gp, C.POINTER(OrcIonPar), C.c_double, C.c_double, C.c_double,
                                           dp, dp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.orc_ion_radtransfer.restype = C.c_int
+        L.orc_ion_radtransfer_root.argtypes = L.orc_ion_radtransfer.argtypes + [dp]
+        L.orc_ion_radtransfer_root.restype = C.c_int
+        op = C.POINTER(OrcOverlap)
+        L.orc_restrict_correct.argtypes = [gp, gp, op, C.c_double]
+        L.orc_ion_restrict.argtypes = [gp, gp, op]
+        L.orc_prolongate.argtypes = [gp, gp, op]
+        L.orc_ion_prolong.argtypes = [gp, dp, gp, dp, op]
+        L.orc_ion_radtransfer_fine.argtypes = [gp, C.POINTER(OrcIonPar), C.c_double, dp, dp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.orc_ion_radtransfer_fine.restype = C.c_int
         _lib = L
     return _lib
 
@@ -79,9 +92,9 @@ VARS = ("d", "M1", "M2", "M3", "E", "s")
 class OracleGrid:
     """SoA state with ghosts + the scalars the reference keeps in MeshS/GridS."""
 
-    def __init__(self, nx, xmin, xmax, gamma, nscal, bc, grav=None):
+    def __init__(self, nx, xmin, xmax, gamma, nscal, bc, grav=None, dx=None, keep_fluxes=False):
         self.nx = tuple(int(n) for n in nx)                     # (Nx1,Nx2,Nx3)
-        self.dx = tuple((xmax[a] - xmin[a]) / self.nx[a] for a in range(3))   # init_mesh.c: dx = (max-min)/Nx
+        self.dx = tuple(dx) if dx is not None else tuple((xmax[a] - xmin[a]) / self.nx[a] for a in range(3))   # init_mesh.c: dx = (max-min)/Nx
         self.xmin = tuple(xmin)
         self.gamma, self.nscal = float(gamma), int(nscal)
         self.bc = (C.c_int * 6)(*bc)
@@ -93,6 +106,11 @@ class OracleGrid:
                          C.cast(grav, C.c_void_p) if grav is not None else None)
         self.edgeflux = np.zeros((self.nx[2] + 1, self.nx[1] + 1, self.nx[0] + 1))
         self.time, self.dt, self.nstep = 0.0, 0.0, 0
+        self.Fsave = None
+        if keep_fluxes:                                         # SMR: myFlx source, zero before the first step (calloc)
+            self.Fsave = [np.zeros(shp + (6,)) for _ in range(3)]
+            for a in range(3):
+                self.g.Fsave[a] = P(self.Fsave[a])
 
     def active(self, v):
         return self.U[v][NG:-NG, NG:-NG, NG:-NG]
@@ -116,11 +134,25 @@ class OracleGrid:
 
     def ion_radtransfer(self, ionpar, flux_i, cour_no):
         dt = C.c_double(self.dt)
+        nchem, ntherm, tc = C.c_int(0), C.c_int(0), C.c_double(0.0)
+        niter = lib().orc_ion_radtransfer_root(C.byref(self.g), C.byref(ionpar), flux_i, self.time, cour_no,
+                                               C.byref(dt), P(self.edgeflux), C.byref(nchem), C.byref(ntherm), C.byref(tc))
+        self.dt = dt.value
+        self.tcoarse = tc.value
+        return niter, ntherm.value, nchem.value
+
+    def ion_radtransfer_fine(self, ionpar, tcoarse):
+        dt = C.c_double(self.dt)
         nchem, ntherm = C.c_int(0), C.c_int(0)
-        niter = lib().orc_ion_radtransfer(C.byref(self.g), C.byref(ionpar), flux_i, self.time, cour_no,
-                                          C.byref(dt), P(self.edgeflux), C.byref(nchem), C.byref(ntherm))
+        niter = lib().orc_ion_radtransfer_fine(C.byref(self.g), C.byref(ionpar), tcoarse, C.byref(dt), P(self.edgeflux),
+                                               C.byref(nchem), C.byref(ntherm))
         self.dt = dt.value
         return niter, ntherm.value, nchem.value
+
+    def max_speeds(self):
+        v = (C.c_double * 3)()
+        lib().orc_max_speeds(C.byref(self.g), v)
+        return tuple(v)
 
 
 def ion_par_from(par, dx):
@@ -152,3 +184,68 @@ def run_main_loop(G, nsteps, cour_no, tlim, ionpar=None, flux_i=0.0, userwork=No
         G.bvals()
         if log is not None:
             log.setdefault("next_dt", []).append(G.dt)
+
+
+def make_overlap(parent_nx, child_nx, child_disp, root_nx, level=1):
+    """CGrid.ijks/ijke and the myFlx != NULL pattern of init_grid.c:395-660 for a root-level parent (Disp 0) and a
+    single-Grid child Domain at `level` with displacement child_disp (child-level cells)."""
+    o = OrcOverlap()
+    ref = 2 ** level
+    for a in range(3):
+        o.cs[a] = child_disp[a] // 2 + NG
+        o.ce[a] = (child_disp[a] + child_nx[a]) // 2 + NG - 1
+        o.cdisp[a] = child_disp[a]
+        o.face[2 * a] = 1 if child_disp[a] != 0 else 0
+        o.face[2 * a + 1] = 1 if (child_disp[a] + child_nx[a]) // ref != root_nx[a] else 0
+    return o
+
+
+def run_main_loop_smr(root, child, o, nsteps, cour_no, tlim, ionpar=None, flux_i=0.0, log=None):
+    """main.c:519-669 with STATIC_MESH_REFINEMENT for a root Grid and one level-1 Grid.  Both must hold problem()
+    data, ghost zones (bvals + Prolongate) and the first dt.  Mesh scalars live on `root` (time, nstep) and in
+    mesh['dt']."""
+    L = lib()
+    mesh_dt = root.dt
+    for _ in range(nsteps):
+        if root.time >= tlim:
+            break
+        if ionpar is not None:
+            r0 = root.ion_radtransfer(ionpar, flux_i, cour_no)
+            mesh_dt = root.dt
+            root.bvals()
+            L.orc_ion_prolong(C.byref(root.g), P(root.edgeflux), C.byref(child.g), P(child.edgeflux), C.byref(o))
+            r1 = child.ion_radtransfer_fine(ionpar, root.tcoarse)
+            mesh_dt = child.dt                                   # ionrad_3d.c:1033 pMesh->dt = pGrid->dt
+            child.bvals()
+            L.orc_ion_restrict(C.byref(root.g), C.byref(child.g), C.byref(o))
+            if log is not None:
+                log.setdefault("rad", []).extend([r0 + (root.dt,), r1 + (child.dt,)])
+        root.integrate()
+        child.integrate()
+        L.orc_restrict_correct(C.byref(root.g), C.byref(child.g), C.byref(o), root.dt)
+        root.nstep += 1
+        root.time += mesh_dt
+        child.time = root.time
+        mesh_dt = new_dt_smr([root, child], cour_no, mesh_dt, root.nstep, root.time, tlim)
+        root.bvals(); child.bvals()
+        L.orc_prolongate(C.byref(root.g), C.byref(child.g), C.byref(o))
+        if log is not None:
+            log.setdefault("next_dt", []).append(mesh_dt)
+    return mesh_dt
+
+
+def new_dt_smr(grids, cour_no, dt_old, nstep, time, tlim):
+    """new_dt.c:58-195 over all levels: one dt for the whole Mesh."""
+    max_dti = 0.0
+    for G in grids:
+        v = G.max_speeds()
+        for a in range(3):
+            if G.nx[a] > 1:
+                x = v[a] / G.dx[a]
+                max_dti = max_dti if max_dti > x else x
+    dt = cour_no / max_dti if nstep == 0 else min(2.0 * dt_old, cour_no / max_dti)
+    if time < tlim and (tlim - time) < dt:
+        dt = tlim - time
+    for G in grids:
+        G.dt = dt
+    return dt
