@@ -49,7 +49,8 @@ __global__ void k_soa_to_aos(GridDev g, int nvar, long ncell, double* aos)
 static const char* KERNEL_NAMES[KID_N] = {
   "k_bvals", "k_max_speeds", "k_first_x1", "k_first_march<1>", "k_first_march<2>", "k_dhalf",
   "k_correct<0>", "k_correct<1>", "k_correct<2>", "k_final<0>", "k_final<1>", "k_final<2>", "k_update",
-  "k_apply_fixed", "k_ion_prep", "k_ion_rates", "k_ion_update", "k_bvals_ionrad", "k_transpose" };
+  "k_apply_fixed", "k_ion_prep", "k_ion_rates", "k_ion_update", "k_bvals_ionrad", "k_transpose",
+  "k_smr_restrict", "k_smr_flux_correct", "k_smr_prolongate" };
 
 cudaEvent_t ab2_prof_event(ab2_grid* h)
 {
@@ -116,7 +117,7 @@ ab2_grid* ab2_grid_create(const ab2_grid_desc* d)
   memset(&h->g, 0, sizeof h->g);
   h->nscal = d->nscal; h->device = d->device;
   h->has_grav = false; h->has_ion = false; h->n_fixed = 0; h->d_fixed_cells = nullptr; h->d_fixed_vals = nullptr;
-  h->bytes_allocated = 0; h->launches = 0; h->maxiter = 0;
+  h->bytes_allocated = 0; h->launches = 0; h->maxiter = 0; h->tcoarse = 0.0;
   h->prof_on = false;
   for (int n=0; n<KID_N; n++) { h->prof_ms[n] = 0.0; h->prof_cnt[n] = 0; }
   memset(&h->ion, 0, sizeof h->ion);
@@ -405,5 +406,14 @@ int ab2_ion_radtransfer_3d(ab2_grid* h, double flux_i, double time, double cour_
   if (!h->has_ion) { ab2_set_error("[ab2_ion_radtransfer_3d]: ab2_ion_init not called"); return -1; }
   return ion_radtransfer(h, ab2_ion_entering_flux(flux_i, time), cour_no, dt, niter, nchem, ntherm, reduce, ctx);
 }
+
+int ab2_ion_radtransfer_3d_fine(ab2_grid* h, double tcoarse, double* dt, int* niter, int* nchem, int* ntherm,
+                                ab2_reduce_fn reduce, void* ctx)
+{
+  if (!h->has_ion) { ab2_set_error("[ab2_ion_radtransfer_3d_fine]: ab2_ion_init not called"); return -1; }
+  return ion_radtransfer_fine(h, tcoarse, dt, niter, nchem, ntherm, reduce, ctx);
+}
+
+double ab2_ion_coarse_time(const ab2_grid* h) { return h->tcoarse; }
 
 } // extern "C"

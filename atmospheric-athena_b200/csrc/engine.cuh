@@ -71,7 +71,8 @@ typedef void (*ab2_reduce_fn_t)(double* vals, int n, int op, void* ctx);
 enum {
   KID_BVALS = 0, KID_MAX_SPEEDS, KID_FIRST_X1, KID_FIRST_X2, KID_FIRST_X3, KID_DHALF,
   KID_CORRECT_X1, KID_CORRECT_X2, KID_CORRECT_X3, KID_FINAL_X1, KID_FINAL_X2, KID_FINAL_X3, KID_UPDATE,
-  KID_APPLY_FIXED, KID_ION_PREP, KID_ION_RATES, KID_ION_UPDATE, KID_BVALS_IONRAD, KID_TRANSPOSE, KID_N
+  KID_APPLY_FIXED, KID_ION_PREP, KID_ION_RATES, KID_ION_UPDATE, KID_BVALS_IONRAD, KID_TRANSPOSE,
+  KID_SMR_RESTRICT, KID_SMR_FLUXCORR, KID_SMR_PROLONG, KID_N
 };
 struct ProfPending { int id; cudaEvent_t a, b; };
 
@@ -90,6 +91,7 @@ struct ab2_grid {
   IonParDev ionpar;
   IonDev ion;
   int maxiter;
+  double tcoarse;                  // ionrad_3d.c:1028: dt_done of the last root-level radiation call
   long n_fixed;                    // Userwork_in_loop replay table
   long* d_fixed_cells;
   double* d_fixed_vals;
@@ -125,3 +127,5 @@ int hydro_apply_fixed(ab2_grid* h);
 int ion_bvals_ionrad(ab2_grid* h, double flux_i);
 int ion_radtransfer(ab2_grid* h, double flux_in, double cour_no, double* dt_io, int* niter, int* nchem, int* ntherm,
                     ab2_reduce_fn_t reduce, void* ctx);
+int ion_radtransfer_fine(ab2_grid* h, double tcoarse, double* dt_io, int* niter, int* nchem, int* ntherm,
+                         ab2_reduce_fn_t reduce, void* ctx);

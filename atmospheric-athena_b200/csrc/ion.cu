@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(128) k_ion_prep(GridDev g, IonParDev p, IonDev
 // ---------------------------------------------------------------------------------------------------
 // k_ion_rates: ray trace (ionradplane_3d.c:254-310) + chem rates (ionrad_3d.c:307-394) + therm rates (:433-550)
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_ion_rates(GridDev g, IonParDev p, IonDev ion, double flux_in, unsigned long long* scal)
+__global__ void __launch_bounds__(128) k_ion_rates(GridDev g, IonParDev p, IonDev ion, double flux_in_root, int finegrid, unsigned long long* scal)
 {
   const int lane = threadIdx.x & 31;
   const long ray = (long)blockIdx.x*(blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -132,6 +132,8 @@ __global__ void __launch_bounds__(128) k_ion_rates(GridDev g, IonParDev p, IonDe
   const double dx1 = g.dx[0];
   const int nx1 = g.nx[0];
 
+  // root level: the time-ramped plane flux; finer levels: the value handed down into EdgeFlux[k][j][0] (ionradplane_3d.c:263-272)
+  const double flux_in = finegrid ? ef[0] : flux_in_root;
   double carry = flux_in;         // flux entering the current chunk
   bool alive = true;              // false once the ray has been cut
   double dt_chem_min = LARGE, dt_therm_min = LARGE;
@@ -351,8 +353,24 @@ static inline unsigned long long double_to_bits(double v) { unsigned long long b
 // face (the caller evaluates the reference's time ramp, ionradplane_3d.c:265).  reduce(vals,n,op,ctx) combines
 // sub-cycle scalars across the Grids of a Domain (op 0 MIN, 1 MAX, 2 SUM): the MPI_Allreduce sites of
 // ionrad_3d.c:275,399,554,672; NULL for a single Grid.
+static int ion_radtransfer_impl(ab2_grid* h, int finegrid, double flux_in, double cour_no, double tcoarse, double* dt_io,
+                                int* niter_out, int* nchem_out, int* ntherm_out, ab2_reduce_fn_t reduce, void* ctx);
+
 int ion_radtransfer(ab2_grid* h, double flux_in, double cour_no, double* dt_io, int* niter_out, int* nchem_out, int* ntherm_out,
                     ab2_reduce_fn_t reduce, void* ctx)
+{
+  return ion_radtransfer_impl(h, 0, flux_in, cour_no, 0.0, dt_io, niter_out, nchem_out, ntherm_out, reduce, ctx);
+}
+
+// fine level (ionrad_3d.c:919-1014 with finegrid = 1): sub-cycle until the coarse time is reached; no check_range / dt_hydro stop
+int ion_radtransfer_fine(ab2_grid* h, double tcoarse, double* dt_io, int* niter_out, int* nchem_out, int* ntherm_out,
+                         ab2_reduce_fn_t reduce, void* ctx)
+{
+  return ion_radtransfer_impl(h, 1, 0.0, 0.0, tcoarse, dt_io, niter_out, nchem_out, ntherm_out, reduce, ctx);
+}
+
+static int ion_radtransfer_impl(ab2_grid* h, int finegrid, double flux_in, double cour_no, double tcoarse, double* dt_io,
+                                int* niter_out, int* nchem_out, int* ntherm_out, ab2_reduce_fn_t reduce, void* ctx)
 {
   GridDev& g = h->g;
   cudaStream_t st = h->stream;
@@ -365,15 +383,15 @@ int ion_radtransfer(ab2_grid* h, double flux_in, double cour_no, double* dt_io, 
   AB2_LAUNCH(h, KID_ION_PREP, (k_ion_prep<<<cgrid, 128, 0, st>>>(g, p, h->ion)));
 
   double grid_dt = *dt_io, dt_done = 0.0, dt = 0.0, dt_chem = 0.0, dt_therm = 0.0, dt_hydro = 0.0;
-  int niter = 0, hydro_done = 0, nchem = 0, ntherm = 0;
-  while (!hydro_done) {
+  int niter = 0, hydro_done = 0, nchem = 0, ntherm = 0, coarsetime_done = 0;
+  while (finegrid || !hydro_done) {
     // rates + per-cell limits
     h->h_scal[SC_MAXV1] = h->h_scal[SC_MAXV2] = h->h_scal[SC_MAXV3] = double_to_bits(0.0);
     h->h_scal[SC_DT_CHEM] = double_to_bits(LARGE); h->h_scal[SC_DT_THERM] = double_to_bits(LARGE);
     h->h_scal[SC_MAX_DTI] = double_to_bits(0.0); h->h_scal[SC_COUNT] = 0;
     if (!ab2_check(cudaMemcpyAsync(h->d_scal + SC_MAXV1, h->h_scal + SC_MAXV1, 7*sizeof(unsigned long long),
                                    cudaMemcpyHostToDevice, st), "ion scalars H2D")) return -1;
-    AB2_LAUNCH(h, KID_ION_RATES, (k_ion_rates<<<rgrid, 128, 0, st>>>(g, p, h->ion, flux_in, h->d_scal)));
+    AB2_LAUNCH(h, KID_ION_RATES, (k_ion_rates<<<rgrid, 128, 0, st>>>(g, p, h->ion, flux_in, finegrid, h->d_scal)));
     if (!ab2_check(cudaMemcpyAsync(h->h_scal + SC_DT_CHEM, h->d_scal + SC_DT_CHEM, 2*sizeof(unsigned long long),
                                    cudaMemcpyDeviceToHost, st), "ion scalars D2H")) return -1;
     if (!ab2_check(cudaMemcpyAsync(h->h_scal + SC_ERR, h->d_scal + SC_ERR, sizeof(unsigned long long),
@@ -386,7 +404,8 @@ int ion_radtransfer(ab2_grid* h, double flux_in, double cour_no, double* dt_io, 
 
     if (dt_chem < dt_therm) nchem++; else ntherm++;          // ionrad_3d.c:943-945
     dt = AB2_MIN(dt_therm, dt_chem);
-    if (dt_done + dt > grid_dt) { dt = grid_dt - dt_done; hydro_done = 1; }
+    if (!finegrid) { if (dt_done + dt > grid_dt) { dt = grid_dt - dt_done; hydro_done = 1; } }
+    else if (dt_done + dt > tcoarse) { dt = tcoarse - dt_done; coarsetime_done = 1; }      // :958-961
 
     AB2_LAUNCH(h, KID_ION_UPDATE, (k_ion_update<<<cgrid, 128, 0, st>>>(g, p, h->ion, dt, h->d_scal)));
     dt_done += dt;
@@ -399,17 +418,21 @@ int ion_radtransfer(ab2_grid* h, double flux_in, double cour_no, double* dt_io, 
     for (int dd=0; dd<3; dd++) if (g.nx[dd] > 1) { const double x = bits_to_double(h->h_scal[SC_MAXV1+dd])/g.dx[dd]; mx = AB2_MAX(mx, x); }
     if (reduce) { reduce(&cnt, 1, 2, ctx); reduce(&mx, 1, 1, ctx); }
 
+    if (finegrid) { if (coarsetime_done) { grid_dt = dt_done; break; } continue; }        // :1008-1012
     if (cnt > MAXCELLCOUNT) { grid_dt = dt_done; break; }      // check_range (:982)
     if (hydro_done) break;                                     // :989
     dt_hydro = cour_no/mx;                                     // :997
     if (dt_hydro < dt_done) { grid_dt = dt_done; break; }
   }
-  if (niter == h->maxiter) grid_dt = dt_done;                  // :1022
+  if (!finegrid) {
+    if (niter == h->maxiter) grid_dt = dt_done;                // :1022
+    h->tcoarse = dt_done;                                      // :1028
+  }
   *dt_io = grid_dt;
   if (niter_out) *niter_out = niter;
   if (nchem_out) *nchem_out = nchem;
   if (ntherm_out) *ntherm_out = ntherm;
-  if (grid_dt < 0) {                                           // :1044-1046
+  if (!finegrid && grid_dt < 0) {                              // :1044-1046
     ab2_set_error("[ion_radtransfer_3d]: dt < 0");
     return -3;
   }

@@ -166,3 +166,88 @@ class Run:
     @property
     def zones(self):
         return self.nx[0] * self.nx[1] * self.nx[2]
+
+
+class SmrRun:
+    """main.c:355-669 with STATIC_MESH_REFINEMENT for a root Domain and one level-1 Domain (one Grid each, one GPU):
+    RestrictCorrect / Prolongate / ionradRestrictCorrect / ionrad_prolong between the two device mirrors, one dt for
+    the whole Mesh (new_dt.c:58-195), the fine level's radiation sub-cycle running to the root's coarse time."""
+
+    def __init__(self, par, problem: str, U0: dict, U0L1: dict, device: int = 0):
+        p = par
+        self.ion = problem in ("ifront", "ioniz_sphere")
+        self.nscal = 1 if self.ion else 0
+        nx0 = tuple(p.par_geti("domain1", f"Nx{a}") for a in (1, 2, 3))
+        xmin = [p.par_getd("domain1", f"x{a}min") for a in (1, 2, 3)]
+        xmax = [p.par_getd("domain1", f"x{a}max") for a in (1, 2, 3)]
+        dx0 = tuple((xmax[a] - xmin[a]) / nx0[a] for a in range(3))
+        nx1 = tuple(p.par_geti("domain2", f"Nx{a}") for a in (1, 2, 3))
+        disp1 = tuple(p.par_geti("domain2", k) for k in ("iDisp", "jDisp", "kDisp"))
+        dx1 = tuple(dx0[a] / 2.0 for a in range(3))
+        xmin1 = tuple(xmin[a] if disp1[a] == 0 else xmin[a] + float(disp1[a]) * dx1[a] for a in range(3))   # init_mesh.c:377-382
+        self.bc0 = [p.par_geti("domain1", k) for k in ("bc_ix1", "bc_ox1", "bc_ix2", "bc_ox2", "bc_ix3", "bc_ox3")]
+        self.bc1 = []
+        for a in range(3):      # interior faces of the child are prolongated, not BC'd (bvals_mhd.c:549-550 ProlongateLater)
+            self.bc1.append(self.bc0[2 * a] if disp1[a] == 0 else 0)
+            self.bc1.append(self.bc0[2 * a + 1] if (disp1[a] + nx1[a]) // 2 == nx0[a] else 0)
+        self.gamma = p.par_getd("problem", "gamma")
+        self.cour_no = p.par_getd("time", "cour_no")
+        self.tlim = p.par_getd("time", "tlim")
+        self.flux_i = p.par_getd("problem", "flux") if self.ion else 0.0
+        self.o = engine.make_overlap(nx1, disp1, nx0)
+        self.root = engine.Grid(nx0, dx0, xmin, self.gamma, self.nscal, device=device)
+        self.child = engine.Grid(nx1, dx1, xmin1, self.gamma, self.nscal, device=device)
+        self.root.upload_active(U0)
+        self.child.upload_active(U0L1)
+        if self.ion:
+            ip = engine.ion_par_from(p, dx0)                    # min_area, d_nlo from the ROOT spacing (ionrad.c:115-131)
+            self.root.ion_init(ip); self.child.ion_init(ip)
+        self.time, self.dt, self.nstep = 0.0, 0.0, 0
+        self.dt0 = self.dt1 = 0.0                               # GridS.dt of the two Grids
+        self.rad_log = []
+        # main.c:400-451
+        self.root.smr_restrict_correct(self.child, self.o, 0.0)
+        self.root.bvals_mhd(self.bc0); self.child.bvals_mhd(self.bc1)
+        if self.ion:                                            # bvals_ionrad.c:27-29,178: the first Domain's BC function wins
+            self.root.bvals_ionrad(self.flux_i); self.child.bvals_ionrad(self.flux_i)
+        self.root.smr_prolongate(self.child, self.o)
+        self.new_dt()
+
+    def new_dt(self):
+        max_dti = 0.0
+        for G in (self.root, self.child):
+            v = G.max_wave_speeds()
+            for a in range(3):
+                if G.nx[a] > 1:
+                    x = v[a] / G.dx[a]
+                    max_dti = max_dti if max_dti > x else x
+        dt = self.cour_no / max_dti if self.nstep == 0 else min(2.0 * self.dt, self.cour_no / max_dti)
+        if self.time < self.tlim and (self.tlim - self.time) < dt:
+            dt = self.tlim - self.time
+        self.dt = self.dt0 = self.dt1 = dt
+        return dt
+
+    def step(self):
+        if self.ion:
+            self.dt0, ni, nt, nc = self.root.ion_radtransfer_3d(self.flux_i, self.time, self.cour_no, self.dt0)
+            self.rad_log.append((ni, nt, nc, self.dt0))
+            self.dt = self.dt0
+            self.root.bvals_mhd(self.bc0)
+            self.root.smr_ion_prolong(self.child, self.o)
+            self.dt1, ni, nt, nc = self.child.ion_radtransfer_3d_fine(self.root.ion_coarse_time, self.dt1)
+            self.rad_log.append((ni, nt, nc, self.dt1))
+            self.dt = self.dt1                                   # ionrad_3d.c:1033
+            self.child.bvals_mhd(self.bc1)
+            self.root.smr_ion_restrict(self.child, self.o)
+        self.root.integrate_3d_ctu(self.dt0)
+        self.child.integrate_3d_ctu(self.dt1)
+        self.root.smr_restrict_correct(self.child, self.o, self.dt0)
+        self.nstep += 1
+        self.time += self.dt
+        self.new_dt()
+        self.root.bvals_mhd(self.bc0); self.child.bvals_mhd(self.bc1)
+        self.root.smr_prolongate(self.child, self.o)
+
+    def run(self, nlim):
+        while self.time < self.tlim and self.nstep < nlim:
+            self.step()

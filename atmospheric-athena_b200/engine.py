@@ -40,6 +40,25 @@ class IonPar(C.Structure):
                  "tfloor", "tceil")] + [("maxiter", C.c_int), ("min_area", C.c_double), ("d_nlo", C.c_double)]
 
 
+class Overlap(C.Structure):
+    """ab2_overlap: GridOvrlpS as plain ints (include/athena_b200.h)."""
+    _fields_ = [("cs", C.c_int * 3), ("ce", C.c_int * 3), ("face", C.c_int * 6), ("cdisp", C.c_int * 3)]
+
+
+def make_overlap(child_nx, child_disp, root_nx, level=1) -> Overlap:
+    """CGrid.ijks/ijke and the myFlx != NULL pattern init_grid.c:395-660 produces for a root-level parent (Disp 0)
+    and a single-Grid child Domain with displacement child_disp (child-level cells)."""
+    o = Overlap()
+    ref = 2 ** level
+    for a in range(3):
+        o.cs[a] = child_disp[a] // 2 + NG
+        o.ce[a] = (child_disp[a] + child_nx[a]) // 2 + NG - 1
+        o.cdisp[a] = child_disp[a]
+        o.face[2 * a] = 1 if child_disp[a] != 0 else 0
+        o.face[2 * a + 1] = 1 if (child_disp[a] + child_nx[a]) // ref != root_nx[a] else 0
+    return o
+
+
 EXPORTS = ["ab2_last_error", "ab2_version", "ab2_device_count", "ab2_grid_create", "ab2_grid_destroy",
            "ab2_bytes_allocated", "ab2_kernel_launches", "ab2_synchronize", "ab2_upload_cons_aos",
            "ab2_download_cons_aos", "ab2_upload_cons_soa", "ab2_download_cons_soa", "ab2_upload_edgeflux",
@@ -47,7 +66,9 @@ EXPORTS = ["ab2_last_error", "ab2_version", "ab2_device_count", "ab2_grid_create
            "ab2_set_static_grav_pot", "ab2_integrate_3d_ctu", "ab2_set_fixed_cells", "ab2_apply_fixed_cells",
            "ab2_ion_init", "ab2_ion_derived", "ab2_bvals_ionrad", "ab2_ion_entering_flux", "ab2_ion_radtransfer_3d",
            "ab2_unit_roe_flux", "ab2_unit_convert", "ab2_unit_lr_states",
-           "ab2_profile_enable", "ab2_profile_kernels", "ab2_profile_kernel_name", "ab2_profile_read"]
+           "ab2_profile_enable", "ab2_profile_kernels", "ab2_profile_kernel_name", "ab2_profile_read",
+           "ab2_smr_restrict_correct", "ab2_smr_ion_restrict", "ab2_smr_prolongate", "ab2_smr_ion_prolong",
+           "ab2_ion_radtransfer_3d_fine", "ab2_ion_coarse_time"]
 
 
 def build(verbose=False):
@@ -105,6 +126,14 @@ def lib():
     L.ab2_ion_entering_flux.restype = C.c_double
     L.ab2_ion_radtransfer_3d.argtypes = [vp, C.c_double, C.c_double, C.c_double, dp,
                                          C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), vp, vp]
+    op = C.POINTER(Overlap)
+    L.ab2_smr_restrict_correct.argtypes = [vp, vp, op, C.c_double]
+    L.ab2_smr_ion_restrict.argtypes = [vp, vp, op]
+    L.ab2_smr_prolongate.argtypes = [vp, vp, op]
+    L.ab2_smr_ion_prolong.argtypes = [vp, vp, op]
+    L.ab2_ion_radtransfer_3d_fine.argtypes = [vp, C.c_double, dp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), vp, vp]
+    L.ab2_ion_coarse_time.argtypes = [vp]
+    L.ab2_ion_coarse_time.restype = C.c_double
     L.ab2_profile_enable.argtypes = [vp, C.c_int]
     L.ab2_profile_kernel_name.argtypes = [C.c_int]
     L.ab2_profile_kernel_name.restype = C.c_char_p
@@ -283,6 +312,30 @@ class Grid:
         cb = self._reduce_cb(reduce)
         self._ck(lib().ab2_ion_radtransfer_3d(self.h, flux_i, time, cour_no, C.byref(dtc), C.byref(ni), C.byref(nc), C.byref(nt), cb, None))
         return dtc.value, ni.value, nt.value, nc.value
+
+    def ion_radtransfer_3d_fine(self, tcoarse, dt, reduce=None):
+        dtc = C.c_double(dt)
+        ni, nc, nt = C.c_int(0), C.c_int(0), C.c_int(0)
+        cb = self._reduce_cb(reduce)
+        self._ck(lib().ab2_ion_radtransfer_3d_fine(self.h, tcoarse, C.byref(dtc), C.byref(ni), C.byref(nc), C.byref(nt), cb, None))
+        return dtc.value, ni.value, nt.value, nc.value
+
+    @property
+    def ion_coarse_time(self):
+        return lib().ab2_ion_coarse_time(self.h)
+
+    # -- SMR: this Grid as the parent of `child` ---------------------------------------------------
+    def smr_restrict_correct(self, child, o, dt_parent):
+        self._ck(lib().ab2_smr_restrict_correct(self.h, child.h, C.byref(o), dt_parent))
+
+    def smr_ion_restrict(self, child, o):
+        self._ck(lib().ab2_smr_ion_restrict(self.h, child.h, C.byref(o)))
+
+    def smr_prolongate(self, child, o):
+        self._ck(lib().ab2_smr_prolongate(self.h, child.h, C.byref(o)))
+
+    def smr_ion_prolong(self, child, o):
+        self._ck(lib().ab2_smr_ion_prolong(self.h, child.h, C.byref(o)))
 
     def _reduce_cb(self, reduce):
         if reduce is None:

@@ -118,6 +118,32 @@ double ab2_ion_entering_flux(double flux_i, double time);
 int ab2_ion_radtransfer_3d(ab2_grid* g, double flux_i, double time, double cour_no, double* dt,
                            int* niter, int* nchem, int* ntherm, ab2_reduce_fn reduce, void* ctx);
 
+/* ---- static mesh refinement: one parent Grid and one child Grid on the same device ------------------------ */
+/* GridOvrlpS (athena.h:258-275) as plain ints.  cs/ce = CGrid.ijks/ijke on the PARENT (local indices incl. ghosts);
+ * the child's own overlap is its whole active region (one Grid per Domain).  face[dim] = 1 where the reference
+ * allocates myFlx[dim] (fine/coarse boundary interior to the root Domain, init_grid.c:508-510,624-626).
+ * cdisp = DomainS.Disp of the child in child-level cells.  The tables come from init_grid.c unchanged. */
+typedef struct ab2_overlap {
+  int cs[3], ce[3];
+  int face[6];
+  int cdisp[3];
+} ab2_overlap;
+/* RestrictCorrect (smr.c:1207-2352): child -> parent 8-cell average, then U -= +-dt/dx (F_coarse - <F_fine>) on the
+ * coarse cells outside the child faces, with the final fluxes of both Grids' last ab2_integrate_3d_ctu call. */
+int ab2_smr_restrict_correct(ab2_grid* parent, ab2_grid* child, const ab2_overlap* o, double dt_parent);
+/* ionradRestrictCorrect (smr.c:85-1205): E and s[0] only */
+int ab2_smr_ion_restrict(ab2_grid* parent, ab2_grid* child, const ab2_overlap* o);
+/* Prolongate (smr.c:2359-2923) + ProCon (:3068-3325): parent -> child ghost zones, MC-limited linear interpolation */
+int ab2_smr_prolongate(ab2_grid* parent, ab2_grid* child, const ab2_overlap* o);
+/* ionrad_prolong_snd + ionrad_prolong_rcv (ionradiation/ionrad_smr.c:345-459, 34-343): parent EdgeFlux plane at the
+ * child's upstream x1 face -> child EdgeFlux[k][j][0] */
+int ab2_smr_ion_prolong(ab2_grid* parent, ab2_grid* child, const ab2_overlap* o);
+/* ion_radtransfer_3d on a level > 0 (ionrad_3d.c:919-1014, finegrid): sub-cycles to tcoarse; *dt returns GridS.dt */
+int ab2_ion_radtransfer_3d_fine(ab2_grid* g, double tcoarse, double* dt, int* niter, int* nchem, int* ntherm,
+                                ab2_reduce_fn reduce, void* ctx);
+/* the reference's file-static tcoarse (ionrad_3d.c:47,1028): dt_done of the last root-level ab2_ion_radtransfer_3d */
+double ab2_ion_coarse_time(const ab2_grid* g);
+
 /* ---- per-kernel device timing (bench.py's roofline) ------------------------------------------------------ */
 /* When enabled every kernel launch is bracketed by CUDA events on the launching stream; ab2_profile_read drains
  * them into ms[id] / counts[id] (id < ab2_profile_kernels(), names from ab2_profile_kernel_name). */
