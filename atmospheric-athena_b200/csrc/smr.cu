@@ -156,7 +156,9 @@ __global__ void k_smr_ion_prolong(GridDev pa, GridDev ch, OvDev o, const double*
   const int j = o.cs[1]-NG + (int)(t % nj), k = o.cs[2]-NG + (int)(t / nj);
   const int pe1 = pa.nx[0]+1, pe2 = pa.nx[1]+1, ce1 = ch.nx[0]+1, ce2 = ch.nx[1]+1;
   const double val = efp[((long)k*pe2 + j)*pe1 + (o.cs[0]-NG)];             // ionrad_smr.c:375-387
-  const int ks = k*2 - o.cdisp[2], js = j*2 - o.cdisp[1];                  // :293-294 (valid for a root-level parent)
+  // :293-294 writes `k*2 - Disp` with k parent-local, which is right only below a root-level parent; the
+  // same cell in parent-relative form, identical for level 1 and meaningful for deeper levels:
+  const int ks = 2*(k - (o.cs[2]-NG)), js = 2*(j - (o.cs[1]-NG));
 #define EFC(kk,jj) efc[((long)(kk)*ce2 + (jj))*ce1]
   EFC(ks,js) = val;
   if (j < (o.ce[1]+1-NG)) {

@@ -50,3 +50,63 @@ def test_dropin_ion(name):
     assert np.allclose(g["edgeflux"], case.gold["U1_edgeflux"], rtol=1e-9, atol=0)
     if name.startswith("ioniz"):
         assert "Userwork_in_loop replayed on the device" in r.stdout
+
+
+# ---- SMR builds (--enable-smr): the reference's init_grid.c builds the overlap tables, the shim hands them to the engine ----
+def run_dropin_smr(case, build):
+    exe = os.path.join(ROOT, "build", "dropin", build, "athena")
+    if not os.path.exists(exe):
+        pytest.skip("build/dropin not built")
+    with tempfile.TemporaryDirectory() as tmp:
+        cmd = [exe, "-i", os.path.join(DECKS, str(case.gold["deck"])), f"time/nlim={case.nsteps}"] + [str(x) for x in case.gold["overrides"]]
+        r = subprocess.run(cmd, cwd=tmp, capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        rst = sorted(f for f in os.listdir(tmp) if f.endswith(".rst"))
+        d1 = read_restart(os.path.join(tmp, rst[-1]))
+    rad = [int(a) for a in re.findall(r"Radiation done in (\d+) iterations", r.stderr)]
+    return d1, rad
+
+
+def test_dropin_smr_hydro_bit_exact():
+    from smr_cases import SmrCase
+    case = SmrCase("blastsmr_k4")
+    d1, _ = run_dropin_smr(case, "blast_smr")
+    assert d1["time"] == float(case.gold["time1"]) and d1["dt"] == float(case.gold["dt1"])
+    for v in case.U1:
+        assert np.array_equal(d1["grids"][0][v], case.U1[v]), f"root {v}"
+        assert np.array_equal(d1["grids"][1][v], case.U1L1[v]), f"level-1 {v}"
+
+
+def test_dropin_smr_ion():
+    from smr_cases import SmrCase
+    case = SmrCase("ifrontsmr_k3")
+    d1, rad = run_dropin_smr(case, "ifront_smr")
+    assert rad == [int(x) for x in case.gold["rad"][:, 0]]
+    for lev, ref in ((0, case.U1), (1, case.U1L1)):
+        for v in ("d", "E", "s"):
+            assert np.allclose(d1["grids"][lev][v], ref[v], rtol=1e-10, atol=0), (lev, v)
+    assert np.allclose(d1["grids"][0]["edgeflux"], case.gold["U1_edgeflux"], rtol=1e-10, atol=0)
+    assert np.allclose(d1["grids"][1]["edgeflux"], case.gold["U1L1_edgeflux"], rtol=1e-10, atol=0)
+
+
+def test_dropin_smr_shipped_two_level_geometry_vs_reference_live():
+    """SURVEY App. C 'SMR golden': the 2-level cut of the shipped ioniz_sphere_hires deck (root 80^3 + level-1 52^3 at
+    displacement 54), static potential + Userwork reset on both levels, 3 steps -- against the reference binary run here."""
+    ref = os.path.join(ROOT, "oracle", "_ref", "ioniz_smr", "athena")
+    exe = os.path.join(ROOT, "build", "dropin", "ioniz_smr", "athena")
+    if not (os.path.exists(ref) and os.path.exists(exe)):
+        pytest.skip("needs oracle/_ref/ioniz_smr and build/dropin/ioniz_smr")
+    out = {}
+    for tag, binary in (("ref", ref), ("b200", exe)):
+        with tempfile.TemporaryDirectory() as tmp:
+            cmd = [binary, "-i", os.path.join(DECKS, "ioniz_sphere.athinput"), "job/num_domains=2", "time/nlim=3"]
+            r = subprocess.run(cmd, cwd=tmp, capture_output=True, text=True)
+            assert r.returncode == 0, tag + r.stdout[-1500:] + r.stderr[-1500:]
+            rst = sorted(f for f in os.listdir(tmp) if f.endswith(".rst"))
+            out[tag] = (read_restart(os.path.join(tmp, rst[-1])), [int(a) for a in re.findall(r"Radiation done in (\d+) iterations", r.stderr)])
+    (a, rad_a), (b, rad_b) = out["ref"], out["b200"]
+    assert rad_a == rad_b
+    assert abs(a["time"] - b["time"]) <= 1e-10 * a["time"]
+    for lev in (0, 1):
+        for v in ("d", "E", "s"):
+            assert np.allclose(b["grids"][lev][v], a["grids"][lev][v], rtol=1e-9, atol=0), (lev, v)
