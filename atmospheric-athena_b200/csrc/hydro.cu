@@ -19,6 +19,11 @@
 
 #define NG AB2_NG
 
+// Run a block of per-cell arithmetic with the branch-free IEEE division/sqrt (Arith<true>); if any operand fell outside
+// the range where that refinement is the correctly rounded result, redo the block with the plain operators.  The block
+// must only assign its outputs from unchanged inputs.  (physics.cuh, "IEEE-754 division and square root without control flow")
+#define AB2_GUARDED(...) { Arith<true> ar; __VA_ARGS__; if (ar.bad) { Arith<false> ar; __VA_ARGS__; } }
+
 // ---------------------------------------------------------------------------------------------------
 // sweep-order <-> physical-order register shuffles
 // ---------------------------------------------------------------------------------------------------
@@ -56,13 +61,13 @@ template <int DIR, int NS> __device__ __forceinline__ S6 sweep_from_phys(const d
 #define A1_F (A1_T-3)
 // minimum resident blocks per SM (register caps), tuned on B200 at 256^3 (profiles/r1_tuning.md)
 #ifndef AB2_LB_FIRST
-#define AB2_LB_FIRST 4
+#define AB2_LB_FIRST 3
 #endif
 #ifndef AB2_LB_FIRST_X1
-#define AB2_LB_FIRST_X1 5
+#define AB2_LB_FIRST_X1 4
 #endif
 #ifndef AB2_LB_FINAL
-#define AB2_LB_FINAL 5
+#define AB2_LB_FINAL 4
 #endif
 template <int NS, bool GRAV>
 __global__ void __launch_bounds__(A1_T, AB2_LB_FIRST_X1) k_first_x1(GridDev g, double dt)
@@ -80,7 +85,7 @@ __global__ void __launch_bounds__(A1_T, AB2_LB_FIRST_X1) k_first_x1(GridDev g, d
   S6 W0;
   if (c <= iu+1) {
     S6 U = load_sweep<0,NS>(g.U, row+c);
-    W0 = cons_to_prim<NS>(U, g.Gamma_1);
+    AB2_GUARDED(W0 = cons_to_prim<NS>(U, g.Gamma_1, ar));
     sW[0][t] = W0.d; sW[1][t] = W0.x; sW[2][t] = W0.y; sW[3][t] = W0.z; sW[4][t] = W0.e; sW[5][t] = W0.s;
   }
   __syncthreads();
@@ -90,7 +95,7 @@ __global__ void __launch_bounds__(A1_T, AB2_LB_FIRST_X1) k_first_x1(GridDev g, d
     S6 Wm, Wp;
     Wm.d = sW[0][t-1]; Wm.x = sW[1][t-1]; Wm.y = sW[2][t-1]; Wm.z = sW[3][t-1]; Wm.e = sW[4][t-1]; Wm.s = sW[5][t-1];
     Wp.d = sW[0][t+1]; Wp.x = sW[1][t+1]; Wp.y = sW[2][t+1]; Wp.z = sW[3][t+1]; Wp.e = sW[4][t+1]; Wp.s = sW[5][t+1];
-    plm_cell<NS>(Wm, W0, Wp, dtodx, g.Gamma, Wl_next, Wr_this);
+    AB2_GUARDED(plm_cell<NS>(Wm, W0, Wp, dtodx, g.Gamma, Wl_next, Wr_this, ar));
     if (GRAV) {   // integrate_3d_ctu.c:318-342
       const long cc = row + c;
       Wl_next.x -= dtodx*(g.phi[PHI_MH0][cc+1] - g.phi[PHI_M0][cc+1]);
@@ -102,10 +107,9 @@ __global__ void __launch_bounds__(A1_T, AB2_LB_FIRST_X1) k_first_x1(GridDev g, d
   if ((t >= 2) && (t <= A1_T-2) && (c <= iu)) {
     S6 Wl;
     Wl.d = sL[0][t-1]; Wl.x = sL[1][t-1]; Wl.y = sL[2][t-1]; Wl.z = sL[3][t-1]; Wl.e = sL[4][t-1]; Wl.s = sL[5][t-1];
-    const S6 Ul = prim_to_cons<NS>(Wl, g.Gamma_1);
-    const S6 Ur = prim_to_cons<NS>(Wr_this, g.Gamma_1);
-    S6 F;
-    roe_flux<NS>(Ul, Ur, Wl, Wr_this, 0.0, g.Gamma, g.Gamma_1, F);
+    S6 Ul, Ur, F;
+    AB2_GUARDED(Ul = prim_to_cons<NS>(Wl, g.Gamma_1, ar); Ur = prim_to_cons<NS>(Wr_this, g.Gamma_1, ar);
+                roe_flux<NS>(Ul, Ur, Wl, Wr_this, 0.0, g.Gamma, g.Gamma_1, F, ar));
     store_sweep<0,NS>(g.Ul[0], row+c, Ul);
     store_sweep<0,NS>(g.Ur[0], row+c, Ur);
     store_sweep<0,NS>(g.F[0], row+c, F);
@@ -131,23 +135,35 @@ __global__ void __launch_bounds__(128, AB2_LB_FIRST) k_first_march(GridDev g, do
   const long base = (long)i + (long)o*g.st[OTH];
   const double dtodx = dt/g.dx[DIR];
 
-  S6 Wm = cons_to_prim<NS>(load_sweep<DIR,NS>(g.U, base + (long)(fs-2)*sd), g.Gamma_1);
-  S6 W0 = cons_to_prim<NS>(load_sweep<DIR,NS>(g.U, base + (long)(fs-1)*sd), g.Gamma_1);
+  S6 Wm, W0;
+  {
+    const S6 Ua = load_sweep<DIR,NS>(g.U, base + (long)(fs-2)*sd), Ub = load_sweep<DIR,NS>(g.U, base + (long)(fs-1)*sd);
+    AB2_GUARDED(Wm = cons_to_prim<NS>(Ua, g.Gamma_1, ar); W0 = cons_to_prim<NS>(Ub, g.Gamma_1, ar));
+  }
   S6 Wl_prev;
+  // Register prefetch: the conserved state of cell c+2 and the potential values of this iteration are requested at the
+  // top of iteration c and consumed ~one PLM+Roe evaluation later, so the HBM/L2 latency (the kernel's dominant stall
+  // in the first ncu profile: long-scoreboard waits on the first use of each freshly loaded value) overlaps the FP64 work.
+  S6 Unext = load_sweep<DIR,NS>(g.U, base + (long)fs*sd);
   for (int c = fs-1; c < fe; c++) {
     const long cc = base + (long)c*sd;
-    const S6 Wp = cons_to_prim<NS>(load_sweep<DIR,NS>(g.U, cc + sd), g.Gamma_1);
-    S6 Wl_next, Wr_this;
-    plm_cell<NS>(Wm, W0, Wp, dtodx, g.Gamma, Wl_next, Wr_this);
+    const S6 Ucur = Unext;                                                   // cell c+1
+    if (c+1 < fe) Unext = load_sweep<DIR,NS>(g.U, cc + 2*sd);                // cell c+2 <= fu+1: always inside the array
+    double phi_mh_p = 0.0, phi_m_p = 0.0, phi_c = 0.0, phi_mh = 0.0;
+    if (GRAV) {
+      phi_mh_p = g.phi[PHI_MH0+DIR][cc+sd]; phi_m_p = g.phi[PHI_M0+DIR][cc+sd];
+      phi_c = g.phi[PHI_C][cc]; phi_mh = g.phi[PHI_MH0+DIR][cc];
+    }
+    S6 Wp, Wl_next, Wr_this;
+    AB2_GUARDED(Wp = cons_to_prim<NS>(Ucur, g.Gamma_1, ar); plm_cell<NS>(Wm, W0, Wp, dtodx, g.Gamma, Wl_next, Wr_this, ar));
     if (GRAV) {   // integrate_3d_ctu.c:635-645, 819-829
-      Wl_next.x -= dtodx*(g.phi[PHI_MH0+DIR][cc+sd] - g.phi[PHI_M0+DIR][cc+sd]);
-      Wr_this.x -= dtodx*(g.phi[PHI_C][cc] - g.phi[PHI_MH0+DIR][cc]);
+      Wl_next.x -= dtodx*(phi_mh_p - phi_m_p);
+      Wr_this.x -= dtodx*(phi_c - phi_mh);
     }
     if (c >= fs) {
-      const S6 Ul = prim_to_cons<NS>(Wl_prev, g.Gamma_1);
-      const S6 Ur = prim_to_cons<NS>(Wr_this, g.Gamma_1);
-      S6 F;
-      roe_flux<NS>(Ul, Ur, Wl_prev, Wr_this, 0.0, g.Gamma, g.Gamma_1, F);
+      S6 Ul, Ur, F;
+      AB2_GUARDED(Ul = prim_to_cons<NS>(Wl_prev, g.Gamma_1, ar); Ur = prim_to_cons<NS>(Wr_this, g.Gamma_1, ar);
+                  roe_flux<NS>(Ul, Ur, Wl_prev, Wr_this, 0.0, g.Gamma, g.Gamma_1, F, ar));
       store_sweep<DIR,NS>(g.Ul[DIR], cc, Ul);
       store_sweep<DIR,NS>(g.Ur[DIR], cc, Ur);
       store_sweep<DIR,NS>(g.F[DIR], cc, F);
@@ -232,7 +248,12 @@ __global__ void __launch_bounds__(128) k_correct(GridDev g, Box b, double dt)
   }
 #pragma unroll
   for (int v=0; v<5+NS; v++) { g.Ul[DIR][v][cR] = UL[v]; g.Ur[DIR][v][cR] = UR[v]; }
-  g.eta[DIR][cR] = eta_face(sweep_from_phys<DIR,NS>(UL), sweep_from_phys<DIR,NS>(UR), g.Gamma, g.Gamma_1);
+  {
+    const S6 sl = sweep_from_phys<DIR,NS>(UL), sr = sweep_from_phys<DIR,NS>(UR);
+    double eta;
+    AB2_GUARDED(eta = eta_face(sl, sr, g.Gamma, g.Gamma_1, ar));
+    g.eta[DIR][cR] = eta;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -256,10 +277,9 @@ __global__ void __launch_bounds__(128, AB2_LB_FINAL) k_final(GridDev g, Box b)
   etah = AB2_MAX(etah, g.eta[DIR][c]);
   const S6 Ul = load_sweep<DIR,NS>(g.Ul[DIR], c);
   const S6 Ur = load_sweep<DIR,NS>(g.Ur[DIR], c);
-  const S6 Wl = cons_to_prim<NS>(Ul, g.Gamma_1);
-  const S6 Wr = cons_to_prim<NS>(Ur, g.Gamma_1);
   S6 F;
-  roe_flux<NS>(Ul, Ur, Wl, Wr, etah, g.Gamma, g.Gamma_1, F);
+  AB2_GUARDED(const S6 Wl = cons_to_prim<NS>(Ul, g.Gamma_1, ar); const S6 Wr = cons_to_prim<NS>(Ur, g.Gamma_1, ar);
+              roe_flux<NS>(Ul, Ur, Wl, Wr, etah, g.Gamma, g.Gamma_1, F, ar));
   store_sweep<DIR,NS>(g.F[DIR], c, F);
 }
 

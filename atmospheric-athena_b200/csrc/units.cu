@@ -15,7 +15,9 @@ template <int NS> __global__ void k_unit_flux(int n, const double* Ul, const dou
   const int t = blockIdx.x*blockDim.x + threadIdx.x;
   if (t >= n) return;
   S6 f;
-  roe_flux<NS>(ld6(Ul+6*t), ld6(Ur+6*t), ld6(Wl+6*t), ld6(Wr+6*t), etah[t], Gamma, Gamma-1.0, f);
+  const S6 ul = ld6(Ul+6*t), ur = ld6(Ur+6*t), wl = ld6(Wl+6*t), wr = ld6(Wr+6*t);
+  { Arith<true> ar; roe_flux<NS>(ul, ur, wl, wr, etah[t], Gamma, Gamma-1.0, f, ar);
+    if (ar.bad) { Arith<false> ax; roe_flux<NS>(ul, ur, wl, wr, etah[t], Gamma, Gamma-1.0, f, ax); } }
   st6(F+6*t, f);
 }
 
@@ -24,8 +26,11 @@ template <int NS> __global__ void k_unit_convert(int n, const double* in, double
   const int t = blockIdx.x*blockDim.x + threadIdx.x;
   if (t >= n) return;
   const S6 a = ld6(in+6*t);
-  st6(out+6*t, to_prim ? cons_to_prim<NS>(a, Gamma-1.0) : prim_to_cons<NS>(a, Gamma-1.0));
-  if (cf) cf[t] = cfast(a, Gamma, Gamma-1.0);
+  S6 o; double c;
+  { Arith<true> ar; o = to_prim ? cons_to_prim<NS>(a, Gamma-1.0, ar) : prim_to_cons<NS>(a, Gamma-1.0, ar); c = cfast(a, Gamma, Gamma-1.0, ar);
+    if (ar.bad) { Arith<false> ax; o = to_prim ? cons_to_prim<NS>(a, Gamma-1.0, ax) : prim_to_cons<NS>(a, Gamma-1.0, ax); c = cfast(a, Gamma, Gamma-1.0, ax); } }
+  st6(out+6*t, o);
+  if (cf) cf[t] = c;
 }
 
 // one thread per (pencil, cell): cells il-1..iu+1 write Wl[i+1], Wr[i]  (lr_states_plm.c:96)
@@ -37,9 +42,27 @@ template <int NS> __global__ void k_unit_plm(int npen, int n, const double* W, d
   const int pen = t / ncell, i = il - 1 + t % ncell;
   const double* w = W + (size_t)pen*n*6;
   S6 wl, wr;
-  plm_cell<NS>(ld6(w+6*(i-1)), ld6(w+6*i), ld6(w+6*(i+1)), dtodx, Gamma, wl, wr);
+  const S6 wm = ld6(w+6*(i-1)), w0 = ld6(w+6*i), wp = ld6(w+6*(i+1));
+  { Arith<true> ar; plm_cell<NS>(wm, w0, wp, dtodx, Gamma, wl, wr, ar);
+    if (ar.bad) { Arith<false> ax; plm_cell<NS>(wm, w0, wp, dtodx, Gamma, wl, wr, ax); } }
   st6(Wl + ((size_t)pen*n + i+1)*6, wl);
   st6(Wr + ((size_t)pen*n + i)*6, wr);
+}
+
+// raw check of Arith<true>: out[0..n) = fast a/b (or NaN-tagged when the range test rejects), out2 = a/b; same for sqrt
+__global__ void k_unit_ieee(int n, const double* a, const double* b, double* qf, double* qe, double* sf, double* se, int* nbad)
+{
+  const int t = blockIdx.x*blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  Arith<true> ar;
+  qf[t] = ar.div(a[t], b[t]);
+  const unsigned bad_div = ar.bad; ar.bad = 0;
+  sf[t] = ar.sqrt_(a[t]);
+  const unsigned bad_sqrt = ar.bad;
+  qe[t] = a[t]/b[t];
+  se[t] = sqrt(a[t]);
+  if (bad_div) { qf[t] = qe[t]; atomicAdd(&nbad[0], 1); }      // rejected operands take the plain-operator path
+  if (bad_sqrt) { sf[t] = se[t]; atomicAdd(&nbad[1], 1); }
 }
 
 struct DevBuf {
@@ -70,6 +93,22 @@ int ab2_unit_convert(int n, const double* in, int nscal, double gamma, int to_pr
   if (!ab2_check(cudaMemcpy(out, o.p, 6*n*sizeof(double), cudaMemcpyDeviceToHost), "unit convert")) return -1;
   if (cfast_out && !ab2_check(cudaMemcpy(cfast_out, cf.p, n*sizeof(double), cudaMemcpyDeviceToHost), "unit cfast")) return -1;
   return 0;
+}
+
+int ab2_unit_ieee(int n, const double* a, const double* b, double* q_fast, double* q_exact, double* s_fast, double* s_exact, int* nrejected)
+{
+  DevBuf A(n,a), B(n,b), qf(n), qe(n), sf(n), se(n);
+  int* nb = nullptr;
+  if (!A.p || !B.p || !qf.p || !qe.p || !sf.p || !se.p || cudaMalloc(&nb, 2*sizeof(int)) != cudaSuccess) { ab2_set_error("[ab2_unit_ieee]: cudaMalloc failed"); return -1; }
+  cudaMemset(nb, 0, 2*sizeof(int));
+  k_unit_ieee<<<(n+127)/128,128>>>(n, A.p, B.p, qf.p, qe.p, sf.p, se.p, nb);
+  bool ok = ab2_check(cudaMemcpy(q_fast, qf.p, n*sizeof(double), cudaMemcpyDeviceToHost), "unit ieee") &&
+            ab2_check(cudaMemcpy(q_exact, qe.p, n*sizeof(double), cudaMemcpyDeviceToHost), "unit ieee") &&
+            ab2_check(cudaMemcpy(s_fast, sf.p, n*sizeof(double), cudaMemcpyDeviceToHost), "unit ieee") &&
+            ab2_check(cudaMemcpy(s_exact, se.p, n*sizeof(double), cudaMemcpyDeviceToHost), "unit ieee") &&
+            ab2_check(cudaMemcpy(nrejected, nb, 2*sizeof(int), cudaMemcpyDeviceToHost), "unit ieee");
+  cudaFree(nb);
+  return ok ? 0 : -1;
 }
 
 int ab2_unit_lr_states(int npencil, int n, const double* W, int nscal, double gamma, double dt, double dx,

@@ -158,6 +158,9 @@ int ab2_unit_roe_flux(int n, const double* Ul, const double* Ur, const double* W
                       int nscal, double gamma, const double* etah, double* F);
 /* Cons1D_to_Prim1D / Prim1D_to_Cons1D / cfast (convert_var.c:389-499); cfast_out may be NULL */
 int ab2_unit_convert(int n, const double* in, int nscal, double gamma, int to_prim, double* out, double* cfast_out);
+/* a/b and sqrt(a) through the engine's branch-free IEEE refinement (csrc/physics.cuh Arith<true>, plain operators where
+ * its range test rejects the operands) next to the plain operators; nrejected[2] = rejected divisions, square roots */
+int ab2_unit_ieee(int n, const double* a, const double* b, double* q_fast, double* q_exact, double* s_fast, double* s_exact, int* nrejected);
 /* lr_states() of reconstruction/lr_states_plm.c:62-374 on npencil pencils of n cells */
 int ab2_unit_lr_states(int npencil, int n, const double* W, int nscal, double gamma, double dt, double dx,
                        int il, int iu, double* Wl, double* Wr);

@@ -51,6 +51,30 @@ def test_units_bit_exact(nscal):
     assert np.array_equal(Wr[:, il - 1:iu + 1], g["pencil_Wr"][:, il - 1:iu + 1])
 
 
+def test_fast_ieee_division_and_sqrt_are_correctly_rounded():
+    """Arith<true> (branch-free MUFU + FMA refinement) must return the bits of a/b and sqrt(a) for every operand its
+    range test accepts; rejected operands go through the plain operators.  4e6 operand pairs over 600 binades plus
+    the special values."""
+    L = engine().lib()
+    rng = np.random.default_rng(7)
+    n = 1 << 22
+    a = rng.uniform(1, 2, n) * 2.0 ** rng.integers(-300, 300, n) * rng.choice([-1.0, 1.0], n)
+    b = rng.uniform(1, 2, n) * 2.0 ** rng.integers(-300, 300, n) * rng.choice([-1.0, 1.0], n)
+    sp = np.array([0.0, -0.0, 1.0, np.inf, -np.inf, np.nan, 5e-324, 1e-310, 1e308, 1.7e308, 1e-20, 2.2250738585072014e-308])
+    a[:len(sp) ** 2] = np.repeat(sp, len(sp)); b[:len(sp) ** 2] = np.tile(sp, len(sp))
+    a[1000:2000] = rng.uniform(1, 2, 1000) * 2.0 ** rng.integers(-1074, -960, 1000)       # tiny numerators / radicands
+    b[2000:3000] = rng.uniform(1, 2, 1000) * 2.0 ** rng.integers(1000, 1023, 1000)        # huge divisors
+    qf, qe, sf, se = (np.empty(n) for _ in range(4))
+    nrej = (C.c_int * 2)()
+    assert L.ab2_unit_ieee(n, P(a), P(b), P(qf), P(qe), P(sf), P(se), nrej) == 0
+    assert np.array_equal(qf.view(np.int64), qe.view(np.int64)) or np.array_equal(qf, qe, equal_nan=True)
+    assert np.array_equal(sf, se, equal_nan=True)
+    host_q = a / b
+    ok = np.isfinite(host_q)
+    assert np.array_equal(qe[ok], host_q[ok])                  # and the device operator agrees with the host's IEEE division
+    assert nrej[0] < n // 100 and nrej[1] > n // 3             # divisions: few rejected; square roots: the negative half is
+
+
 def gpu_run(case):
     from athena_b200.driver import Run
     R = Run(case.par, case.build, device=0, U0=case.U0)
