@@ -416,7 +416,7 @@ static int ion_radtransfer_impl(ab2_grid* h, int finegrid, double flux_in, doubl
     double cnt = (double)h->h_scal[SC_COUNT];
     double mx = 0.0;
     for (int dd=0; dd<3; dd++) if (g.nx[dd] > 1) { const double x = bits_to_double(h->h_scal[SC_MAXV1+dd])/g.dx[dd]; mx = AB2_MAX(mx, x); }
-    if (reduce) { reduce(&cnt, 1, 2, ctx); reduce(&mx, 1, 1, ctx); }
+    if (reduce) { double cm[2] = { cnt, mx }; reduce(cm, 2, 3, ctx); cnt = cm[0]; mx = cm[1]; }   // one exchange: {SUM count, MAX 1/dt_hydro}
 
     if (finegrid) { if (coarsetime_done) { grid_dt = dt_done; break; } continue; }        // :1008-1012
     if (cnt > MAXCELLCOUNT) { grid_dt = dt_done; break; }      // check_range (:982)
