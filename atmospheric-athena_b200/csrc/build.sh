@@ -5,7 +5,7 @@
 set -e
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
-FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo --fmad=false -prec-div=true -prec-sqrt=true -std=c++17 -Xcompiler -fPIC,-O2 ${AB2_EXTRA_NVCC_FLAGS}"
+FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo ${AB2_FMAD:---fmad=false} -prec-div=true -prec-sqrt=true -std=c++17 -Xcompiler -fPIC,-O2 ${AB2_EXTRA_NVCC_FLAGS}"
 for f in hydro ion api units smr; do
   if [ ! -f $f.o ] || [ $f.cu -nt $f.o ] || [ physics.cuh -nt $f.o ] || [ engine.cuh -nt $f.o ] || [ ../../include/athena_b200.h -nt $f.o ]; then
     $NVCC $FLAGS ${AB2_PTXAS_V:+-Xptxas -v} -c $f.cu -o $f.o &

@@ -57,8 +57,9 @@ template <int DIR, int NS> __device__ __forceinline__ S6 sweep_from_phys(const d
 // Pass A, x1: one block = 128 consecutive cells of one (j,k) row -> 125 faces.  Primitive states and the
 // left states travel between neighbouring threads through shared memory.
 // ---------------------------------------------------------------------------------------------------
-#define A1_T 128
-#define A1_F (A1_T-3)
+// tile width (threads = cells of one row) is chosen per grid so the last tile of a row is not mostly idle:
+// a tile of T cells yields T-3 faces, and Nx1+4 faces per row must be covered (256 zones: 3 tiles of 96, 90 % busy,
+// instead of 3 tiles of 128, 68 % busy)
 // minimum resident blocks per SM (register caps), tuned on B200 at 256^3 (profiles/r1_tuning.md)
 #ifndef AB2_LB_FIRST
 #define AB2_LB_FIRST 3
@@ -69,9 +70,10 @@ template <int DIR, int NS> __device__ __forceinline__ S6 sweep_from_phys(const d
 #ifndef AB2_LB_FINAL
 #define AB2_LB_FINAL 4
 #endif
-template <int NS, bool GRAV>
-__global__ void __launch_bounds__(A1_T, AB2_LB_FIRST_X1) k_first_x1(GridDev g, double dt)
+template <int NS, bool GRAV, int A1_T>
+__global__ void __launch_bounds__(A1_T, (AB2_LB_FIRST_X1*128)/A1_T) k_first_x1(GridDev g, double dt)
 {
+  constexpr int A1_F = A1_T-3;
   __shared__ double sW[6][A1_T];
   __shared__ double sL[6][A1_T];
   const int t = threadIdx.x;
@@ -123,11 +125,13 @@ __global__ void __launch_bounds__(A1_T, AB2_LB_FIRST_X1) k_first_x1(GridDev g, d
 template <int DIR, int NS, bool GRAV>
 __global__ void __launch_bounds__(128, AB2_LB_FIRST) k_first_march(GridDev g, double dt, int seg)
 {
-  const int il = NG-2, iu = g.nx[0]+NG+1;
-  const int i = il + blockIdx.x*blockDim.x + threadIdx.x;
-  if (i > iu) return;
+  // threads enumerate the (x1, other transverse axis) pencils in one flat index, so every warp is full
+  const int il = NG-2, ni = g.nx[0]+4;
   constexpr int OTH = (DIR == 1) ? 2 : 1;                 // the transverse axis that is not x1
-  const int o = NG-2 + blockIdx.z;                        // range [l, u] of that axis
+  const long tp = (long)blockIdx.x*blockDim.x + threadIdx.x;
+  if (tp >= (long)ni*(g.nx[OTH]+4)) return;
+  const int o = NG-2 + (int)(tp / ni);                    // range [l, u] of that axis
+  const int i = il + (int)(tp - (long)(o-(NG-2))*ni);
   const int fl = NG-2+1, fu = g.nx[DIR]+NG+1;             // faces [l+1, u] along the sweep
   const int fs = fl + blockIdx.y*seg;
   int fe = fs + seg; if (fe > fu+1) fe = fu+1;
@@ -467,18 +471,33 @@ static int integrate_impl(ab2_grid* h, double dt)
   const int s[3] = {NG,NG,NG}, e[3] = {g.nx[0]+NG-1, g.nx[1]+NG-1, g.nx[2]+NG-1};
   int l[3], u[3];
   for (int a=0; a<3; a++) { l[a] = s[a]-2; u[a] = e[a]+2; }
-  const int seg = 32;
+  // faces per marching segment: ~32, balanced so the last segment of a pencil is not a stub
+  auto seg_for = [](int nf) { const int ns = (nf + 31)/32; return (nf + ns-1)/ns; };
 
   // Pass A
   {
     const int nf = g.nx[0]+4;
-    dim3 grid((nf + A1_F-1)/A1_F, u[1]-l[1]+1, u[2]-l[2]+1);
-    AB2_LAUNCH(h, KID_FIRST_X1, (k_first_x1<NS,GRAV><<<grid, A1_T, 0, st>>>(g, dt)));
-    const int ni = u[0]-l[0]+1;
-    dim3 g2((ni+127)/128, (g.nx[1]+4 + seg-1)/seg, u[2]-l[2]+1);
-    AB2_LAUNCH(h, KID_FIRST_X2, (k_first_march<1,NS,GRAV><<<g2, 128, 0, st>>>(g, dt, seg)));
-    dim3 g3((ni+127)/128, (g.nx[2]+4 + seg-1)/seg, u[1]-l[1]+1);
-    AB2_LAUNCH(h, KID_FIRST_X3, (k_first_march<2,NS,GRAV><<<g3, 128, 0, st>>>(g, dt, seg)));
+    int bestT = 128; double bestw = 1e30;
+    for (int T : {64, 96, 128, 160, 192, 256}) {          // least padded tile width
+      const int nt = (nf + T-4)/(T-3);
+      const double w = (double)nt*T/nf + 0.02*(256.0/T);  // padding, with a small bias against very narrow tiles
+      if (w < bestw) { bestw = w; bestT = T; }
+    }
+    const dim3 grid((nf + bestT-4)/(bestT-3), u[1]-l[1]+1, u[2]-l[2]+1);
+    switch (bestT) {
+      case 64:  AB2_LAUNCH(h, KID_FIRST_X1, (k_first_x1<NS,GRAV,64><<<grid, 64, 0, st>>>(g, dt))); break;
+      case 96:  AB2_LAUNCH(h, KID_FIRST_X1, (k_first_x1<NS,GRAV,96><<<grid, 96, 0, st>>>(g, dt))); break;
+      case 160: AB2_LAUNCH(h, KID_FIRST_X1, (k_first_x1<NS,GRAV,160><<<grid, 160, 0, st>>>(g, dt))); break;
+      case 192: AB2_LAUNCH(h, KID_FIRST_X1, (k_first_x1<NS,GRAV,192><<<grid, 192, 0, st>>>(g, dt))); break;
+      case 256: AB2_LAUNCH(h, KID_FIRST_X1, (k_first_x1<NS,GRAV,256><<<grid, 256, 0, st>>>(g, dt))); break;
+      default:  AB2_LAUNCH(h, KID_FIRST_X1, (k_first_x1<NS,GRAV,128><<<grid, 128, 0, st>>>(g, dt))); break;
+    }
+    const long ni = u[0]-l[0]+1;
+    const int seg2 = seg_for(g.nx[1]+4), seg3 = seg_for(g.nx[2]+4);
+    dim3 g2((unsigned)((ni*(u[2]-l[2]+1)+127)/128), (g.nx[1]+4 + seg2-1)/seg2, 1);
+    AB2_LAUNCH(h, KID_FIRST_X2, (k_first_march<1,NS,GRAV><<<g2, 128, 0, st>>>(g, dt, seg2)));
+    dim3 g3((unsigned)((ni*(u[1]-l[1]+1)+127)/128), (g.nx[2]+4 + seg3-1)/seg3, 1);
+    AB2_LAUNCH(h, KID_FIRST_X3, (k_first_march<2,NS,GRAV><<<g3, 128, 0, st>>>(g, dt, seg3)));
   }
   Box act; for (int a=0; a<3; a++) { act.lo[a] = s[a]; act.hi[a] = e[a]; }
   // Pass B
