@@ -50,7 +50,7 @@ static const char* KERNEL_NAMES[KID_N] = {
   "k_bvals", "k_max_speeds", "k_first_x1", "k_first_march<1>", "k_first_march<2>", "k_dhalf",
   "k_correct<0>", "k_correct<1>", "k_correct<2>", "k_final<0>", "k_final<1>", "k_final<2>", "k_update",
   "k_apply_fixed", "k_ion_prep", "k_ion_rates", "k_ion_update", "k_bvals_ionrad", "k_transpose",
-  "k_smr_restrict", "k_smr_flux_correct", "k_smr_prolongate" };
+  "k_smr_restrict", "k_smr_flux_correct", "k_smr_prolongate", "k_ion_rates<fused update>" };
 
 cudaEvent_t ab2_prof_event(ab2_grid* h)
 {
@@ -225,6 +225,7 @@ int ab2_upload_edgeflux(ab2_grid* h, const double* ef)
 {
   if (!h->has_ion) { ab2_set_error("[ab2_upload_edgeflux]: ab2_ion_init not called"); return -1; }
   CK(cudaMemcpyAsync(h->ion.edgeflux, ef, edge_count(h)*sizeof(double), cudaMemcpyHostToDevice, h->stream), "upload edgeflux");
+  CK(cudaMemcpyAsync(h->ion.edgeflux_alt, ef, edge_count(h)*sizeof(double), cudaMemcpyHostToDevice, h->stream), "upload edgeflux");
   CK(cudaStreamSynchronize(h->stream), "upload edgeflux sync");
   return 0;
 }
@@ -384,7 +385,7 @@ int ab2_ion_init(ab2_grid* h, const ab2_ion_par* par)
     IonDev& I = h->ion;
     if (!(I.ph_rate = dev_alloc(h, ncell)) || !(I.edot = dev_alloc(h, ncell)) || !(I.nHdot = dev_alloc(h, ncell)) ||
         !(I.e_init = dev_alloc(h, ncell)) || !(I.e_th_init = dev_alloc(h, ncell)) || !(I.x_init = dev_alloc(h, ncell)) ||
-        !(I.edgeflux = dev_alloc(h, edge_count(h)))) return -1;
+        !(I.edgeflux = dev_alloc(h, edge_count(h))) || !(I.edgeflux_alt = dev_alloc(h, edge_count(h)))) return -1;
     double* s = dev_alloc(h, (ncell+1)/2);
     if (!s) return -1;
     I.sign_state = (int*)s;

@@ -62,7 +62,8 @@ struct IonParDev {
 struct IonDev {
   double *ph_rate, *edot, *nHdot, *e_init, *e_th_init, *x_init;
   int* sign_state;            // (sign_count << 2) | (last_sign + 1)
-  double* edgeflux;           // [nx3+1][nx2+1][nx1+1]
+  double* edgeflux;           // [nx3+1][nx2+1][nx1+1], current
+  double* edgeflux_alt;       // written by a fused update+rates launch; becomes current when the sub-cycle continues
 };
 
 typedef void (*ab2_reduce_fn_t)(double* vals, int n, int op, void* ctx);
@@ -72,7 +73,7 @@ enum {
   KID_BVALS = 0, KID_MAX_SPEEDS, KID_FIRST_X1, KID_FIRST_X2, KID_FIRST_X3, KID_DHALF,
   KID_CORRECT_X1, KID_CORRECT_X2, KID_CORRECT_X3, KID_FINAL_X1, KID_FINAL_X2, KID_FINAL_X3, KID_UPDATE,
   KID_APPLY_FIXED, KID_ION_PREP, KID_ION_RATES, KID_ION_UPDATE, KID_BVALS_IONRAD, KID_TRANSPOSE,
-  KID_SMR_RESTRICT, KID_SMR_FLUXCORR, KID_SMR_PROLONG, KID_N
+  KID_SMR_RESTRICT, KID_SMR_FLUXCORR, KID_SMR_PROLONG, KID_ION_FUSED, KID_N
 };
 struct ProfPending { int id; cudaEvent_t a, b; };
 

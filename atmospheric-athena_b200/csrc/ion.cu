@@ -15,7 +15,9 @@
 // products, so this path agrees with the reference to ~1e-13 relative per iteration, not bit for bit.
 #include <float.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
+#include <utility>
 #include "engine.cuh"
 #include "physics.cuh"
 
@@ -120,7 +122,65 @@ __global__ void __launch_bounds__(128) k_ion_prep(GridDev g, IonParDev p, IonDev
 // ---------------------------------------------------------------------------------------------------
 // k_ion_rates: ray trace (ionradplane_3d.c:254-310) + chem rates (ionrad_3d.c:307-394) + therm rates (:433-550)
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_ion_rates(GridDev g, IonParDev p, IonDev ion, double flux_in_root, int finegrid, unsigned long long* scal)
+// ionization_update (:565-590) + floors (:970-971) + check_range (:206-283) + compute_dt_hydro (:593-678) for ONE cell.
+// E,s are updated in place (and stored); count and the three per-direction maxima accumulate.
+__device__ __forceinline__ void cell_update(const GridDev& g, const IonParDev& p, const IonDev& ion, long c, double dt,
+                                            double d, double M1, double M2, double M3, double& E, double& s,
+                                            unsigned long long& count, double& m1, double& m2, double& m3)
+{
+    const double nHdot = ion.nHdot[c];
+    double d_nlim = d*IONFRACFLOOR;
+    d_nlim = d_nlim < p.d_nlo ? d_nlim : p.d_nlo;
+    if ((nHdot > 0) || (s > 1.0001*d_nlim)) {
+      E += ion.edot[c] * dt;
+      s += nHdot * dt * p.m_H;
+    }
+    // floors (apply_temp_floor :70-136, apply_neutral_floor :140-157), keeping the cell's chemistry state: when no
+    // floor fires (the common case) check_range below re-evaluates the very same expressions on the same values,
+    // so the seven divisions are shared; when one fires they are recomputed from the floored E,s as the reference does
+    CellChem cs = chem_state(p, g.Gamma_1, d, M1, M2, M3, E, s);
+    bool changed = false;
+    if (cs.T < p.tfloor) {
+      const double e_sp = p.tfloor * p.k_B / ((cs.x*0.5*p.m_H+(1.0-cs.x)*p.mu) * g.Gamma_1);
+      E = kinetic(d,M1,M2,M3) + e_sp * d; changed = true;
+    }
+    if ((cs.T > p.tceil) && (p.tceil > 0)) {
+      const double e_sp = p.tceil * p.k_B / ((cs.x*0.5*p.m_H+(1.0-cs.x)*p.mu) * g.Gamma_1);
+      E = kinetic(d,M1,M2,M3) + e_sp * d; changed = true;
+    }
+    if (s < d_nlim) { s = d_nlim; changed = true; }
+    else if (s > d) { s = d; changed = true; }
+    g.U[4][c] = E; g.U[5][c] = s;
+    if (changed) cs = chem_state(p, g.Gamma_1, d, M1, M2, M3, E, s);
+
+    // check_range (ionrad_3d.c:222-264)
+    if (!(ion.ph_rate[c] / (p.min_area * cs.n_H) > 2.0*CION)) {
+      const double eth0 = ion.e_th_init[c], e0 = ion.e_init[c], x0 = ion.x_init[c];
+      if ((cs.e_thermal / eth0 >= 1 + p.max_de_therm_step) || (eth0 / cs.e_thermal >= 1 + p.max_de_therm_step)) count += 1;
+      else if ((p.max_de_step > 0) && ((E / e0 >= 1 + p.max_de_step) || (e0 / E >= 1 + p.max_de_step))) count += 1;
+      else if ((p.max_dx_step > 0) && ((cs.x / x0 >= 1 + p.max_dx_step) || (x0 / cs.x >= 1 + p.max_dx_step))) count += 1;
+    }
+    // compute_dt_hydro (:609-663): max over cells of (|v_d|+a)/dx_d.  Division by the positive constant dx_d is
+    // monotone under rounding, so max_c fl(x_c/dx) == fl((max_c x_c)/dx): keep three per-direction maxima here and
+    // divide once on the host (new_dt.c:126-161 has this very form).
+    const double di = 1.0/d;
+    const double v1 = M1*di, v2 = M2*di, v3 = M3*di;
+    const double qsq = v1*v1 + v2*v2 + v3*v3;
+    const double pr = AB2_MAX(g.Gamma_1*(E - 0.5*d*qsq), AB2_TINY);
+    const double asq = g.Gamma*pr*di;
+    const double a = sqrt(asq);
+    { const double x1 = fabs(v1)+a, x2 = fabs(v2)+a, x3 = fabs(v3)+a;
+      m1 = AB2_MAX(m1, x1); m2 = AB2_MAX(m2, x2); m3 = AB2_MAX(m3, x3); }
+}
+
+// UPDATE = true fuses the previous iteration's k_ion_update (same arithmetic, same order) in front of the rates of
+// the next one: the cells are updated, floored and range-checked while they stream through for the ray trace, which
+// saves one pass over U per sub-cycle iteration and lets the host read all six loop scalars in ONE synchronisation.
+// The new EdgeFlux goes to ef_out (the alternate buffer) because the iteration may turn out to be the last one,
+// in which case the reference's EdgeFlux is the one written before this update.
+template <bool UPDATE>
+__global__ void __launch_bounds__(128) k_ion_rates(GridDev g, IonParDev p, IonDev ion, double flux_in_root, int finegrid, double dt_upd,
+                                                   const double* ef_in_base, double* ef_out_base, unsigned long long* scal)
 {
   const int lane = threadIdx.x & 31;
   const long ray = (long)blockIdx.x*(blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -128,12 +188,15 @@ __global__ void __launch_bounds__(128) k_ion_rates(GridDev g, IonParDev p, IonDe
   if (ray >= nrays) return;
   const int jj = (int)(ray % g.nx[1]), kk = (int)(ray / g.nx[1]);
   const long row = (long)(kk+NG)*g.st[2] + (long)(jj+NG)*g.st[1] + NG;
-  double* ef = ion.edgeflux + ((long)kk*(g.nx[1]+1) + jj)*(g.nx[0]+1);
+  const long efo = ((long)kk*(g.nx[1]+1) + jj)*(g.nx[0]+1);
+  double* ef = ef_out_base + efo;
   const double dx1 = g.dx[0];
   const int nx1 = g.nx[0];
 
   // root level: the time-ramped plane flux; finer levels: the value handed down into EdgeFlux[k][j][0] (ionradplane_3d.c:263-272)
-  const double flux_in = finegrid ? ef[0] : flux_in_root;
+  const double flux_in = finegrid ? ef_in_base[efo] : flux_in_root;
+  unsigned long long count = 0;                       // check_range / compute_dt_hydro of the fused update
+  double m1 = 0.0, m2 = 0.0, m3 = 0.0;
   double carry = flux_in;         // flux entering the current chunk
   bool alive = true;              // false once the ray has been cut
   double dt_chem_min = LARGE, dt_therm_min = LARGE;
@@ -143,7 +206,9 @@ __global__ void __launch_bounds__(128) k_ion_rates(GridDev g, IonParDev p, IonDe
     const int ii = c0 + lane;
     const bool valid = ii < nx1;
     const long c = row + (valid ? ii : nx1-1);
-    const double d = g.U[0][c], M1 = g.U[1][c], M2 = g.U[2][c], M3 = g.U[3][c], E = g.U[4][c], s = g.U[5][c];
+    const double d = g.U[0][c], M1 = g.U[1][c], M2 = g.U[2][c], M3 = g.U[3][c];
+    double E = g.U[4][c], s = g.U[5][c];
+    if (UPDATE && valid) cell_update(g, p, ion, c, dt_upd, d, M1, M2, M3, E, s, count, m1, m2, m3);
 
     // --- ray: tau, attenuation, photoionisation rate
     const double n_H = s / p.m_H;
@@ -254,10 +319,25 @@ __global__ void __launch_bounds__(128) k_ion_rates(GridDev g, IonParDev p, IonDe
     y = __shfl_xor_sync(0xffffffffu, dt_therm_min, o); if (y < dt_therm_min) dt_therm_min = y;
     err |= __shfl_xor_sync(0xffffffffu, err, o);
   }
+  if (UPDATE) {
+    for (int o=16; o>0; o>>=1) {
+      count += __shfl_xor_sync(0xffffffffu, count, o);
+      double y;
+      y = __shfl_xor_sync(0xffffffffu, m1, o); m1 = AB2_MAX(m1, y);
+      y = __shfl_xor_sync(0xffffffffu, m2, o); m2 = AB2_MAX(m2, y);
+      y = __shfl_xor_sync(0xffffffffu, m3, o); m3 = AB2_MAX(m3, y);
+    }
+  }
   if (lane == 0) {
     atomic_min_double(&scal[SC_DT_CHEM], dt_chem_min);
     atomic_min_double(&scal[SC_DT_THERM], dt_therm_min);
     if (err) atomicOr(&scal[SC_ERR], err);
+    if (UPDATE) {
+      if (count) atomicAdd(&scal[SC_COUNT], count);
+      atomic_max_double(&scal[SC_MAXV1], m1);
+      atomic_max_double(&scal[SC_MAXV2], m2);
+      atomic_max_double(&scal[SC_MAXV3], m3);
+    }
   }
 }
 
@@ -273,48 +353,7 @@ __global__ void __launch_bounds__(128) k_ion_update(GridDev g, IonParDev p, IonD
   if (act) {
     const double d = g.U[0][c], M1 = g.U[1][c], M2 = g.U[2][c], M3 = g.U[3][c];
     double E = g.U[4][c], s = g.U[5][c];
-    const double nHdot = ion.nHdot[c];
-    double d_nlim = d*IONFRACFLOOR;
-    d_nlim = d_nlim < p.d_nlo ? d_nlim : p.d_nlo;
-    if ((nHdot > 0) || (s > 1.0001*d_nlim)) {
-      E += ion.edot[c] * dt;
-      s += nHdot * dt * p.m_H;
-    }
-    // floors (apply_temp_floor :70-136, apply_neutral_floor :140-157), keeping the cell's chemistry state: when no
-    // floor fires (the common case) check_range below re-evaluates the very same expressions on the same values,
-    // so the seven divisions are shared; when one fires they are recomputed from the floored E,s as the reference does
-    CellChem cs = chem_state(p, g.Gamma_1, d, M1, M2, M3, E, s);
-    bool changed = false;
-    if (cs.T < p.tfloor) {
-      const double e_sp = p.tfloor * p.k_B / ((cs.x*0.5*p.m_H+(1.0-cs.x)*p.mu) * g.Gamma_1);
-      E = kinetic(d,M1,M2,M3) + e_sp * d; changed = true;
-    }
-    if ((cs.T > p.tceil) && (p.tceil > 0)) {
-      const double e_sp = p.tceil * p.k_B / ((cs.x*0.5*p.m_H+(1.0-cs.x)*p.mu) * g.Gamma_1);
-      E = kinetic(d,M1,M2,M3) + e_sp * d; changed = true;
-    }
-    if (s < d_nlim) { s = d_nlim; changed = true; }
-    else if (s > d) { s = d; changed = true; }
-    g.U[4][c] = E; g.U[5][c] = s;
-    if (changed) cs = chem_state(p, g.Gamma_1, d, M1, M2, M3, E, s);
-
-    // check_range (ionrad_3d.c:222-264)
-    if (!(ion.ph_rate[c] / (p.min_area * cs.n_H) > 2.0*CION)) {
-      const double eth0 = ion.e_th_init[c], e0 = ion.e_init[c], x0 = ion.x_init[c];
-      if ((cs.e_thermal / eth0 >= 1 + p.max_de_therm_step) || (eth0 / cs.e_thermal >= 1 + p.max_de_therm_step)) count = 1;
-      else if ((p.max_de_step > 0) && ((E / e0 >= 1 + p.max_de_step) || (e0 / E >= 1 + p.max_de_step))) count = 1;
-      else if ((p.max_dx_step > 0) && ((cs.x / x0 >= 1 + p.max_dx_step) || (x0 / cs.x >= 1 + p.max_dx_step))) count = 1;
-    }
-    // compute_dt_hydro (:609-663): max over cells of (|v_d|+a)/dx_d.  Division by the positive constant dx_d is
-    // monotone under rounding, so max_c fl(x_c/dx) == fl((max_c x_c)/dx): keep three per-direction maxima here and
-    // divide once on the host (new_dt.c:126-161 has this very form).
-    const double di = 1.0/d;
-    const double v1 = M1*di, v2 = M2*di, v3 = M3*di;
-    const double qsq = v1*v1 + v2*v2 + v3*v3;
-    const double pr = AB2_MAX(g.Gamma_1*(E - 0.5*d*qsq), AB2_TINY);
-    const double asq = g.Gamma*pr*di;
-    const double a = sqrt(asq);
-    m1 = fabs(v1)+a; m2 = fabs(v2)+a; m3 = fabs(v3)+a;
+    cell_update(g, p, ion, c, dt, d, M1, M2, M3, E, s, count, m1, m2, m3);
   }
   for (int o=16; o>0; o>>=1) {
     count += __shfl_xor_sync(0xffffffffu, count, o);
@@ -332,10 +371,11 @@ __global__ void __launch_bounds__(128) k_ion_update(GridDev g, IonParDev p, IonD
 }
 
 __global__ void k_bvals_ionrad(IonDev ion, int nx1, int nx2, int nx3, double flux_i)
-{ // bvals_ionrad.c:308-332 outflow_flux_ix1
+{ // bvals_ionrad.c:308-332 outflow_flux_ix1 (both EdgeFlux buffers: the edge rows j=Nx2, k=Nx3 are never rewritten)
   const long t = (long)blockIdx.x*blockDim.x + threadIdx.x;
   if (t >= (long)(nx2+1)*(nx3+1)) return;
   ion.edgeflux[t*(nx1+1)] = flux_i;
+  ion.edgeflux_alt[t*(nx1+1)] = flux_i;
 }
 
 int ion_bvals_ionrad(ab2_grid* h, double flux_i)
@@ -379,50 +419,77 @@ static int ion_radtransfer_impl(ab2_grid* h, int finegrid, double flux_in, doubl
   const dim3 cgrid((unsigned)((nij+127)/128), (unsigned)g.nx[2], 1);
   const long nrays = (long)g.nx[1]*g.nx[2];
   const unsigned rgrid = (unsigned)((nrays + 3)/4);
+  unsigned long long* hs = h->h_scal;
+
+  // one host<->device round trip of the loop scalars: reset, run `launch`, read back
+  auto reset_scalars = [&]() -> bool {
+    hs[SC_MAXV1] = hs[SC_MAXV2] = hs[SC_MAXV3] = double_to_bits(0.0);
+    hs[SC_DT_CHEM] = double_to_bits(LARGE); hs[SC_DT_THERM] = double_to_bits(LARGE);
+    hs[SC_MAX_DTI] = double_to_bits(0.0); hs[SC_COUNT] = 0;
+    return ab2_check(cudaMemcpyAsync(h->d_scal + SC_MAXV1, hs + SC_MAXV1, 7*sizeof(unsigned long long), cudaMemcpyHostToDevice, st), "ion scalars H2D");
+  };
+  auto read_scalars = [&]() -> bool {
+    return ab2_check(cudaMemcpyAsync(hs + SC_MAXV1, h->d_scal + SC_MAXV1, 8*sizeof(unsigned long long), cudaMemcpyDeviceToHost, st), "ion scalars D2H")
+        && ab2_check(cudaStreamSynchronize(st), "ion sync");
+  };
 
   AB2_LAUNCH(h, KID_ION_PREP, (k_ion_prep<<<cgrid, 128, 0, st>>>(g, p, h->ion)));
 
-  double grid_dt = *dt_io, dt_done = 0.0, dt = 0.0, dt_chem = 0.0, dt_therm = 0.0, dt_hydro = 0.0;
-  int niter = 0, hydro_done = 0, nchem = 0, ntherm = 0, coarsetime_done = 0;
-  while (finegrid || !hydro_done) {
-    // rates + per-cell limits
-    h->h_scal[SC_MAXV1] = h->h_scal[SC_MAXV2] = h->h_scal[SC_MAXV3] = double_to_bits(0.0);
-    h->h_scal[SC_DT_CHEM] = double_to_bits(LARGE); h->h_scal[SC_DT_THERM] = double_to_bits(LARGE);
-    h->h_scal[SC_MAX_DTI] = double_to_bits(0.0); h->h_scal[SC_COUNT] = 0;
-    if (!ab2_check(cudaMemcpyAsync(h->d_scal + SC_MAXV1, h->h_scal + SC_MAXV1, 7*sizeof(unsigned long long),
-                                   cudaMemcpyHostToDevice, st), "ion scalars H2D")) return -1;
-    AB2_LAUNCH(h, KID_ION_RATES, (k_ion_rates<<<rgrid, 128, 0, st>>>(g, p, h->ion, flux_in, finegrid, h->d_scal)));
-    if (!ab2_check(cudaMemcpyAsync(h->h_scal + SC_DT_CHEM, h->d_scal + SC_DT_CHEM, 2*sizeof(unsigned long long),
-                                   cudaMemcpyDeviceToHost, st), "ion scalars D2H")) return -1;
-    if (!ab2_check(cudaMemcpyAsync(h->h_scal + SC_ERR, h->d_scal + SC_ERR, sizeof(unsigned long long),
-                                   cudaMemcpyDeviceToHost, st), "ion err D2H")) return -1;
-    if (!ab2_check(cudaStreamSynchronize(st), "ion rates sync")) return -1;
-    if (h->h_scal[SC_ERR] & ERR_DT_CHEM_NEG) { ab2_set_error("[compute_chem_rates]: dt_chem < 0"); return -2; }
-    double v[2] = { bits_to_double(h->h_scal[SC_DT_CHEM]), bits_to_double(h->h_scal[SC_DT_THERM]) };
-    if (reduce) reduce(v, 2, 0, ctx);
-    dt_chem = v[0]; dt_therm = v[1];
+  // first iteration's rates (ph_rate_init + get_ph_rate_plane + compute_chem_rates + compute_therm_rates, :922-938)
+  if (!reset_scalars()) return -1;
+  AB2_LAUNCH(h, KID_ION_RATES, (k_ion_rates<false><<<rgrid, 128, 0, st>>>(g, p, h->ion, flux_in, finegrid, 0.0, h->ion.edgeflux, h->ion.edgeflux, h->d_scal)));
+  if (!read_scalars()) return -1;
+  if (hs[SC_ERR] & ERR_DT_CHEM_NEG) { ab2_set_error("[compute_chem_rates]: dt_chem < 0"); return -2; }
+  double v[4] = { 0.0, 0.0, bits_to_double(hs[SC_DT_CHEM]), bits_to_double(hs[SC_DT_THERM]) };
+  if (reduce) reduce(v + 2, 2, 0, ctx);
+  double dt_chem = v[2], dt_therm = v[3];
 
+  // Fusing update(n) with rates(n+1) halves the host synchronisations and cross-rank exchanges per iteration but
+  // spends one discarded rates evaluation whenever check_range / dt_hydro end the loop unannounced.  Measured on B200:
+  // a gain where an iteration is launch/latency-bound (small Grids, several ranks), a 2 % loss at 256^3 on one GPU.
+  bool fuse = (reduce != nullptr) || ((long)g.nx[0]*g.nx[1]*g.nx[2] < (4L<<20));
+  if (const char* env = getenv("AB2_ION_FUSE")) fuse = (atoi(env) != 0);
+
+  double grid_dt = *dt_io, dt_done = 0.0, dt = 0.0, dt_hydro = 0.0;
+  int niter = 0, hydro_done = 0, nchem = 0, ntherm = 0, coarsetime_done = 0;
+  while (1) {
     if (dt_chem < dt_therm) nchem++; else ntherm++;          // ionrad_3d.c:943-945
     dt = AB2_MIN(dt_therm, dt_chem);
     if (!finegrid) { if (dt_done + dt > grid_dt) { dt = grid_dt - dt_done; hydro_done = 1; } }
     else if (dt_done + dt > tcoarse) { dt = tcoarse - dt_done; coarsetime_done = 1; }      // :958-961
+    const bool last = hydro_done || coarsetime_done;          // the loop ends after this update whatever it finds
 
-    AB2_LAUNCH(h, KID_ION_UPDATE, (k_ion_update<<<cgrid, 128, 0, st>>>(g, p, h->ion, dt, h->d_scal)));
+    if (!reset_scalars()) return -1;
+    if (last || !fuse) AB2_LAUNCH(h, KID_ION_UPDATE, (k_ion_update<<<cgrid, 128, 0, st>>>(g, p, h->ion, dt, h->d_scal)));
+    else      AB2_LAUNCH(h, KID_ION_FUSED, (k_ion_rates<true><<<rgrid, 128, 0, st>>>(g, p, h->ion, flux_in, finegrid, dt, h->ion.edgeflux, h->ion.edgeflux_alt, h->d_scal)));
     dt_done += dt;
     niter++;
-    if (!ab2_check(cudaMemcpyAsync(h->h_scal + SC_MAXV1, h->d_scal + SC_MAXV1, 7*sizeof(unsigned long long),
-                                   cudaMemcpyDeviceToHost, st), "ion scalars D2H")) return -1;
-    if (!ab2_check(cudaStreamSynchronize(st), "ion update sync")) return -1;
-    double cnt = (double)h->h_scal[SC_COUNT];
+    if (!read_scalars()) return -1;
+    if (hs[SC_ERR] & ERR_DT_CHEM_NEG) { ab2_set_error("[compute_chem_rates]: dt_chem < 0"); return -2; }
     double mx = 0.0;
-    for (int dd=0; dd<3; dd++) if (g.nx[dd] > 1) { const double x = bits_to_double(h->h_scal[SC_MAXV1+dd])/g.dx[dd]; mx = AB2_MAX(mx, x); }
-    if (reduce) { double cm[2] = { cnt, mx }; reduce(cm, 2, 3, ctx); cnt = cm[0]; mx = cm[1]; }   // one exchange: {SUM count, MAX 1/dt_hydro}
+    for (int dd=0; dd<3; dd++) if (g.nx[dd] > 1) { const double x = bits_to_double(hs[SC_MAXV1+dd])/g.dx[dd]; mx = AB2_MAX(mx, x); }
+    v[0] = (double)hs[SC_COUNT]; v[1] = mx; v[2] = bits_to_double(hs[SC_DT_CHEM]); v[3] = bits_to_double(hs[SC_DT_THERM]);
+    if (reduce) reduce(v, 4, 4, ctx);        // one exchange per iteration: {SUM count, MAX 1/dt_hydro, MIN dt_chem, MIN dt_therm}
 
-    if (finegrid) { if (coarsetime_done) { grid_dt = dt_done; break; } continue; }        // :1008-1012
-    if (cnt > MAXCELLCOUNT) { grid_dt = dt_done; break; }      // check_range (:982)
-    if (hydro_done) break;                                     // :989
-    dt_hydro = cour_no/mx;                                     // :997
-    if (dt_hydro < dt_done) { grid_dt = dt_done; break; }
+    if (finegrid) { if (coarsetime_done) { grid_dt = dt_done; break; } }                   // :1008-1012
+    else {
+      if (v[0] > MAXCELLCOUNT) { grid_dt = dt_done; break; }   // check_range (:982)
+      if (hydro_done) break;                                   // :989
+      dt_hydro = cour_no/v[1];                                 // :997
+      if (dt_hydro < dt_done) { grid_dt = dt_done; break; }
+    }
+    if (fuse) {            // continue: the rates computed behind this update become current
+      std::swap(h->ion.edgeflux, h->ion.edgeflux_alt);
+      dt_chem = v[2]; dt_therm = v[3];
+    } else {               // separate rates pass of the next iteration
+      if (!reset_scalars()) return -1;
+      AB2_LAUNCH(h, KID_ION_RATES, (k_ion_rates<false><<<rgrid, 128, 0, st>>>(g, p, h->ion, flux_in, finegrid, 0.0, h->ion.edgeflux, h->ion.edgeflux, h->d_scal)));
+      if (!read_scalars()) return -1;
+      if (hs[SC_ERR] & ERR_DT_CHEM_NEG) { ab2_set_error("[compute_chem_rates]: dt_chem < 0"); return -2; }
+      v[2] = bits_to_double(hs[SC_DT_CHEM]); v[3] = bits_to_double(hs[SC_DT_THERM]);
+      if (reduce) reduce(v + 2, 2, 0, ctx);
+      dt_chem = v[2]; dt_therm = v[3];
+    }
   }
   if (!finegrid) {
     if (niter == h->maxiter) grid_dt = dt_done;                // :1022

@@ -148,7 +148,7 @@ __global__ void k_smr_prolongate(GridDev pa, GridDev ch, OvDev o, int nvar, int 
 }
 
 // ---- ionising flux hand-down: parent EdgeFlux plane at the child's upstream x1 face -> child EdgeFlux[..][..][0] ----
-__global__ void k_smr_ion_prolong(GridDev pa, GridDev ch, OvDev o, const double* efp, double* efc)
+__global__ void k_smr_ion_prolong(GridDev pa, GridDev ch, OvDev o, const double* efp, double* efc_cur, double* efc_alt)
 {
   const int nj = o.ce[1]-o.cs[1]+2, nk = o.ce[2]-o.cs[2]+2;
   const long t = (long)blockIdx.x*blockDim.x + threadIdx.x;
@@ -159,7 +159,7 @@ __global__ void k_smr_ion_prolong(GridDev pa, GridDev ch, OvDev o, const double*
   // :293-294 writes `k*2 - Disp` with k parent-local, which is right only below a root-level parent; the
   // same cell in parent-relative form, identical for level 1 and meaningful for deeper levels:
   const int ks = 2*(k - (o.cs[2]-NG)), js = 2*(j - (o.cs[1]-NG));
-#define EFC(kk,jj) efc[((long)(kk)*ce2 + (jj))*ce1]
+#define EFC(kk,jj) efc_cur[((long)(kk)*ce2 + (jj))*ce1] = efc_alt[((long)(kk)*ce2 + (jj))*ce1]
   EFC(ks,js) = val;
   if (j < (o.ce[1]+1-NG)) {
     if (k < (o.ce[2]+1-NG)) { EFC(ks+1,js+1) = val; EFC(ks,js+1) = val; EFC(ks+1,js) = val; }
@@ -233,7 +233,7 @@ int ab2_smr_ion_prolong(ab2_grid* pa, ab2_grid* ch, const ab2_overlap* o)
   if (!od.face[0]) return 0;
   if (!stream_wait(ch->stream, pa->stream)) return -1;
   const long n = (long)(od.ce[1]-od.cs[1]+2)*(od.ce[2]-od.cs[2]+2);
-  AB2_LAUNCH(ch, KID_SMR_PROLONG, (k_smr_ion_prolong<<<(unsigned)((n+127)/128), 128, 0, ch->stream>>>(pa->g, ch->g, od, pa->ion.edgeflux, ch->ion.edgeflux)));
+  AB2_LAUNCH(ch, KID_SMR_PROLONG, (k_smr_ion_prolong<<<(unsigned)((n+127)/128), 128, 0, ch->stream>>>(pa->g, ch->g, od, pa->ion.edgeflux, ch->ion.edgeflux, ch->ion.edgeflux_alt)));
   if (!stream_wait(pa->stream, ch->stream)) return -1;
   return ab2_check(cudaGetLastError(), "ionrad_prolong") ? 0 : -1;
 }

@@ -130,18 +130,18 @@ class Run:
         ops = {0: dist.ReduceOp.MIN, 1: dist.ReduceOp.MAX, 2: dist.ReduceOp.SUM}
         dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
         world = dist.get_world_size()
-        buf = torch.zeros(2, dtype=torch.float64, device=dev)
-        gat = torch.zeros(2 * world, dtype=torch.float64, device=dev)
-        host = torch.zeros(2, dtype=torch.float64).pin_memory() if dev == "cuda" else torch.zeros(2, dtype=torch.float64)
+        buf = torch.zeros(4, dtype=torch.float64, device=dev)
+        gat = torch.zeros(4 * world, dtype=torch.float64, device=dev)
+        host = torch.zeros(4, dtype=torch.float64).pin_memory() if dev == "cuda" else torch.zeros(4, dtype=torch.float64)
 
         def reduce(vals, op):
             n = len(vals)
             host[:n] = torch.from_numpy(vals)
             buf[:n].copy_(host[:n], non_blocking=True)
-            if op == 3:          # {SUM, MAX} in one exchange: gather the pairs, combine locally
+            if op == 4:          # {SUM, MAX, MIN, MIN} in one exchange: gather the quadruples, combine locally
                 dist.all_gather_into_tensor(gat, buf)
-                g = gat.cpu().view(world, 2)
-                return np.array([float(g[:, 0].sum()), float(g[:, 1].max())])
+                g = gat.cpu().view(world, 4)
+                return np.array([float(g[:, 0].sum()), float(g[:, 1].max()), float(g[:, 2].min()), float(g[:, 3].min())])
             dist.all_reduce(buf[:n], op=ops[op])
             return buf[:n].cpu().numpy()
         return reduce

@@ -49,7 +49,7 @@ KERNEL_BYTES = {
     "k_correct<0>": (6, 1, 4), "k_correct<1>": (6, 1, 4), "k_correct<2>": (6, 1, 4),
     "k_final<0>": (3, 3, 0), "k_final<1>": (3, 3, 0), "k_final<2>": (3, 3, 0),
     "k_update": (5, 0, 5),
-    "k_ion_prep": (0, 11.5, 0), "k_ion_rates": (0, 11, 0), "k_ion_update": (0, 14, 0),
+    "k_ion_prep": (0, 11.5, 0), "k_ion_rates": (0, 11, 0), "k_ion_update": (0, 14, 0), "k_ion_rates<fused update>": (0, 19, 0),
     "k_max_speeds": (0, 5, 0),
 }
 

@@ -58,8 +58,9 @@ typedef struct ab2_ion_par {
 
 /* StaticGravPot: athena.h:503 GravPotFun_t, globals.h:24 */
 typedef double (*ab2_grav_pot_fn)(double x1, double x2, double x3);
-/* Combines scalars over the Grids of one Domain; op: 0 MIN, 1 MAX, 2 SUM, 3 = vals[0] SUM and vals[1] MAX in one
- * exchange (n == 2).  Stands where the reference calls MPI_Allreduce (new_dt.c:175-179; ionrad_3d.c:275,399,554,672). */
+/* Combines scalars over the Grids of one Domain; op: 0 MIN, 1 MAX, 2 SUM, 4 = the four sub-cycle scalars of one ion
+ * iteration in ONE exchange (n == 4: vals[0] SUM, vals[1] MAX, vals[2..3] MIN).  Stands where the reference calls
+ * MPI_Allreduce (new_dt.c:175-179; ionrad_3d.c:275,399,554,672). */
 typedef void (*ab2_reduce_fn)(double* vals, int n, int op, void* ctx);
 
 /* ---- lifetime ------------------------------------------------------------------------------------ */

@@ -53,7 +53,8 @@ def _worker(rank, world, port, bc, q):
         v = np.array([1.0 + rank, 10.0 - rank])
         ok_red = (np.array_equal(red(v, 0), [1.0, 10.0 - (world - 1)]) and np.array_equal(red(v, 1), [float(world), 10.0])
                   and np.array_equal(red(v, 2), [sum(1.0 + r for r in range(world)), sum(10.0 - r for r in range(world))]))
-        ok_red = ok_red and np.array_equal(red(v, 3), [sum(1.0 + r for r in range(world)), 10.0])
+        v4 = np.array([1.0 + rank, 10.0 - rank, 5.0 + rank, 7.0 - rank])
+        ok_red = ok_red and np.array_equal(red(v4, 4), [sum(1.0 + r for r in range(world)), 10.0, 5.0, 7.0 - (world - 1)])
         q.put((rank, ok_exchange, ok_red))
     finally:
         dist.destroy_process_group()
