@@ -11,8 +11,10 @@
 //                  prefix product with the reference's 1e-3 ray cut, then photo/chem/thermal rates and the
 //                  per-cell dt limits of those same cells while they are in registers.
 //   k_ion_update : E,s update, temperature and neutral floors, check_range count and the new hydro dt.
-// exp/pow come from the CUDA math library (<= 2 ulp) and the prefix product reassociates the flux
-// products, so this path agrees with the reference to ~1e-13 relative per iteration, not bit for bit.
+// Arithmetic: every per-cell formula keeps the reference's operations and order; exp() and pow() are the host glibc's
+// own algorithms re-implemented operation for operation (glibc_math.cuh), and the attenuation along a ray is the
+// reference's sequential product.  On hosts whose libm selects the same (FMA) variants this path is bit-identical to
+// the reference, sub-cycle decisions included; tests hold it to <= 1e-10 per cell after a step in any case.
 #include <float.h>
 #include <math.h>
 #include <stdlib.h>
@@ -20,6 +22,7 @@
 #include <utility>
 #include "engine.cuh"
 #include "physics.cuh"
+#include "glibc_math.cuh"
 
 #define NG AB2_NG
 #define MINFLUXFRAC 1.0e-3     // ionrad.h:26
@@ -213,16 +216,17 @@ __global__ void __launch_bounds__(128) k_ion_rates(GridDev g, IonParDev p, IonDe
     // --- ray: tau, attenuation, photoionisation rate
     const double n_H = s / p.m_H;
     const double tau = p.sigma_ph * n_H * dx1;
-    const double etau = valid ? exp(-tau) : 1.0;
-    double incl = etau;
+    const double etau = valid ? gl_exp(-tau) : 1.0;
+    // flux entering each cell = the reference's sequential product ((F*e0)*e1)*... (ionradplane_3d.c:298 `flux *= etau`):
+    // every lane applies the attenuation factors of the lanes before it IN ORDER (32 broadcast+multiply steps in
+    // lockstep).  A log-step prefix scan would be 5 steps but reassociates the product, and a last-bit difference in a
+    // flux is enough to flip a check_range / dt decision of the sub-cycle tens of steps later.
+    double flux_before = carry;
 #pragma unroll
-    for (int o=1; o<32; o<<=1) {
-      const double y = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl *= y;
+    for (int l=0; l<31; l++) {
+      const double el = __shfl_sync(0xffffffffu, etau, l);
+      if (lane > l) flux_before *= el;
     }
-    double excl = __shfl_up_sync(0xffffffffu, incl, 1);
-    if (lane == 0) excl = 1.0;
-    const double flux_before = carry*excl;
     const double flux_after = flux_before*etau;
     const double flux_frac = flux_after / (flux_in + 1e-12);
     const unsigned cutmask = __ballot_sync(0xffffffffu, valid && (flux_frac < MINFLUXFRAC));
@@ -242,7 +246,7 @@ __global__ void __launch_bounds__(128) k_ion_rates(GridDev g, IonParDev p, IonDe
       const CellChem cs = chem_state(p, g.Gamma_1, d, M1, M2, M3, E, s);
       double T = cs.T;
       if (T < p.tfloor) T = p.tfloor;
-      double nHdot = 2.59e-13*pow(T/1.0e4, -0.7) * p.time_unit * cs.n_e * cs.n_Hplus - ph * cs.n_H;
+      double nHdot = 2.59e-13*gl_pow(T/1.0e4, -0.7) * p.time_unit * cs.n_e * cs.n_Hplus - ph * cs.n_H;
       int st = ion.sign_state[c];
       int last_sign = (st & 3) - 1, sign_count = st >> 2;
       if (nHdot < 0.0) {
@@ -284,8 +288,8 @@ __global__ void __launch_bounds__(128) k_ion_rates(GridDev g, IonParDev p, IonDe
       if (cs.T < p.tfloor) { edot = 0.0; constrain = false; }
       else if ((nHdot < 0) && (s < 1.0001*d_nlim)) { edot = 0.0; constrain = false; }
       else {
-        const double rc = (cs.T < 100.0) ? 0.0 : 6.11e-10*pow(cs.T,-0.89)*KB*cs.T;
-        const double lya = -7.5e-19*cs.n_e*cs.n_H*exp(-118348/cs.T);
+        const double rc = (cs.T < 100.0) ? 0.0 : 6.11e-10*gl_pow(cs.T,-0.89)*KB*cs.T;
+        const double lya = -7.5e-19*cs.n_e*cs.n_H*gl_exp(-118348/cs.T);
         edot = ph * p.e_gamma * cs.n_H
           - rc * p.time_unit * cs.n_Hplus * cs.n_e
           + lya * p.time_unit;

@@ -5,6 +5,7 @@
 #include "../../include/athena_b200.h"
 #include "engine.cuh"
 #include "physics.cuh"
+#include "glibc_math.cuh"
 
 static __device__ __forceinline__ S6 ld6(const double* p) { S6 r; r.d=p[0]; r.x=p[1]; r.y=p[2]; r.z=p[3]; r.e=p[4]; r.s=p[5]; return r; }
 static __device__ __forceinline__ void st6(double* p, const S6& r) { p[0]=r.d; p[1]=r.x; p[2]=r.y; p[3]=r.z; p[4]=r.e; p[5]=r.s; }
@@ -65,6 +66,14 @@ __global__ void k_unit_ieee(int n, const double* a, const double* b, double* qf,
   if (bad_sqrt) { sf[t] = se[t]; atomicAdd(&nbad[1], 1); }
 }
 
+__global__ void k_unit_libm(int n, const double* x, const double* y, double* e, double* p)
+{
+  const int t = blockIdx.x*blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  e[t] = gl_exp(x[t]);
+  p[t] = gl_pow(y[t], x[t]);       // base y[t], exponent x[t]
+}
+
 struct DevBuf {
   double* p = nullptr;
   DevBuf(size_t n, const double* host = nullptr) { if (cudaMalloc(&p, n*sizeof(double)) != cudaSuccess) p = nullptr; else if (host) cudaMemcpy(p, host, n*sizeof(double), cudaMemcpyHostToDevice); else cudaMemset(p, 0, n*sizeof(double)); }
@@ -109,6 +118,16 @@ int ab2_unit_ieee(int n, const double* a, const double* b, double* q_fast, doubl
             ab2_check(cudaMemcpy(nrejected, nb, 2*sizeof(int), cudaMemcpyDeviceToHost), "unit ieee");
   cudaFree(nb);
   return ok ? 0 : -1;
+}
+
+int ab2_unit_libm(int n, const double* x, const double* y, double* exp_x, double* pow_y_x)
+{
+  DevBuf X(n,x), Y(n,y), E(n), Pw(n);
+  if (!X.p || !Y.p || !E.p || !Pw.p) { ab2_set_error("[ab2_unit_libm]: cudaMalloc failed"); return -1; }
+  k_unit_libm<<<(n+127)/128,128>>>(n, X.p, Y.p, E.p, Pw.p);
+  if (!ab2_check(cudaMemcpy(exp_x, E.p, n*sizeof(double), cudaMemcpyDeviceToHost), "unit libm")) return -1;
+  if (!ab2_check(cudaMemcpy(pow_y_x, Pw.p, n*sizeof(double), cudaMemcpyDeviceToHost), "unit libm")) return -1;
+  return 0;
 }
 
 int ab2_unit_lr_states(int npencil, int n, const double* W, int nscal, double gamma, double dt, double dx,

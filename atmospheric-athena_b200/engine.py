@@ -65,7 +65,7 @@ EXPORTS = ["ab2_last_error", "ab2_version", "ab2_device_count", "ab2_grid_create
            "ab2_download_edgeflux", "ab2_device_ptr", "ab2_bvals_mhd", "ab2_max_wave_speeds", "ab2_new_dt",
            "ab2_set_static_grav_pot", "ab2_integrate_3d_ctu", "ab2_set_fixed_cells", "ab2_apply_fixed_cells",
            "ab2_ion_init", "ab2_ion_derived", "ab2_bvals_ionrad", "ab2_ion_entering_flux", "ab2_ion_radtransfer_3d",
-           "ab2_unit_roe_flux", "ab2_unit_convert", "ab2_unit_lr_states", "ab2_unit_ieee",
+           "ab2_unit_roe_flux", "ab2_unit_convert", "ab2_unit_lr_states", "ab2_unit_ieee", "ab2_unit_libm",
            "ab2_profile_enable", "ab2_profile_kernels", "ab2_profile_kernel_name", "ab2_profile_read",
            "ab2_smr_restrict_correct", "ab2_smr_ion_restrict", "ab2_smr_prolongate", "ab2_smr_ion_prolong",
            "ab2_ion_radtransfer_3d_fine", "ab2_ion_coarse_time"]
@@ -139,6 +139,7 @@ def lib():
     L.ab2_profile_kernel_name.restype = C.c_char_p
     L.ab2_profile_read.argtypes = [vp, dp, C.POINTER(C.c_longlong), C.c_int]
     L.ab2_unit_ieee.argtypes = [C.c_int, dp, dp, dp, dp, dp, dp, C.POINTER(C.c_int)]
+    L.ab2_unit_libm.argtypes = [C.c_int, dp, dp, dp, dp]
     L.ab2_unit_roe_flux.argtypes = [C.c_int, dp, dp, dp, dp, C.c_int, C.c_double, dp, dp]
     L.ab2_unit_convert.argtypes = [C.c_int, dp, C.c_int, C.c_double, C.c_int, dp, dp]
     L.ab2_unit_lr_states.argtypes = [C.c_int, C.c_int, dp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, dp, dp]

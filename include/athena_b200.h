@@ -162,6 +162,8 @@ int ab2_unit_convert(int n, const double* in, int nscal, double gamma, int to_pr
 /* a/b and sqrt(a) through the engine's branch-free IEEE refinement (csrc/physics.cuh Arith<true>, plain operators where
  * its range test rejects the operands) next to the plain operators; nrejected[2] = rejected divisions, square roots */
 int ab2_unit_ieee(int n, const double* a, const double* b, double* q_fast, double* q_exact, double* s_fast, double* s_exact, int* nrejected);
+/* exp(x[i]) and pow(y[i], x[i]) as the ion kernels evaluate them (csrc/glibc_math.cuh: the host glibc's algorithms) */
+int ab2_unit_libm(int n, const double* x, const double* y, double* exp_x, double* pow_y_x);
 /* lr_states() of reconstruction/lr_states_plm.c:62-374 on npencil pencils of n cells */
 int ab2_unit_lr_states(int npencil, int n, const double* W, int nscal, double gamma, double dt, double dx,
                        int il, int iu, double* Wl, double* Wr);

@@ -1,0 +1,68 @@
+"""north_star bars that need many steps: volume-L1 <= 1e-8 after 100 steps and the ionisation-front position within
+one cell, against the reference binary (oracle/_ref, prebuilt; travels with the snapshot) run on the box's host."""
+import os
+import re
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from cases import ROOT, DECKS, VARS
+from athena_b200.athinput import ParFile
+from athena_b200.restart import read_restart
+
+pytestmark = pytest.mark.gpu
+
+
+def reference_run(build, deck, overrides, nlim):
+    exe = os.path.join(ROOT, "oracle", "_ref", build, "athena")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref not built")
+    with tempfile.TemporaryDirectory() as tmp:
+        r = subprocess.run([exe, "-i", os.path.join(DECKS, deck), f"time/nlim={nlim}"] + overrides, cwd=tmp, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-1000:]
+        rst = sorted(f for f in os.listdir(tmp) if f.endswith(".rst"))
+        d0, d1 = read_restart(os.path.join(tmp, rst[0])), read_restart(os.path.join(tmp, rst[-1]))
+    rad = [int(a) for a in re.findall(r"Radiation done in (\d+) iterations", r.stderr)]
+    return d0, d1, rad
+
+
+def engine_run(problem, deck, overrides, nlim, U0):
+    from athena_b200.driver import Run
+    par = ParFile.par_open(os.path.join(DECKS, deck))
+    par.par_cmdline(overrides)
+    R = Run(par, problem, device=0, U0=U0)
+    R.run(nlim)
+    return R
+
+
+def volume_l1(a, b):
+    """sum |a-b| dV / sum |b| dV (uniform cells)"""
+    return float(np.abs(a - b).sum() / np.abs(b).sum())
+
+
+@pytest.mark.parametrize("problem,deck,ov", [
+    ("blast", "blast.athinput", ["domain1/Nx1=32", "domain1/Nx2=32", "domain1/Nx3=32", "problem/radius=0.2"]),
+    ("ifront", "ifront.athinput", ["domain1/Nx1=48", "domain1/Nx2=16", "domain1/Nx3=16"]),
+])
+def test_100_steps_volume_l1(problem, deck, ov):
+    d0, d1, rad = reference_run(problem, deck, ov, 100)
+    nv = 6 if problem != "blast" else 5
+    U0 = {v: d0["grids"][0][v] for v in VARS[:nv]}
+    R = engine_run(problem, deck, ov, 100, U0)
+    assert R.nstep == d1["nstep"] == 100
+    out = R.G.download_active()
+    assert abs(R.time - d1["time"]) <= 1e-10 * d1["time"]
+    for v in ("d", "E") + (("s",) if nv == 6 else ()):
+        l1 = volume_l1(out[v], d1["grids"][0][v])
+        assert l1 <= 1e-8, f"{problem}: volume-L1 of {v} after 100 steps = {l1:.3e}"
+    # momenta relative to the total momentum scale sum(d*cs)
+    ref = d1["grids"][0]
+    scale = (ref["d"] * np.sqrt(5 / 3 * (2 / 3) * np.abs(ref["E"]) / ref["d"])).sum()
+    for v in ("M1", "M2", "M3"):
+        assert np.abs(out[v] - ref[v]).sum() / scale <= 1e-8, v
+    if problem == "ifront":
+        assert [r[0] for r in R.rad_log] == rad, "sub-cycle iteration counts over 100 steps"
+        front = lambda U: np.argmax((U["s"] / U["d"]) >= 0.5, axis=2)
+        assert np.abs(front(out) - front(ref)).max() <= 1, "I-front position within one cell on every ray"

@@ -75,6 +75,32 @@ def test_fast_ieee_division_and_sqrt_are_correctly_rounded():
     assert nrej[0] < n // 100 and nrej[1] > n // 3             # divisions: few rejected; square roots: the negative half is
 
 
+def test_glibc_math_matches_host_libm_bit_for_bit():
+    """The ion kernels' exp()/pow() (csrc/glibc_math.cuh) against the host libm the reference links, on the arguments
+    the path produces: exp(-tau), exp(-118348/T), pow(T/1e4,-0.7), pow(T,-0.89), plus wide random ranges."""
+    import ctypes.util
+    import math
+    L = engine().lib()
+    rng = np.random.default_rng(11)
+    n = 1 << 21
+    x = np.concatenate([-10.0 ** rng.uniform(-12, 3.2, n // 4), rng.uniform(-745, 709, n // 4),
+                        np.full(n // 4, -0.7), np.full(n // 4, -0.89)])
+    y = np.concatenate([rng.uniform(0.5, 2, n // 4), 10.0 ** rng.uniform(-300, 300, n // 4),
+                        10.0 ** rng.uniform(-4, 6, n // 4), 10.0 ** rng.uniform(0, 9, n // 4)])
+    x[:8] = [0.0, -0.0, 1e-300, -1e-300, -745.2, -800.0, 710.0, -1e-17]
+    e = np.empty(n); p = np.empty(n)
+    assert L.ab2_unit_libm(n, P(x), P(y), P(e), P(p)) == 0
+    libm = C.CDLL(ctypes.util.find_library("m"))          # the host libm itself: no Python range errors in the way
+    libm.exp.restype = C.c_double; libm.exp.argtypes = [C.c_double]
+    libm.pow.restype = C.c_double; libm.pow.argtypes = [C.c_double, C.c_double]
+    he = np.array([libm.exp(v) for v in x[:n // 2]])
+    assert np.array_equal(e[:n // 2], he), f"exp differs in {(e[:n//2] != he).sum()} of {n//2}"
+    for sel in (np.r_[n // 2:n], np.r_[0:n // 4]):
+        hp = np.array([libm.pow(b, a) for b, a in zip(y[sel], x[sel])])
+        bad = p[sel] != hp
+        assert not bad.any(), f"pow differs in {bad.sum()} of {len(sel)}: {y[sel][bad][:4]} ^ {x[sel][bad][:4]}"
+
+
 def gpu_run(case):
     from athena_b200.driver import Run
     R = Run(case.par, case.build, device=0, U0=case.U0)
