@@ -179,84 +179,104 @@ class Run:
 
 
 class SmrRun:
-    """main.c:355-669 with STATIC_MESH_REFINEMENT for a root Domain and one level-1 Domain (one Grid each, one GPU):
-    RestrictCorrect / Prolongate / ionradRestrictCorrect / ionrad_prolong between the two device mirrors, one dt for
-    the whole Mesh (new_dt.c:58-195), the fine level's radiation sub-cycle running to the root's coarse time."""
+    """main.c:355-669 with STATIC_MESH_REFINEMENT for a nest of single-Grid Domains on one GPU (root + one Domain per
+    finer level, `job/num_domains` of them): RestrictCorrect / Prolongate / ionradRestrictCorrect / ionrad_prolong
+    between the device mirrors of adjacent levels, one dt for the whole Mesh (new_dt.c:58-195), every fine level's
+    radiation sub-cycle running to the root's coarse time."""
 
-    def __init__(self, par, problem: str, U0: dict, U0L1: dict, device: int = 0):
+    def __init__(self, par, problem: str, U0: dict, *U0_fine: dict, device: int = 0):
         p = par
         self.ion = problem in ("ifront", "ioniz_sphere")
         self.nscal = 1 if self.ion else 0
+        nlev = 1 + len(U0_fine)
         nx0 = tuple(p.par_geti("domain1", f"Nx{a}") for a in (1, 2, 3))
         xmin = [p.par_getd("domain1", f"x{a}min") for a in (1, 2, 3)]
         xmax = [p.par_getd("domain1", f"x{a}max") for a in (1, 2, 3)]
         dx0 = tuple((xmax[a] - xmin[a]) / nx0[a] for a in range(3))
-        nx1 = tuple(p.par_geti("domain2", f"Nx{a}") for a in (1, 2, 3))
-        disp1 = tuple(p.par_geti("domain2", k) for k in ("iDisp", "jDisp", "kDisp"))
-        dx1 = tuple(dx0[a] / 2.0 for a in range(3))
-        xmin1 = tuple(xmin[a] if disp1[a] == 0 else xmin[a] + float(disp1[a]) * dx1[a] for a in range(3))   # init_mesh.c:377-382
-        self.bc0 = [p.par_geti("domain1", k) for k in ("bc_ix1", "bc_ox1", "bc_ix2", "bc_ox2", "bc_ix3", "bc_ox3")]
-        self.bc1 = []
-        for a in range(3):      # interior faces of the child are prolongated, not BC'd (bvals_mhd.c:549-550 ProlongateLater)
-            self.bc1.append(self.bc0[2 * a] if disp1[a] == 0 else 0)
-            self.bc1.append(self.bc0[2 * a + 1] if (disp1[a] + nx1[a]) // 2 == nx0[a] else 0)
+        bc0 = [p.par_geti("domain1", k) for k in ("bc_ix1", "bc_ox1", "bc_ix2", "bc_ox2", "bc_ix3", "bc_ox3")]
         self.gamma = p.par_getd("problem", "gamma")
         self.cour_no = p.par_getd("time", "cour_no")
         self.tlim = p.par_getd("time", "tlim")
         self.flux_i = p.par_getd("problem", "flux") if self.ion else 0.0
-        self.o = engine.make_overlap(nx1, disp1, nx0)
-        self.root = engine.Grid(nx0, dx0, xmin, self.gamma, self.nscal, device=device)
-        self.child = engine.Grid(nx1, dx1, xmin1, self.gamma, self.nscal, device=device)
-        self.root.upload_active(U0)
-        self.child.upload_active(U0L1)
+        self.grids, self.bcs, self.ovs, disps = [], [], [], []
+        for n in range(nlev):
+            blk = f"domain{n + 1}"
+            nx = tuple(p.par_geti(blk, f"Nx{a}") for a in (1, 2, 3))
+            disp = (0, 0, 0) if n == 0 else tuple(p.par_geti(blk, k) for k in ("iDisp", "jDisp", "kDisp"))
+            dx = tuple(dx0[a] / 2.0 ** n for a in range(3))
+            xm = tuple(xmin[a] if disp[a] == 0 else xmin[a] + float(disp[a]) * dx[a] for a in range(3))   # init_mesh.c:377-382
+            bc = []             # interior faces of a child are prolongated, not BC'd (bvals_mhd.c:549-550 ProlongateLater)
+            for a in range(3):
+                bc.append(bc0[2 * a] if disp[a] == 0 else 0)
+                bc.append(bc0[2 * a + 1] if (disp[a] + nx[a]) // 2 ** n == nx0[a] else 0)
+            if n > 0:
+                self.ovs.append(engine.make_overlap(nx, disp, nx0, level=n, parent_disp=disps[-1]))
+            G = engine.Grid(nx, dx, xm, self.gamma, self.nscal, device=device)
+            G.upload_active(U0 if n == 0 else U0_fine[n - 1])
+            self.grids.append(G); self.bcs.append(bc); disps.append(disp)
         if self.ion:
             ip = engine.ion_par_from(p, dx0)                    # min_area, d_nlo from the ROOT spacing (ionrad.c:115-131)
-            self.root.ion_init(ip); self.child.ion_init(ip)
+            for G in self.grids:
+                G.ion_init(ip)
+        self.root = self.grids[0]
+        self.child = self.grids[1] if nlev > 1 else None
         self.time, self.dt, self.nstep = 0.0, 0.0, 0
-        self.dt0 = self.dt1 = 0.0                               # GridS.dt of the two Grids
+        self.gdt = [0.0] * nlev                                 # GridS.dt per level
         self.rad_log = []
         # main.c:400-451
-        self.root.smr_restrict_correct(self.child, self.o, 0.0)
-        self.root.bvals_mhd(self.bc0); self.child.bvals_mhd(self.bc1)
+        for n in range(nlev - 2, -1, -1):
+            self.grids[n].smr_restrict_correct(self.grids[n + 1], self.ovs[n], 0.0)
+        for G, bc in zip(self.grids, self.bcs):
+            G.bvals_mhd(bc)
         if self.ion:                                            # bvals_ionrad.c:27-29,178: the first Domain's BC function wins
-            self.root.bvals_ionrad(self.flux_i); self.child.bvals_ionrad(self.flux_i)
-        self.root.smr_prolongate(self.child, self.o)
+            for G in self.grids:
+                G.bvals_ionrad(self.flux_i)
+        for n in range(nlev - 1):
+            self.grids[n].smr_prolongate(self.grids[n + 1], self.ovs[n])
         self.new_dt()
 
     def new_dt(self):
         max_dti = 0.0
-        for G in (self.root, self.child):
+        max_v = [0.0, 0.0, 0.0]      # new_dt.c:53: never reset between Grids -> running maximum over the levels so far
+        for G in self.grids:
             v = G.max_wave_speeds()
             for a in range(3):
                 if G.nx[a] > 1:
-                    x = v[a] / G.dx[a]
+                    max_v[a] = max_v[a] if max_v[a] > v[a] else v[a]
+                    x = max_v[a] / G.dx[a]
                     max_dti = max_dti if max_dti > x else x
         dt = self.cour_no / max_dti if self.nstep == 0 else min(2.0 * self.dt, self.cour_no / max_dti)
         if self.time < self.tlim and (self.tlim - self.time) < dt:
             dt = self.tlim - self.time
-        self.dt = self.dt0 = self.dt1 = dt
+        self.dt = dt
+        self.gdt = [dt] * len(self.grids)
         return dt
 
     def step(self):
+        g, nlev = self.grids, len(self.grids)
         if self.ion:
-            self.dt0, ni, nt, nc = self.root.ion_radtransfer_3d(self.flux_i, self.time, self.cour_no, self.dt0)
-            self.rad_log.append((ni, nt, nc, self.dt0))
-            self.dt = self.dt0
-            self.root.bvals_mhd(self.bc0)
-            self.root.smr_ion_prolong(self.child, self.o)
-            self.dt1, ni, nt, nc = self.child.ion_radtransfer_3d_fine(self.root.ion_coarse_time, self.dt1)
-            self.rad_log.append((ni, nt, nc, self.dt1))
-            self.dt = self.dt1                                   # ionrad_3d.c:1033
-            self.child.bvals_mhd(self.bc1)
-            self.root.smr_ion_restrict(self.child, self.o)
-        self.root.integrate_3d_ctu(self.dt0)
-        self.child.integrate_3d_ctu(self.dt1)
-        self.root.smr_restrict_correct(self.child, self.o, self.dt0)
+            for n in range(nlev):                               # main.c:546-556, coarse to fine
+                if n == 0:
+                    self.gdt[0], ni, nt, nc = g[0].ion_radtransfer_3d(self.flux_i, self.time, self.cour_no, self.gdt[0])
+                else:
+                    g[n - 1].smr_ion_prolong(g[n], self.ovs[n - 1])
+                    self.gdt[n], ni, nt, nc = g[n].ion_radtransfer_3d_fine(g[0].ion_coarse_time, self.gdt[n])
+                self.rad_log.append((ni, nt, nc, self.gdt[n]))
+                self.dt = self.gdt[n]                           # ionrad_3d.c:1033
+                g[n].bvals_mhd(self.bcs[n])
+            for n in range(nlev - 2, -1, -1):                   # ionradRestrictCorrect, finest pair first
+                g[n].smr_ion_restrict(g[n + 1], self.ovs[n])
+        for n in range(nlev):
+            g[n].integrate_3d_ctu(self.gdt[n])
+        for n in range(nlev - 2, -1, -1):                       # RestrictCorrect, finest pair first
+            g[n].smr_restrict_correct(g[n + 1], self.ovs[n], self.gdt[n])
         self.nstep += 1
         self.time += self.dt
         self.new_dt()
-        self.root.bvals_mhd(self.bc0); self.child.bvals_mhd(self.bc1)
-        self.root.smr_prolongate(self.child, self.o)
+        for n in range(nlev):
+            g[n].bvals_mhd(self.bcs[n])
+        for n in range(nlev - 1):                               # Prolongate, root first
+            g[n].smr_prolongate(g[n + 1], self.ovs[n])
 
     def run(self, nlim):
         while self.time < self.tlim and self.nstep < nlim:

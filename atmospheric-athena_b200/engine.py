@@ -45,14 +45,15 @@ class Overlap(C.Structure):
     _fields_ = [("cs", C.c_int * 3), ("ce", C.c_int * 3), ("face", C.c_int * 6), ("cdisp", C.c_int * 3)]
 
 
-def make_overlap(child_nx, child_disp, root_nx, level=1) -> Overlap:
-    """CGrid.ijks/ijke and the myFlx != NULL pattern init_grid.c:395-660 produces for a root-level parent (Disp 0)
-    and a single-Grid child Domain with displacement child_disp (child-level cells)."""
+def make_overlap(child_nx, child_disp, root_nx, level=1, parent_disp=(0, 0, 0)) -> Overlap:
+    """CGrid.ijks/ijke and the myFlx != NULL pattern init_grid.c:395-660 produces for a single-Grid parent Domain with
+    displacement parent_disp (parent-level cells; 0 for the root) and a single-Grid child Domain at `level` with
+    displacement child_disp (child-level cells from the root origin)."""
     o = Overlap()
     ref = 2 ** level
     for a in range(3):
-        o.cs[a] = child_disp[a] // 2 + NG
-        o.ce[a] = (child_disp[a] + child_nx[a]) // 2 + NG - 1
+        o.cs[a] = child_disp[a] // 2 - parent_disp[a] + NG
+        o.ce[a] = (child_disp[a] + child_nx[a]) // 2 - parent_disp[a] + NG - 1
         o.cdisp[a] = child_disp[a]
         o.face[2 * a] = 1 if child_disp[a] != 0 else 0
         o.face[2 * a + 1] = 1 if (child_disp[a] + child_nx[a]) // ref != root_nx[a] else 0

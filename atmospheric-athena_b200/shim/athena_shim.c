@@ -142,13 +142,15 @@ void new_dt(MeshS *pM)
 { /* new_dt.c:58-195: one dt for every level */
   DomainS *pD; GridS *pG;
   Real max_dti = 0.0, tlim, v[3], x;
+  Real max_v[3] = {0.0, 0.0, 0.0};   /* new_dt.c:53: declared outside the Domain loops and never reset, so each Grid's
+                                      * speed is the running maximum over the Grids before it (coarser levels) too */
   FOR_ALL_GRIDS(pM, pD, pG) {
     Mirror *m = mirror_of(pG);
     ensure_device(m);
     if (ab2_max_wave_speeds(m->h, v) != 0) die("new_dt");
-    if (pG->Nx[0] > 1) { x = v[0]/pG->dx1; max_dti = MAX(max_dti, x); }
-    if (pG->Nx[1] > 1) { x = v[1]/pG->dx2; max_dti = MAX(max_dti, x); }
-    if (pG->Nx[2] > 1) { x = v[2]/pG->dx3; max_dti = MAX(max_dti, x); }
+    if (pG->Nx[0] > 1) { max_v[0] = MAX(max_v[0], v[0]); x = max_v[0]/pG->dx1; max_dti = MAX(max_dti, x); }
+    if (pG->Nx[1] > 1) { max_v[1] = MAX(max_v[1], v[1]); x = max_v[1]/pG->dx2; max_dti = MAX(max_dti, x); }
+    if (pG->Nx[2] > 1) { max_v[2] = MAX(max_v[2], v[2]); x = max_v[2]/pG->dx3; max_dti = MAX(max_dti, x); }
   }
   if (pM->nstep == 0) pM->dt = CourNo/max_dti;
   else pM->dt = MIN(2.0*pM->dt, CourNo/max_dti);

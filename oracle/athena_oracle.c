@@ -1434,14 +1434,18 @@ void orc_prolongate(const OrcGrid *pa, OrcGrid *ch, const OrcOverlap *o)        
 }
 
 void orc_ion_prolong(const OrcGrid *pa, const double *efp, const OrcGrid *ch, double *efc, const OrcOverlap *o)
-{ /* ionrad_smr.c:345-459 (snd, dim 0) + :34-343 (rcv, serial branch: indices valid for a root-level parent) */
+{ /* ionrad_smr.c:345-459 (snd, dim 0) + :34-343 (rcv).  The serial branch (:282-337) forms the child index as
+   * `k*2 - Disp` with k parent-LOCAL, which is only right below a root-level parent (and reads out of bounds below
+   * that); the MPI branch (:142-211) maps child edge (kk,jj) to coarse edge (kk/2, jj/2) of the overlap.
+   * Both are the same map for level 1; written here in the overlap-relative form so it also holds for deeper
+   * levels, where only the MPI branch can be executed (oracle/mpi_stub) to pin it. */
   const int pe1 = pa->nx1+1, pe2 = pa->nx2+1, ce1 = ch->nx1+1, ce2 = ch->nx2+1;
   const int fixed_p = o->cs[0] - NG, fixed_c = 0;
   int k, j;
   if (!o->face[0]) return;
   for (k=o->cs[2]-NG; k<=o->ce[2]+1-NG; k++) for (j=o->cs[1]-NG; j<=o->ce[1]+1-NG; j++) {
     const double val = efp[((size_t)k*pe2 + j)*pe1 + fixed_p];
-    const int ks = k*2 - o->cdisp[2], js = j*2 - o->cdisp[1];
+    const int ks = 2*(k - (o->cs[2]-NG)), js = 2*(j - (o->cs[1]-NG));
 #define EFC(kk,jj) efc[((size_t)(kk)*ce2 + (jj))*ce1 + fixed_c]
     EFC(ks,js) = val;
     if (j < (o->ce[1]+1-NG)) {

@@ -51,6 +51,17 @@ CASES = {
     "ifrontsmr": ("ifront_smr", "ifront.athinput",
                   ["job/num_domains=2", "domain1/Nx1=32", "domain1/Nx2=16", "domain1/Nx3=16",
                    "domain2/Nx1=24", "domain2/Nx2=16", "domain2/Nx3=16", "domain2/iDisp=8", "domain2/jDisp=8", "domain2/kDisp=8"], [1, 3]),
+    # three nested levels.  The reference's serial build segfaults below level 1 with ion RT, so these
+    # come from its MPI branch run as one rank against oracle/mpi_stub (builds *_smr_mpi).  n_H lowered so the box
+    # is optically thin-ish (tau ~ 0.3 per root cell) and non-trivial fluxes are handed down to both fine levels.
+    "ifrontsmr3": ("ifront_smr_mpi", "ifront.athinput",
+                   ["job/num_domains=3", "domain1/Nx1=32", "domain1/Nx2=16", "domain1/Nx3=16", "problem/n_H=0.05",
+                    "domain2/Nx1=24", "domain2/Nx2=16", "domain2/Nx3=16", "domain2/iDisp=8", "domain2/jDisp=8", "domain2/kDisp=8",
+                    "domain3/Nx1=16", "domain3/Nx2=16", "domain3/Nx3=16", "domain3/iDisp=24", "domain3/jDisp=24", "domain3/kDisp=24"], [1, 3]),
+    "blastsmr3": ("blast_smr_mpi", "blast.athinput",
+                  ["job/num_domains=3", "domain1/Nx1=16", "domain1/Nx2=16", "domain1/Nx3=16", "problem/radius=0.25",
+                   "domain2/Nx1=16", "domain2/Nx2=12", "domain2/Nx3=16", "domain2/iDisp=8", "domain2/jDisp=10", "domain2/kDisp=8",
+                   "domain3/Nx1=12", "domain3/Nx2=8", "domain3/Nx3=12", "domain3/iDisp=28", "domain3/jDisp=28", "domain3/kDisp=24"], [4]),
 }
 
 
@@ -59,10 +70,11 @@ def run_reference(build, deck, overrides, nlim):
     with tempfile.TemporaryDirectory() as tmp:
         cmd = [exe, "-i", os.path.join(DECKS, deck), f"time/nlim={nlim}"] + overrides
         r = subprocess.run(cmd, cwd=tmp, capture_output=True, text=True, check=True)
-        rst = sorted(f for f in os.listdir(tmp) if f.endswith(".rst"))
+        out = os.path.join(tmp, "id0") if build.endswith("_mpi") else tmp        # MPI builds write into id<rank>/
+        rst = sorted(f for f in os.listdir(out) if f.endswith(".rst"))
         assert len(rst) == 2, rst
-        d0 = read_restart(os.path.join(tmp, rst[0]))
-        d1 = read_restart(os.path.join(tmp, rst[1]))
+        d0 = read_restart(os.path.join(out, rst[0]))
+        d1 = read_restart(os.path.join(out, rst[1]))
     next_dt = [float(x) for x in re.findall(r"cycle=\d+ time=\S+ next dt=(\S+)", r.stdout)]
     rad = [(int(a), int(b), int(c), float(d)) for a, b, c, d in re.findall(
         r"Radiation done in (\d+) iterations: (\d+) thermal, (\d+) chemical; new dt = (\S+)", r.stderr)]
@@ -147,7 +159,7 @@ if __name__ == "__main__":
     spec = importlib.util.spec_from_file_location("build_ref", os.path.join(ROOT, "oracle", "build_ref.py"))
     br = importlib.util.module_from_spec(spec); spec.loader.exec_module(br)
     if os.path.isdir(os.path.join(br.REF, "src")):
-        for c in ("ifront", "ioniz_sphere", "blast", "ifront_smr", "blast_smr"):
+        for c in ("ifront", "ioniz_sphere", "blast", "ifront_smr", "blast_smr", "ifront_smr_mpi", "blast_smr_mpi"):
             br.build(c)
         for c in ("ifront", "blast"):
             br.build_units(c)

@@ -186,14 +186,15 @@ def run_main_loop(G, nsteps, cour_no, tlim, ionpar=None, flux_i=0.0, userwork=No
             log.setdefault("next_dt", []).append(G.dt)
 
 
-def make_overlap(parent_nx, child_nx, child_disp, root_nx, level=1):
-    """CGrid.ijks/ijke and the myFlx != NULL pattern of init_grid.c:395-660 for a root-level parent (Disp 0) and a
-    single-Grid child Domain at `level` with displacement child_disp (child-level cells)."""
+def make_overlap(parent_nx, child_nx, child_disp, root_nx, level=1, parent_disp=(0, 0, 0)):
+    """CGrid.ijks/ijke and the myFlx != NULL pattern of init_grid.c:395-660 for a single-Grid parent Domain with
+    displacement parent_disp (parent-level cells; 0 for the root) and a single-Grid child Domain at `level` with
+    displacement child_disp (child-level cells, from the root origin)."""
     o = OrcOverlap()
     ref = 2 ** level
     for a in range(3):
-        o.cs[a] = child_disp[a] // 2 + NG
-        o.ce[a] = (child_disp[a] + child_nx[a]) // 2 + NG - 1
+        o.cs[a] = child_disp[a] // 2 - parent_disp[a] + NG
+        o.ce[a] = (child_disp[a] + child_nx[a]) // 2 - parent_disp[a] + NG - 1
         o.cdisp[a] = child_disp[a]
         o.face[2 * a] = 1 if child_disp[a] != 0 else 0
         o.face[2 * a + 1] = 1 if (child_disp[a] + child_nx[a]) // ref != root_nx[a] else 0
@@ -201,34 +202,48 @@ def make_overlap(parent_nx, child_nx, child_disp, root_nx, level=1):
 
 
 def run_main_loop_smr(root, child, o, nsteps, cour_no, tlim, ionpar=None, flux_i=0.0, log=None):
-    """main.c:519-669 with STATIC_MESH_REFINEMENT for a root Grid and one level-1 Grid.  Both must hold problem()
-    data, ghost zones (bvals + Prolongate) and the first dt.  Mesh scalars live on `root` (time, nstep) and in
-    mesh['dt']."""
+    """Two-level form of run_main_loop_levels (root Grid + one level-1 Grid)."""
+    return run_main_loop_levels([root, child], [o], nsteps, cour_no, tlim, ionpar, flux_i, log)
+
+
+def run_main_loop_levels(grids, ovs, nsteps, cour_no, tlim, ionpar=None, flux_i=0.0, log=None):
+    """main.c:519-669 with STATIC_MESH_REFINEMENT for a nest of single-Grid Domains, grids[n] at level n and
+    ovs[n] the overlap of grids[n+1] on grids[n].  All must hold problem() data, ghost zones (bvals + Prolongate)
+    and the first dt.  Mesh scalars live on the root (time, nstep)."""
     L = lib()
+    root = grids[0]
+    nlev = len(grids)
     mesh_dt = root.dt
     for _ in range(nsteps):
         if root.time >= tlim:
             break
         if ionpar is not None:
-            r0 = root.ion_radtransfer(ionpar, flux_i, cour_no)
-            mesh_dt = root.dt
-            root.bvals()
-            L.orc_ion_prolong(C.byref(root.g), P(root.edgeflux), C.byref(child.g), P(child.edgeflux), C.byref(o))
-            r1 = child.ion_radtransfer_fine(ionpar, root.tcoarse)
-            mesh_dt = child.dt                                   # ionrad_3d.c:1033 pMesh->dt = pGrid->dt
-            child.bvals()
-            L.orc_ion_restrict(C.byref(root.g), C.byref(child.g), C.byref(o))
-            if log is not None:
-                log.setdefault("rad", []).extend([r0 + (root.dt,), r1 + (child.dt,)])
-        root.integrate()
-        child.integrate()
-        L.orc_restrict_correct(C.byref(root.g), C.byref(child.g), C.byref(o), root.dt)
+            for n, G in enumerate(grids):                        # main.c:546-556, coarse to fine
+                if n == 0:
+                    r = G.ion_radtransfer(ionpar, flux_i, cour_no)
+                else:                                            # ionrad_3d.c:880 ionrad_prolong_rcv from the parent's :1037 snd
+                    pa = grids[n - 1]
+                    L.orc_ion_prolong(C.byref(pa.g), P(pa.edgeflux), C.byref(G.g), P(G.edgeflux), C.byref(ovs[n - 1]))
+                    r = G.ion_radtransfer_fine(ionpar, root.tcoarse)
+                mesh_dt = G.dt                                   # ionrad_3d.c:1033 pMesh->dt = pGrid->dt
+                G.bvals()
+                if log is not None:
+                    log.setdefault("rad", []).append(r + (G.dt,))
+            for n in range(nlev - 2, -1, -1):                    # ionradRestrictCorrect, finest pair first (smr.c:111)
+                L.orc_ion_restrict(C.byref(grids[n].g), C.byref(grids[n + 1].g), C.byref(ovs[n]))
+        for G in grids:
+            G.integrate()
+        for n in range(nlev - 2, -1, -1):                        # RestrictCorrect (smr.c:1233), finest pair first
+            L.orc_restrict_correct(C.byref(grids[n].g), C.byref(grids[n + 1].g), C.byref(ovs[n]), grids[n].dt)
         root.nstep += 1
         root.time += mesh_dt
-        child.time = root.time
-        mesh_dt = new_dt_smr([root, child], cour_no, mesh_dt, root.nstep, root.time, tlim)
-        root.bvals(); child.bvals()
-        L.orc_prolongate(C.byref(root.g), C.byref(child.g), C.byref(o))
+        for G in grids[1:]:
+            G.time = root.time
+        mesh_dt = new_dt_smr(grids, cour_no, mesh_dt, root.nstep, root.time, tlim)
+        for G in grids:
+            G.bvals()
+        for n in range(nlev - 1):                                # Prolongate (smr.c:2386), root first
+            L.orc_prolongate(C.byref(grids[n].g), C.byref(grids[n + 1].g), C.byref(ovs[n]))
         if log is not None:
             log.setdefault("next_dt", []).append(mesh_dt)
     return mesh_dt
@@ -237,11 +252,13 @@ def run_main_loop_smr(root, child, o, nsteps, cour_no, tlim, ionpar=None, flux_i
 def new_dt_smr(grids, cour_no, dt_old, nstep, time, tlim):
     """new_dt.c:58-195 over all levels: one dt for the whole Mesh."""
     max_dti = 0.0
+    max_v = [0.0, 0.0, 0.0]          # new_dt.c:53: never reset between Grids -> running maximum over the levels so far
     for G in grids:
         v = G.max_speeds()
         for a in range(3):
             if G.nx[a] > 1:
-                x = v[a] / G.dx[a]
+                max_v[a] = max_v[a] if max_v[a] > v[a] else v[a]
+                x = max_v[a] / G.dx[a]
                 max_dti = max_dti if max_dti > x else x
     dt = cour_no / max_dti if nstep == 0 else min(2.0 * dt_old, cour_no / max_dti)
     if time < tlim and (tlim - time) < dt:
