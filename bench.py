@@ -237,7 +237,10 @@ def gpu_arm(args):
     assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
     n = args.n
-    par = make_par(args.workload, n, n * world)
+    nx3_global = n if args.strong else n * world         # --strong: SURVEY 8d cfg 5, the n^3 box cut into `world` x3 slabs
+    if nx3_global % world:
+        raise SystemExit(f"bench.py: --strong needs n divisible by the number of GPUs ({n} % {world})")
+    par = make_par(args.workload, n, nx3_global)
     prob = WORKLOADS[args.workload][1]
     t_setup = time.time()
     R = Run(par, prob, device=local, dist=d, torch_memory=True)
@@ -344,8 +347,8 @@ def gpu_arm(args):
         line = {
             "metric": "zone-updates/s per hydro+ion-RT step", "value": value, "unit": "zone-updates/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{WORKLOADS[args.workload][2]} {n}x{n}x{n * world}, steps {args.warmup}..{args.warmup + args.steps} from t=0",
+            "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{WORKLOADS[args.workload][2]} {n}x{n}x{nx3_global}, steps {args.warmup}..{args.warmup + args.steps} from t=0",
                        "zones_per_gpu": zones_local, "parallelism": f"x3-slabs x{world}",
                        "ion_iterations_per_step": round(n_iter, 2), "l2": "working set >> L2 (state + scratch = "
                        f"{G.bytes_allocated / 2**30:.1f} GiB per GPU), no flush needed", "setup_s": round(t_setup, 1)},
@@ -365,6 +368,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="ioniz_sphere", choices=sorted(WORKLOADS))
     ap.add_argument("--n", type=int, default=256, help="zones per direction per GPU")
+    ap.add_argument("--strong", action="store_true", help="--n is the GLOBAL cube size, cut into --gpus x3 slabs (strong scaling)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-n", type=int, default=64, help="grid of the bounded CPU sample")
     ap.add_argument("--cpu-steps", type=int, default=8)

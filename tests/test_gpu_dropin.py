@@ -106,3 +106,30 @@ def test_dropin_smr_shipped_two_level_geometry_vs_reference_live():
     for lev in (0, 1):
         for v in ("d", "M1", "M2", "M3", "E", "s", "edgeflux"):
             assert np.array_equal(b["grids"][lev][v], a["grids"][lev][v]), (lev, v)
+
+
+def test_dropin_shipped_five_level_deck_matches_reference_fingerprint():
+    """The SHIPPED 5-level deck (80^3/52^3/96^3/176^3/320^3, 39.8 M zones, static potential, Userwork reset, ion RT on
+    every level) for one step through the unmodified driver, against SHA-256 fingerprints of the reference's own dump
+    (its MPI branch as one rank; 6 minutes of host time, generated by tests/golden/make_hires5_fingerprint.py)."""
+    import importlib.util
+    import json
+    exe = os.path.join(ROOT, "build", "dropin", "ioniz_smr", "athena")
+    if not os.path.exists(exe):
+        pytest.skip("needs build/dropin/ioniz_smr")
+    spec = importlib.util.spec_from_file_location("fp5", os.path.join(ROOT, "tests", "golden", "make_hires5_fingerprint.py"))
+    fp5 = importlib.util.module_from_spec(spec); spec.loader.exec_module(fp5)
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "hires5_k1.json")))
+    with tempfile.TemporaryDirectory() as tmp:
+        r = subprocess.run([exe, "-i", os.path.join(DECKS, "ioniz_sphere_hires.athinput"), "time/nlim=1"], cwd=tmp, capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+        rst = sorted(f for f in os.listdir(tmp) if f.endswith(".rst"))
+        d1 = read_restart(os.path.join(tmp, rst[-1]))
+    rad = [int(a) for a in re.findall(r"Radiation done in (\d+) iterations", r.stderr)]
+    mine = fp5.fingerprint(d1, rad)
+    assert mine["rad"] == gold["rad"]
+    assert mine["time"] == gold["time"] and mine["dt"] == gold["dt"]
+    for lev, (a, b) in enumerate(zip(mine["levels"], gold["levels"])):
+        for v in fp5.VARS:
+            assert a[v]["shape"] == b[v]["shape"]
+            assert a[v]["sha256"] == b[v]["sha256"], f"level {lev} {v}: sum {a[v]['sum']!r} vs {b[v]['sum']!r}, absmax {a[v]['absmax']!r} vs {b[v]['absmax']!r}"
