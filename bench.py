@@ -367,7 +367,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="ioniz_sphere", choices=sorted(WORKLOADS))
-    ap.add_argument("--n", type=int, default=256, help="zones per direction per GPU")
+    ap.add_argument("--n", "--size", dest="n", type=int, default=256, help="zones per direction per GPU (use --size under torchrun, whose own parser trips over --n)")
     ap.add_argument("--strong", action="store_true", help="--n is the GLOBAL cube size, cut into --gpus x3 slabs (strong scaling)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-n", type=int, default=64, help="grid of the bounded CPU sample")
