@@ -19,11 +19,6 @@
 
 #define NG AB2_NG
 
-// Run a block of per-cell arithmetic with the branch-free IEEE division/sqrt (Arith<true>); if any operand fell outside
-// the range where that refinement is the correctly rounded result, redo the block with the plain operators.  The block
-// must only assign its outputs from unchanged inputs.  (physics.cuh, "IEEE-754 division and square root without control flow")
-#define AB2_GUARDED(...) { Arith<true> ar; __VA_ARGS__; if (ar.bad) { Arith<false> ar; __VA_ARGS__; } }
-
 // ---------------------------------------------------------------------------------------------------
 // sweep-order <-> physical-order register shuffles
 // ---------------------------------------------------------------------------------------------------
@@ -69,6 +64,12 @@ template <int DIR, int NS> __device__ __forceinline__ S6 sweep_from_phys(const d
 #endif
 #ifndef AB2_LB_FINAL
 #define AB2_LB_FINAL 4
+#endif
+#ifndef AB2_LB_CORRECT
+#define AB2_LB_CORRECT 6
+#endif
+#ifndef AB2_LB_UPDATE
+#define AB2_LB_UPDATE 1
 #endif
 template <int NS, bool GRAV, int A1_T>
 __global__ void __launch_bounds__(A1_T, (AB2_LB_FIRST_X1*128)/A1_T) k_first_x1(GridDev g, double dt)
@@ -209,7 +210,7 @@ __global__ void k_dhalf(GridDev g, Box b, double dt)
 // add the static-potential source terms (5d/6d/7d), and evaluate eta (9a).  One thread per face.
 // ---------------------------------------------------------------------------------------------------
 template <int DIR, int NS, bool GRAV>
-__global__ void __launch_bounds__(128) k_correct(GridDev g, Box b, double dt)
+__global__ void __launch_bounds__(128, AB2_LB_CORRECT) k_correct(GridDev g, Box b, double dt)
 {
   int i,j,k; if (!box_cell(b,i,j,k)) return;
   const long cR = (long)k*g.st[2] + (long)j*g.st[1] + i;
@@ -292,7 +293,7 @@ __global__ void __launch_bounds__(128, AB2_LB_FINAL) k_final(GridDev g, Box b)
 // three ordered passes (12a-c, :2981-3050), per active cell.
 // ---------------------------------------------------------------------------------------------------
 template <int NS, bool GRAV>
-__global__ void __launch_bounds__(128) k_update(GridDev g, Box b, double dt)
+__global__ void __launch_bounds__(128, AB2_LB_UPDATE) k_update(GridDev g, Box b, double dt)
 {
   int i,j,k; if (!box_cell(b,i,j,k)) return;
   const long c = (long)k*g.st[2] + (long)j*g.st[1] + i;

@@ -36,6 +36,22 @@
 
 #define ERR_DT_CHEM_NEG 1ull
 
+// minimum resident blocks per SM (register caps) and whether the per-cell arithmetic uses the guarded fast divisions
+#ifndef AB2_LB_ION_RATES
+#define AB2_LB_ION_RATES 7
+#endif
+#ifndef AB2_LB_ION_UPDATE
+#define AB2_LB_ION_UPDATE 12
+#endif
+#ifndef AB2_ION_FAST_DIV
+#define AB2_ION_FAST_DIV 1
+#endif
+#if AB2_ION_FAST_DIV
+#define ION_GUARDED(...) AB2_GUARDED(__VA_ARGS__)
+#else
+#define ION_GUARDED(...) { Arith<false> ar; __VA_ARGS__; }
+#endif
+
 __device__ __forceinline__ void atomic_min_double(unsigned long long* addr, double val)
 { // `if (val < cur) cur = val` (NaN never wins), any sign
   unsigned long long old = *addr, assumed;
@@ -57,39 +73,48 @@ __device__ __forceinline__ void atomic_max_double(unsigned long long* addr, doub
 
 struct CellChem { double n_H, n_Hplus, n_e, x, ke, e_thermal, T; };
 
+// The kinetic energy keeps the plain operator: its numerator M.M is below the fast path's range (2^-120) wherever the
+// gas is nearly at rest in CGS units, and those cells would all take the guarded block's second pass.
 __device__ __forceinline__ double kinetic(double d, double M1, double M2, double M3)
 { return 0.5 * (M1*M1 + M2*M2 + M3*M3) / d; }
 
-__device__ __forceinline__ CellChem chem_state(const IonParDev& p, double Gamma_1, double d, double M1, double M2, double M3, double E, double s)
+// Divisions go through Arith (physics.cuh): the same correctly rounded quotients as `/`, straight-line, and the
+// reciprocal refinement of a repeated divisor (m_H, 14 m_H, k_B, d, nHdot, edot ...) is a common subexpression the
+// compiler evaluates once.  Callers wrap a cell's arithmetic in AB2_GUARDED.
+template <bool FAST>
+__device__ __forceinline__ CellChem chem_state(const IonParDev& p, double Gamma_1, double d, double M1, double M2, double M3, double E, double s, Arith<FAST>& ar)
 { // ionrad_3d.c:82-101 == :313-330 == :438-456
   CellChem c;
-  c.n_H = s / p.m_H;
-  c.n_Hplus = (d - s) / p.m_H;
-  c.n_e = c.n_Hplus + d * p.alpha_C / (14.0 * p.m_H);
-  c.x = c.n_e / (c.n_H + c.n_Hplus);
+  c.n_H = ar.div(s, p.m_H);
+  c.n_Hplus = ar.div(d - s, p.m_H);
+  c.n_e = c.n_Hplus + ar.div(d * p.alpha_C, 14.0 * p.m_H);
+  c.x = ar.div(c.n_e, c.n_H + c.n_Hplus);
   c.ke = kinetic(d,M1,M2,M3);
   c.e_thermal = E - c.ke;
-  const double e_sp = c.e_thermal / d;
-  c.T = Gamma_1 * e_sp * (c.x*0.5*p.m_H+(1.0-c.x)*p.mu)/ p.k_B;
+  const double e_sp = ar.div(c.e_thermal, d);
+  c.T = ar.div(Gamma_1 * e_sp * (c.x*0.5*p.m_H+(1.0-c.x)*p.mu), p.k_B);
   return c;
 }
 
-// apply_temp_floor (ionrad_3d.c:70-136) then apply_neutral_floor (:140-157) for one cell
-__device__ __forceinline__ void floors(const IonParDev& p, double Gamma_1, double d, double M1, double M2, double M3, double& E, double& s)
+// apply_temp_floor (ionrad_3d.c:70-136) then apply_neutral_floor (:140-157) for one cell: (E,s) -> (Eo,so)
+template <bool FAST>
+__device__ __forceinline__ void floors(const IonParDev& p, double Gamma_1, double d, double M1, double M2, double M3, double E, double s,
+                                       double& Eo, double& so, Arith<FAST>& ar)
 {
-  const CellChem c = chem_state(p, Gamma_1, d, M1, M2, M3, E, s);
+  const CellChem c = chem_state(p, Gamma_1, d, M1, M2, M3, E, s, ar);
+  Eo = E; so = s;
   if (c.T < p.tfloor) {
-    const double e_sp = p.tfloor * p.k_B / ((c.x*0.5*p.m_H+(1.0-c.x)*p.mu) * Gamma_1);
-    E = kinetic(d,M1,M2,M3) + e_sp * d;
+    const double e_sp = ar.div(p.tfloor * p.k_B, (c.x*0.5*p.m_H+(1.0-c.x)*p.mu) * Gamma_1);
+    Eo = c.ke + e_sp * d;
   }
   if ((c.T > p.tceil) && (p.tceil > 0)) {
-    const double e_sp = p.tceil * p.k_B / ((c.x*0.5*p.m_H+(1.0-c.x)*p.mu) * Gamma_1);
-    E = kinetic(d,M1,M2,M3) + e_sp * d;
+    const double e_sp = ar.div(p.tceil * p.k_B, (c.x*0.5*p.m_H+(1.0-c.x)*p.mu) * Gamma_1);
+    Eo = c.ke + e_sp * d;
   }
   double d_nlim = d*IONFRACFLOOR;
   d_nlim = d_nlim < p.d_nlo ? d_nlim : p.d_nlo;
-  if (s < d_nlim) s = d_nlim;
-  else if (s > d) s = d;
+  if (s < d_nlim) so = d_nlim;
+  else if (s > d) so = d;
 }
 
 // thread -> active cell
@@ -109,28 +134,34 @@ __global__ void __launch_bounds__(128) k_ion_prep(GridDev g, IonParDev p, IonDev
 {
   long c; if (!active_cell(g, c)) return;
   const double d = g.U[0][c], M1 = g.U[1][c], M2 = g.U[2][c], M3 = g.U[3][c];
-  double E = g.U[4][c], s = g.U[5][c];
-  floors(p, g.Gamma_1, d, M1, M2, M3, E, s);
+  const double E0 = g.U[4][c], s0 = g.U[5][c];
+  double E, s, x_init;
+  {                               // plain operators: this pass runs once per step at HBM speed, the guarded form only costs registers
+    Arith<false> ar;
+    floors(p, g.Gamma_1, d, M1, M2, M3, E0, s0, E, s, ar);
+    const double n_H = ar.div(s, p.m_H);
+    const double n_Hplus = ar.div(d - s, p.m_H);
+    const double n_e = n_Hplus + ar.div(d * p.alpha_C, 14.0 * p.m_H);
+    x_init = ar.div(n_e, n_H + n_Hplus);
+  }
   g.U[4][c] = E; g.U[5][c] = s;
-  const double e_thermal = E - kinetic(d,M1,M2,M3);
-  const double n_H = s / p.m_H;
-  const double n_Hplus = (d - s) / p.m_H;
-  const double n_e = n_Hplus + d * p.alpha_C / (14.0 * p.m_H);
   ion.e_init[c] = E;
-  ion.e_th_init[c] = e_thermal;
-  ion.x_init[c] = n_e / (n_H + n_Hplus);
+  ion.e_th_init[c] = E - kinetic(d,M1,M2,M3);
+  ion.x_init[c] = x_init;
   ion.sign_state[c] = 1;          // last_sign = 0, sign_count = 0
 }
 
 // ---------------------------------------------------------------------------------------------------
-// k_ion_rates: ray trace (ionradplane_3d.c:254-310) + chem rates (ionrad_3d.c:307-394) + therm rates (:433-550)
+// ionization_update (:565-590) + floors (:970-971) + check_range (:206-283) + compute_dt_hydro (:593-678) for ONE cell:
+// (E,s) -> (Eo,so), whether the cell counts for check_range, and |v_d| + a per direction.  Pure in its inputs.
 // ---------------------------------------------------------------------------------------------------
-// ionization_update (:565-590) + floors (:970-971) + check_range (:206-283) + compute_dt_hydro (:593-678) for ONE cell.
-// E,s are updated in place (and stored); count and the three per-direction maxima accumulate.
-__device__ __forceinline__ void cell_update(const GridDev& g, const IonParDev& p, const IonDev& ion, long c, double dt,
-                                            double d, double M1, double M2, double M3, double& E, double& s,
-                                            unsigned long long& count, double& m1, double& m2, double& m3)
+struct CellUpd { double E, s, x1, x2, x3; unsigned count; };
+
+template <bool FAST>
+__device__ __forceinline__ CellUpd cell_update(const GridDev& g, const IonParDev& p, const IonDev& ion, long c, double dt,
+                                               double d, double M1, double M2, double M3, double E, double s, Arith<FAST>& ar)
 {
+    CellUpd u;
     const double nHdot = ion.nHdot[c];
     double d_nlim = d*IONFRACFLOOR;
     d_nlim = d_nlim < p.d_nlo ? d_nlim : p.d_nlo;
@@ -141,48 +172,132 @@ __device__ __forceinline__ void cell_update(const GridDev& g, const IonParDev& p
     // floors (apply_temp_floor :70-136, apply_neutral_floor :140-157), keeping the cell's chemistry state: when no
     // floor fires (the common case) check_range below re-evaluates the very same expressions on the same values,
     // so the seven divisions are shared; when one fires they are recomputed from the floored E,s as the reference does
-    CellChem cs = chem_state(p, g.Gamma_1, d, M1, M2, M3, E, s);
+    CellChem cs = chem_state(p, g.Gamma_1, d, M1, M2, M3, E, s, ar);
     bool changed = false;
     if (cs.T < p.tfloor) {
-      const double e_sp = p.tfloor * p.k_B / ((cs.x*0.5*p.m_H+(1.0-cs.x)*p.mu) * g.Gamma_1);
-      E = kinetic(d,M1,M2,M3) + e_sp * d; changed = true;
+      const double e_sp = ar.div(p.tfloor * p.k_B, (cs.x*0.5*p.m_H+(1.0-cs.x)*p.mu) * g.Gamma_1);
+      E = cs.ke + e_sp * d; changed = true;
     }
     if ((cs.T > p.tceil) && (p.tceil > 0)) {
-      const double e_sp = p.tceil * p.k_B / ((cs.x*0.5*p.m_H+(1.0-cs.x)*p.mu) * g.Gamma_1);
-      E = kinetic(d,M1,M2,M3) + e_sp * d; changed = true;
+      const double e_sp = ar.div(p.tceil * p.k_B, (cs.x*0.5*p.m_H+(1.0-cs.x)*p.mu) * g.Gamma_1);
+      E = cs.ke + e_sp * d; changed = true;
     }
     if (s < d_nlim) { s = d_nlim; changed = true; }
     else if (s > d) { s = d; changed = true; }
-    g.U[4][c] = E; g.U[5][c] = s;
-    if (changed) cs = chem_state(p, g.Gamma_1, d, M1, M2, M3, E, s);
+    u.E = E; u.s = s;
+    if (changed) cs = chem_state(p, g.Gamma_1, d, M1, M2, M3, E, s, ar);
 
     // check_range (ionrad_3d.c:222-264)
-    if (!(ion.ph_rate[c] / (p.min_area * cs.n_H) > 2.0*CION)) {
+    u.count = 0;
+    if (!(ar.div(ion.ph_rate[c], p.min_area * cs.n_H) > 2.0*CION)) {
       const double eth0 = ion.e_th_init[c], e0 = ion.e_init[c], x0 = ion.x_init[c];
-      if ((cs.e_thermal / eth0 >= 1 + p.max_de_therm_step) || (eth0 / cs.e_thermal >= 1 + p.max_de_therm_step)) count += 1;
-      else if ((p.max_de_step > 0) && ((E / e0 >= 1 + p.max_de_step) || (e0 / E >= 1 + p.max_de_step))) count += 1;
-      else if ((p.max_dx_step > 0) && ((cs.x / x0 >= 1 + p.max_dx_step) || (x0 / cs.x >= 1 + p.max_dx_step))) count += 1;
+      if ((ar.div(cs.e_thermal, eth0) >= 1 + p.max_de_therm_step) || (ar.div(eth0, cs.e_thermal) >= 1 + p.max_de_therm_step)) u.count = 1;
+      else if ((p.max_de_step > 0) && ((ar.div(E, e0) >= 1 + p.max_de_step) || (ar.div(e0, E) >= 1 + p.max_de_step))) u.count = 1;
+      else if ((p.max_dx_step > 0) && ((ar.div(cs.x, x0) >= 1 + p.max_dx_step) || (ar.div(x0, cs.x) >= 1 + p.max_dx_step))) u.count = 1;
     }
     // compute_dt_hydro (:609-663): max over cells of (|v_d|+a)/dx_d.  Division by the positive constant dx_d is
     // monotone under rounding, so max_c fl(x_c/dx) == fl((max_c x_c)/dx): keep three per-direction maxima here and
     // divide once on the host (new_dt.c:126-161 has this very form).
-    const double di = 1.0/d;
+    const double di = ar.div(1.0, d);
     const double v1 = M1*di, v2 = M2*di, v3 = M3*di;
     const double qsq = v1*v1 + v2*v2 + v3*v3;
     const double pr = AB2_MAX(g.Gamma_1*(E - 0.5*d*qsq), AB2_TINY);
     const double asq = g.Gamma*pr*di;
-    const double a = sqrt(asq);
-    { const double x1 = fabs(v1)+a, x2 = fabs(v2)+a, x3 = fabs(v3)+a;
-      m1 = AB2_MAX(m1, x1); m2 = AB2_MAX(m2, x2); m3 = AB2_MAX(m3, x3); }
+    const double a = ar.sqrt_(asq);
+    u.x1 = fabs(v1)+a; u.x2 = fabs(v2)+a; u.x3 = fabs(v3)+a;
+    return u;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// compute_chem_rates (ionrad_3d.c:307-394) + compute_therm_rates (:433-550) for ONE cell with photoionisation rate ph.
+// Pure in its inputs; dt_therm = LARGE when the cell does not constrain the thermal step.
+// ---------------------------------------------------------------------------------------------------
+struct CellRates { double nHdot, edot, dt_chem, dt_therm; int sign_state; };
+
+template <bool FAST>
+__device__ __forceinline__ CellRates cell_rates(const GridDev& g, const IonParDev& p, double d, double M1, double M2, double M3,
+                                                double E, double s, double ph, int st, Arith<FAST>& ar)
+{
+      CellRates r;
+      // --- chemistry (ionrad_3d.c:313-391)
+      const CellChem cs = chem_state(p, g.Gamma_1, d, M1, M2, M3, E, s, ar);
+      double T = cs.T;
+      if (T < p.tfloor) T = p.tfloor;
+      double nHdot = 2.59e-13*gl_pow(ar.div(T, 1.0e4), -0.7) * p.time_unit * cs.n_e * cs.n_Hplus - ph * cs.n_H;
+      int last_sign = (st & 3) - 1, sign_count = st >> 2;
+      if (nHdot < 0.0) {
+        if (last_sign == 1) sign_count++;
+        else if (sign_count > 0) sign_count--;
+        last_sign = -1;
+      } else if (nHdot > 0.0) {
+        if (last_sign == -1) sign_count++;
+        else if (sign_count > 0) sign_count--;
+        last_sign = 1;
+      } else {
+        sign_count = last_sign = 0;
+      }
+      r.sign_state = (sign_count << 2) | (last_sign + 1);
+      for (int n=MAXSIGNCOUNT; n<sign_count; n++) nHdot *= DAMPFACTOR;
+      r.nHdot = nHdot;
+
+      double d_nlim = d*IONFRACFLOOR;
+      d_nlim = d_nlim < p.d_nlo ? d_nlim : p.d_nlo;
+      double dt1, dt2;
+      if (nHdot == 0.0) {
+        dt1 = dt2 = LARGE;
+      } else if (nHdot > 0.0) {
+        dt1 = ar.div(ar.div(p.max_dx_iter, 1+p.max_dx_iter) * cs.n_e, nHdot);
+        dt2 = ar.div(p.max_dx_iter * cs.n_H, nHdot);
+      } else if (s > 1.0001*d_nlim) {
+        dt1 = ar.div(-p.max_dx_iter * cs.n_e, nHdot);
+        dt2 = ar.div(ar.div(-p.max_dx_iter, 1+p.max_dx_iter) * cs.n_H, nHdot);
+      } else {
+        dt1 = dt2 = LARGE;
+      }
+      r.dt_chem = (dt1 < dt2) ? dt1 : dt2;
+
+      // --- thermal (ionrad_3d.c:438-547), unfloored T
+      double edot;
+      bool constrain = true;
+      if (cs.T < p.tfloor) { edot = 0.0; constrain = false; }
+      else if ((nHdot < 0) && (s < 1.0001*d_nlim)) { edot = 0.0; constrain = false; }
+      else {
+        const double rc = (cs.T < 100.0) ? 0.0 : 6.11e-10*gl_pow(cs.T,-0.89)*KB*cs.T;
+        const double lya = -7.5e-19*cs.n_e*cs.n_H*gl_exp(ar.div(-118348.0, cs.T));
+        edot = ph * p.e_gamma * cs.n_H
+          - rc * p.time_unit * cs.n_Hplus * cs.n_e
+          + lya * p.time_unit;
+        if (edot == 0.0) {
+          dt1 = dt2 = LARGE;
+        } else if (edot > 0.0) {
+          dt1 = ar.div(p.max_de_iter * E, edot);
+          dt2 = ar.div(p.max_de_therm_iter * cs.e_thermal, edot);
+        } else {
+          const double e_sp_min = ar.div(p.tfloor * p.k_B, (cs.x*0.5*p.m_H+(1.0-cs.x)*p.mu) * g.Gamma_1);
+          const double e_th_min = e_sp_min * d;
+          const double e_min = cs.ke + e_th_min;
+          if ((ar.div(cs.e_thermal, 1.0+p.max_de_therm_iter) < e_th_min) && (ar.div(E, 1.0+p.max_de_iter) < e_min)) constrain = false;
+          else {
+            dt1 = ar.div(ar.div(-p.max_de_iter, 1+p.max_de_iter) * E, edot);
+            dt2 = ar.div(ar.div(-p.max_de_therm_iter, 1+p.max_de_therm_iter) * cs.e_thermal, edot);
+          }
+        }
+      }
+      r.edot = edot;
+      r.dt_therm = constrain ? ((dt1 < dt2) ? dt1 : dt2) : LARGE;
+      return r;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k_ion_rates: ray trace (ionradplane_3d.c:254-310) + chem rates (ionrad_3d.c:307-394) + therm rates (:433-550)
+// ---------------------------------------------------------------------------------------------------
 // UPDATE = true fuses the previous iteration's k_ion_update (same arithmetic, same order) in front of the rates of
 // the next one: the cells are updated, floored and range-checked while they stream through for the ray trace, which
 // saves one pass over U per sub-cycle iteration and lets the host read all six loop scalars in ONE synchronisation.
 // The new EdgeFlux goes to ef_out (the alternate buffer) because the iteration may turn out to be the last one,
 // in which case the reference's EdgeFlux is the one written before this update.
 template <bool UPDATE>
-__global__ void __launch_bounds__(128) k_ion_rates(GridDev g, IonParDev p, IonDev ion, double flux_in_root, int finegrid, double dt_upd,
+__global__ void __launch_bounds__(128, AB2_LB_ION_RATES) k_ion_rates(GridDev g, IonParDev p, IonDev ion, double flux_in_root, int finegrid, double dt_upd,
                                                    const double* ef_in_base, double* ef_out_base, unsigned long long* scal)
 {
   const int lane = threadIdx.x & 31;
@@ -211,10 +326,18 @@ __global__ void __launch_bounds__(128) k_ion_rates(GridDev g, IonParDev p, IonDe
     const long c = row + (valid ? ii : nx1-1);
     const double d = g.U[0][c], M1 = g.U[1][c], M2 = g.U[2][c], M3 = g.U[3][c];
     double E = g.U[4][c], s = g.U[5][c];
-    if (UPDATE && valid) cell_update(g, p, ion, c, dt_upd, d, M1, M2, M3, E, s, count, m1, m2, m3);
+    if (UPDATE && valid) {
+      CellUpd u;
+      ION_GUARDED(u = cell_update(g, p, ion, c, dt_upd, d, M1, M2, M3, E, s, ar));
+      E = u.E; s = u.s;
+      g.U[4][c] = E; g.U[5][c] = s;
+      count += u.count;
+      m1 = AB2_MAX(m1, u.x1); m2 = AB2_MAX(m2, u.x2); m3 = AB2_MAX(m3, u.x3);
+    }
 
     // --- ray: tau, attenuation, photoionisation rate
-    const double n_H = s / p.m_H;
+    double n_H;
+    ION_GUARDED(n_H = ar.div(s, p.m_H));
     const double tau = p.sigma_ph * n_H * dx1;
     const double etau = valid ? gl_exp(-tau) : 1.0;
     // flux entering each cell = the reference's sequential product ((F*e0)*e1)*... (ionradplane_3d.c:298 `flux *= etau`):
@@ -228,12 +351,12 @@ __global__ void __launch_bounds__(128) k_ion_rates(GridDev g, IonParDev p, IonDe
       if (lane > l) flux_before *= el;
     }
     const double flux_after = flux_before*etau;
-    const double flux_frac = flux_after / (flux_in + 1e-12);
+    double flux_frac, ph_lit;
+    ION_GUARDED(flux_frac = ar.div(flux_after, flux_in + 1e-12); ph_lit = ar.div(flux_before * (1.0-etau), n_H*dx1));
     const unsigned cutmask = __ballot_sync(0xffffffffu, valid && (flux_frac < MINFLUXFRAC));
     const int first = cutmask ? (__ffs(cutmask) - 1) : 32;
     const bool lit = alive && (lane <= first);
-    double ph = 0.0;
-    if (lit) ph = flux_before * (1.0-etau) / (n_H*dx1);
+    const double ph = lit ? ph_lit : 0.0;
     if (valid) {
       ef[ii] = lit ? flux_before : 0.0;
       ion.ph_rate[c] = ph;
@@ -242,78 +365,15 @@ __global__ void __launch_bounds__(128) k_ion_rates(GridDev g, IonParDev p, IonDe
     if (first < 32) alive = false;
 
     if (valid) {
-      // --- chemistry (ionrad_3d.c:313-391)
-      const CellChem cs = chem_state(p, g.Gamma_1, d, M1, M2, M3, E, s);
-      double T = cs.T;
-      if (T < p.tfloor) T = p.tfloor;
-      double nHdot = 2.59e-13*gl_pow(T/1.0e4, -0.7) * p.time_unit * cs.n_e * cs.n_Hplus - ph * cs.n_H;
-      int st = ion.sign_state[c];
-      int last_sign = (st & 3) - 1, sign_count = st >> 2;
-      if (nHdot < 0.0) {
-        if (last_sign == 1) sign_count++;
-        else if (sign_count > 0) sign_count--;
-        last_sign = -1;
-      } else if (nHdot > 0.0) {
-        if (last_sign == -1) sign_count++;
-        else if (sign_count > 0) sign_count--;
-        last_sign = 1;
-      } else {
-        sign_count = last_sign = 0;
-      }
-      ion.sign_state[c] = (sign_count << 2) | (last_sign + 1);
-      for (int n=MAXSIGNCOUNT; n<sign_count; n++) nHdot *= DAMPFACTOR;
-      ion.nHdot[c] = nHdot;
-
-      double d_nlim = d*IONFRACFLOOR;
-      d_nlim = d_nlim < p.d_nlo ? d_nlim : p.d_nlo;
-      double dt1, dt2;
-      if (nHdot == 0.0) {
-        dt1 = dt2 = LARGE;
-      } else if (nHdot > 0.0) {
-        dt1 = p.max_dx_iter / (1+p.max_dx_iter) * cs.n_e / nHdot;
-        dt2 = p.max_dx_iter * cs.n_H / nHdot;
-      } else if (s > 1.0001*d_nlim) {
-        dt1 = -p.max_dx_iter * cs.n_e / nHdot;
-        dt2 = -p.max_dx_iter / (1+p.max_dx_iter) * cs.n_H / nHdot;
-      } else {
-        dt1 = dt2 = LARGE;
-      }
-      const double dt_chem = (dt1 < dt2) ? dt1 : dt2;
-      if (dt_chem < dt_chem_min) dt_chem_min = dt_chem;
-      if (dt_chem < 0) err |= ERR_DT_CHEM_NEG;
-
-      // --- thermal (ionrad_3d.c:438-547), unfloored T
-      double edot;
-      bool constrain = true;
-      if (cs.T < p.tfloor) { edot = 0.0; constrain = false; }
-      else if ((nHdot < 0) && (s < 1.0001*d_nlim)) { edot = 0.0; constrain = false; }
-      else {
-        const double rc = (cs.T < 100.0) ? 0.0 : 6.11e-10*gl_pow(cs.T,-0.89)*KB*cs.T;
-        const double lya = -7.5e-19*cs.n_e*cs.n_H*gl_exp(-118348/cs.T);
-        edot = ph * p.e_gamma * cs.n_H
-          - rc * p.time_unit * cs.n_Hplus * cs.n_e
-          + lya * p.time_unit;
-        if (edot == 0.0) {
-          dt1 = dt2 = LARGE;
-        } else if (edot > 0.0) {
-          dt1 = p.max_de_iter * E / edot;
-          dt2 = p.max_de_therm_iter * cs.e_thermal / edot;
-        } else {
-          const double e_sp_min = p.tfloor * p.k_B / ((cs.x*0.5*p.m_H+(1.0-cs.x)*p.mu) * g.Gamma_1);
-          const double e_th_min = e_sp_min * d;
-          const double e_min = kinetic(d,M1,M2,M3) + e_th_min;
-          if ((cs.e_thermal/(1.0+p.max_de_therm_iter) < e_th_min) && (E/(1.0+p.max_de_iter) < e_min)) constrain = false;
-          else {
-            dt1 = -p.max_de_iter / (1+p.max_de_iter) * E / edot;
-            dt2 = -p.max_de_therm_iter / (1+p.max_de_therm_iter) * cs.e_thermal / edot;
-          }
-        }
-      }
-      ion.edot[c] = edot;
-      if (constrain) {
-        const double dt_therm = (dt1 < dt2) ? dt1 : dt2;
-        if (dt_therm < dt_therm_min) dt_therm_min = dt_therm;
-      }
+      CellRates r;
+      const int st = ion.sign_state[c];
+      ION_GUARDED(r = cell_rates(g, p, d, M1, M2, M3, E, s, ph, st, ar));
+      ion.sign_state[c] = r.sign_state;
+      ion.nHdot[c] = r.nHdot;
+      ion.edot[c] = r.edot;
+      if (r.dt_chem < dt_chem_min) dt_chem_min = r.dt_chem;
+      if (r.dt_chem < 0) err |= ERR_DT_CHEM_NEG;
+      if (r.dt_therm < dt_therm_min) dt_therm_min = r.dt_therm;
     }
   }
   if (lane == 0) ef[nx1] = alive ? carry : 0.0;      // ionradplane_3d.c:308
@@ -348,7 +408,7 @@ __global__ void __launch_bounds__(128) k_ion_rates(GridDev g, IonParDev p, IonDe
 // ---------------------------------------------------------------------------------------------------
 // k_ion_update: ionization_update (:565-590) + floors (:970-971) + check_range (:206-283) + compute_dt_hydro (:593-678)
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_ion_update(GridDev g, IonParDev p, IonDev ion, double dt, unsigned long long* scal)
+__global__ void __launch_bounds__(128, AB2_LB_ION_UPDATE) k_ion_update(GridDev g, IonParDev p, IonDev ion, double dt, unsigned long long* scal)
 {
   long c;
   const bool act = active_cell(g, c);
@@ -356,8 +416,11 @@ __global__ void __launch_bounds__(128) k_ion_update(GridDev g, IonParDev p, IonD
   double m1 = 0.0, m2 = 0.0, m3 = 0.0;
   if (act) {
     const double d = g.U[0][c], M1 = g.U[1][c], M2 = g.U[2][c], M3 = g.U[3][c];
-    double E = g.U[4][c], s = g.U[5][c];
-    cell_update(g, p, ion, c, dt, d, M1, M2, M3, E, s, count, m1, m2, m3);
+    const double E = g.U[4][c], s = g.U[5][c];
+    CellUpd u;
+    ION_GUARDED(u = cell_update(g, p, ion, c, dt, d, M1, M2, M3, E, s, ar));
+    g.U[4][c] = u.E; g.U[5][c] = u.s;
+    count = u.count; m1 = AB2_MAX(m1, u.x1); m2 = AB2_MAX(m2, u.x2); m3 = AB2_MAX(m3, u.x3);
   }
   for (int o=16; o>0; o>>=1) {
     count += __shfl_xor_sync(0xffffffffu, count, o);
