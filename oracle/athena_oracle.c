@@ -146,6 +146,10 @@ static void esys_roe_adb_hyd(double v1, double v2, double v3, double h, double G
 /* ------------------------------------------------------------------------------------------------
  * lr_states_plm.c:62-374  (CARTESIAN: gamma_curv = 0 => opg = omg = beta = betai = 1)
  * ---------------------------------------------------------------------------------------------- */
+/* which Riemann solver the build is configured with: 0 = roe.c (--with-flux=roe), 1 = hllc.c (--with-flux=hllc).
+ * It selects fluxes() AND the form of PLM steps 8-9 (lr_states_plm.c:257 vs :296). */
+static int orc_riemann = 0;
+
 static void lr_states(const P1 W[], int nscal, double Gamma, double dt, double dx, int il, int iu,
                       P1 Wl[], P1 Wr[])
 {
@@ -222,6 +226,30 @@ static void lr_states(const P1 W[], int nscal, double Gamma, double dt, double d
 
     pWl = (double*)&Wl[i+1];
     pWr = (double*)&Wr[i];
+
+    if (orc_riemann == 1) {
+      /* :257-293, the HLLE/HLLC/HLLD form of steps 8-9: start from the limited face values and subtract each wave
+       * moving TOWARDS the interface.  The passive scalar is not touched by this branch at all: the reference leaves
+       * Wl[i+1].r / Wr[i].r as they are in its malloc'ed pencils (integrate_3d_ctu.c:3438-3439) -- uninitialised
+       * memory, zero in practice on a fresh heap.  Restated as zero; see DESIGN.md "HLLC". */
+      for (n=0; n<NWAVE; n++) { pWl[n] = Wrv[n]; pWr[n] = Wlv[n]; }
+      for (n=0; n<NWAVE; n++) {
+        qa = 0.0;
+        if (ev[n] > 0.) {
+          qx = 0.5*dtodx*ev[n];
+          for (m=0; m<NWAVE; m++) qa += lem[n][m]*qx*dW[m];
+          for (m=0; m<NWAVE; m++) pWl[m] -= qa*rem[m][n];
+        }
+        qa = 0.0;
+        if (ev[n] < 0.) {
+          qx = 0.5*dtodx*ev[n];
+          for (m=0; m<NWAVE; m++) qa += lem[n][m]*qx*dW[m];
+          for (m=0; m<NWAVE; m++) pWr[m] -= qa*rem[m][n];
+        }
+      }
+      Wl[i+1].r = 0.0; Wr[i].r = 0.0;
+      continue;
+    }
 
     qx = 0.5*MAX(ev[NWAVE-1],0.0)*dtodx;                                        /* :297-304 */
     for (n=0; n<NV; n++) pWl[n] = Wrv[n] - qx*dW[n];
@@ -323,9 +351,93 @@ static void flux_hlle(const C1 Ul, const C1 Ur, const P1 Wl, const P1 Wr, int ns
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * hllc.c:50-261 (HYDRO, ADIABATIC, CARTESIAN) -- the reference's --with-flux=hllc build
+ * ---------------------------------------------------------------------------------------------- */
+static void fluxes_hllc(const C1 Ul, const C1 Ur, const P1 Wl, const P1 Wr, int nscal,
+                        double Gamma, double Gamma_1, C1 *pFlux)
+{
+  double sqrtdl, sqrtdr, isdlpdr, v1roe, v2roe, v3roe, hroe;
+  double ev[NWAVE];
+  double *pFl, *pFr, *pF;
+  C1 Fl, Fr;
+  int n;
+  double cfl, cfr, bp, bm, tmp;
+  double al, ar, am, cp;
+  double tl, tr, dl, dr, sl, sm, sr;
+
+  sqrtdl = sqrt(Wl.d);                                                          /* :78-86 */
+  sqrtdr = sqrt(Wr.d);
+  isdlpdr = 1.0/(sqrtdl + sqrtdr);
+  v1roe = (sqrtdl*Wl.Vx + sqrtdr*Wr.Vx)*isdlpdr;
+  v2roe = (sqrtdl*Wl.Vy + sqrtdr*Wr.Vy)*isdlpdr;
+  v3roe = (sqrtdl*Wl.Vz + sqrtdr*Wr.Vz)*isdlpdr;
+  hroe = ((Ul.E + Wl.P)/sqrtdl + (Ur.E + Wr.P)/sqrtdr)*isdlpdr;                 /* :94 */
+  esys_roe_adb_hyd(v1roe, v2roe, v3roe, hroe, Gamma_1, ev, NULL, NULL);
+
+  cfl = sqrt(Gamma*Wl.P/Wl.d);                                                  /* :114-115 */
+  cfr = sqrt(Gamma*Wr.P/Wr.d);
+  ar = MAX(ev[NWAVE-1],(Wr.Vx + cfr));
+  al = MIN(ev[0]      ,(Wl.Vx - cfl));
+  bp = ar > 0.0 ? ar : 0.0;
+  bm = al < 0.0 ? al : 0.0;
+
+  tl = Wl.P + (Wl.Vx - al)*Ul.Mx;                                               /* :132-148 */
+  tr = Wr.P + (Wr.Vx - ar)*Ur.Mx;
+  dl =   Ul.Mx - Ul.d*al;
+  dr = -(Ur.Mx - Ur.d*ar);
+  tmp = 1.0/(dl + dr);
+  am = (tl - tr)*tmp;
+  cp = (dl*tr + dr*tl)*tmp;
+  cp = cp > 0.0 ? cp : 0.0;
+
+  Fl.d  = Ul.Mx - bm*Ul.d;                                                      /* :154-176 */
+  Fr.d  = Ur.Mx - bp*Ur.d;
+  Fl.Mx = Ul.Mx*(Wl.Vx - bm);
+  Fr.Mx = Ur.Mx*(Wr.Vx - bp);
+  Fl.My = Ul.My*(Wl.Vx - bm);
+  Fr.My = Ur.My*(Wr.Vx - bp);
+  Fl.Mz = Ul.Mz*(Wl.Vx - bm);
+  Fr.Mz = Ur.Mz*(Wr.Vx - bp);
+  Fl.Mx += Wl.P;
+  Fr.Mx += Wr.P;
+  Fl.E  = Ul.E*(Wl.Vx - bm) + Wl.P*Wl.Vx;
+  Fr.E  = Ur.E*(Wr.Vx - bp) + Wr.P*Wr.Vx;
+
+  if (am >= 0.0) {                                                              /* :189-198 */
+    sl =  am/(am - bm);
+    sr = 0.0;
+    sm = -bm/(am - bm);
+  } else {
+    sl =  0.0;
+    sr = -am/(bp - am);
+    sm =  bp/(bp - am);
+  }
+  pFl = (double*)&Fl; pFr = (double*)&Fr; pF = (double*)pFlux;
+  for (n=0; n<NWAVE; n++) pF[n] = sl*pFl[n] + sr*pFr[n];                        /* :206 */
+  pFlux->Mx += sm*cp;
+  pFlux->E  += sm*cp*am;
+  pFlux->s = 0.0;
+  if (nscal) {                                                                  /* :215-221 */
+    if (pFlux->d >= 0.0) pFlux->s = pFlux->d*Wl.r;
+    else pFlux->s = pFlux->d*Wr.r;
+  }
+}
+
+void orc_set_riemann_solver(int kind) { orc_riemann = kind; }
+
+static void fluxes_roe(const C1 Ul, const C1 Ur, const P1 Wl, const P1 Wr, int nscal,
+                       double Gamma, double Gamma_1, double etah, C1 *pFlux);
+static void fluxes(const C1 Ul, const C1 Ur, const P1 Wl, const P1 Wr, int nscal,
+                   double Gamma, double Gamma_1, double etah, C1 *pFlux)
+{
+  if (orc_riemann == 1) fluxes_hllc(Ul, Ur, Wl, Wr, nscal, Gamma, Gamma_1, pFlux);
+  else fluxes_roe(Ul, Ur, Wl, Wr, nscal, Gamma, Gamma_1, etah, pFlux);
+}
+
+/* ------------------------------------------------------------------------------------------------
  * roe.c:59-336  (TEST_INTERMEDIATE_STATES is defined at roe.c:45)
  * ---------------------------------------------------------------------------------------------- */
-static void fluxes(const C1 Ul, const C1 Ur, const P1 Wl, const P1 Wr, int nscal,
+static void fluxes_roe(const C1 Ul, const C1 Ur, const P1 Wl, const P1 Wr, int nscal,
                    double Gamma, double Gamma_1, double etah, C1 *pFlux)
 {
   double sqrtdl, sqrtdr, isdlpdr, v1roe, v2roe, v3roe, pbl=0.0, pbr=0.0, hroe;
@@ -399,8 +511,21 @@ void orc_roe_flux(const double Ul[6], const double Ur[6], const double Wl[6], co
   C1 ul, ur, f; P1 wl, wr;
   memcpy(&ul, Ul, sizeof ul); memcpy(&ur, Ur, sizeof ur);
   memcpy(&wl, Wl, sizeof wl); memcpy(&wr, Wr, sizeof wr);
-  fluxes(ul, ur, wl, wr, nscal, gamma, gamma - 1.0, etah, &f);
+  fluxes_roe(ul, ur, wl, wr, nscal, gamma, gamma - 1.0, etah, &f);
   memcpy(F, &f, sizeof f);
+}
+
+void orc_hllc_flux_batch(int n, const double *Ul, const double *Ur, const double *Wl, const double *Wr,
+                         int nscal, double gamma, double *F)
+{
+  int t;
+  for (t=0; t<n; t++) {
+    C1 ul, ur, f; P1 wl, wr;
+    memcpy(&ul, Ul+6*t, sizeof ul); memcpy(&ur, Ur+6*t, sizeof ur);
+    memcpy(&wl, Wl+6*t, sizeof wl); memcpy(&wr, Wr+6*t, sizeof wr);
+    fluxes_hllc(ul, ur, wl, wr, nscal, gamma, gamma - 1.0, &f);
+    memcpy(F+6*t, &f, sizeof f);
+  }
 }
 
 void orc_roe_flux_batch(int n, const double *Ul, const double *Ur, const double *Wl, const double *Wr,

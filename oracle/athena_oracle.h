@@ -85,6 +85,11 @@ void orc_prim_to_cons(const double W[6], int nscal, double gamma, double U[6]);
 void orc_bvals_ionrad(const OrcGrid *g, double flux_i, double *edgeflux);
 
 /* batch helpers for the unit tests: n independent interfaces / states, rows of 6 doubles */
+/* rsolvers/hllc.c:50-261; orc_set_riemann_solver(1) makes orc_integrate_3d_ctu use it (the reference's
+ * --with-flux=hllc build, configured without H-correction: etah lives in roe.c), 0 = Roe (default). */
+void orc_hllc_flux_batch(int n, const double *Ul, const double *Ur, const double *Wl, const double *Wr,
+                         int nscal, double gamma, double *F);
+void orc_set_riemann_solver(int kind);
 void orc_roe_flux_batch(int n, const double *Ul, const double *Ur, const double *Wl, const double *Wr,
                         int nscal, double gamma, const double *etah, double *F);
 void orc_prim_to_cons_batch(int n, const double *W, int nscal, double gamma, double *U);

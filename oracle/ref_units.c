@@ -20,7 +20,11 @@
 
 /* globals.h symbols the units reference */
 Real Gamma, Gamma_1, Gamma_2;
+#ifdef ROE_FLUX
 extern Real etah;                       /* defined in rsolvers/roe.c:33 */
+#else
+static Real etah;                       /* hllc.c takes no H-correction */
+#endif
 
 void ath_error(char *fmt, ...)
 {
@@ -28,6 +32,8 @@ void ath_error(char *fmt, ...)
   va_start(ap, fmt); vfprintf(stderr, fmt, ap); va_end(ap);
   abort();
 }
+
+int ath_perr(const int level, const char *fmt, ...) { (void)level; (void)fmt; return 0; }   /* hllc.c:151 diagnostic */
 
 #define NV ((int)(sizeof(Cons1DS)/sizeof(Real)))
 

@@ -36,6 +36,8 @@ class Case:
         self.par = par_for(self.gold)
         p = self.par
         self.build = str(self.gold["build"])
+        self.riemann = 1 if self.build.endswith("_hllc") else 0          # 0 Roe + H-correction, 1 HLLC (reference --with-flux=hllc)
+        self.problem = self.build.replace("_hllc", "")
         self.nx = tuple(p.par_geti("domain1", f"Nx{a}") for a in (1, 2, 3))
         self.xmin = tuple(p.par_getd("domain1", f"x{a}min") for a in (1, 2, 3))
         self.xmax = tuple(p.par_getd("domain1", f"x{a}max") for a in (1, 2, 3))
@@ -43,13 +45,13 @@ class Case:
         self.gamma = p.par_getd("problem", "gamma")
         self.cour_no = p.par_getd("time", "cour_no")
         self.tlim = p.par_getd("time", "tlim")
-        self.ion = self.build in ("ifront", "ioniz_sphere")
+        self.ion = self.problem in ("ifront", "ioniz_sphere")
         self.nscal = 1 if self.ion else 0
         self.flux_i = p.par_getd("problem", "flux") if self.ion else 0.0
         self.nsteps = int(self.gold["nstep1"])
         self.U0 = {v: self.gold[f"U0_{v}"] for v in VARS[:5 + self.nscal]}
         self.U1 = {v: self.gold[f"U1_{v}"] for v in VARS[:5 + self.nscal]}
-        self.has_grav = self.build == "ioniz_sphere"
+        self.has_grav = self.problem == "ioniz_sphere"
 
     # ---- problem hooks (host C, athena_b200/csrc/problems.c) ------------------------------------
     def problem_lib(self):

@@ -51,6 +51,11 @@ CASES = {
     "ifrontsmr": ("ifront_smr", "ifront.athinput",
                   ["job/num_domains=2", "domain1/Nx1=32", "domain1/Nx2=16", "domain1/Nx3=16",
                    "domain2/Nx1=24", "domain2/Nx2=16", "domain2/Nx3=16", "domain2/iDisp=8", "domain2/jDisp=8", "domain2/kDisp=8"], [1, 3]),
+    # the reference configured --with-flux=hllc (no H-correction: etah is Roe-only)
+    "blast16hllc": ("blast_hllc", "blast.athinput",
+                    ["domain1/Nx1=16", "domain1/Nx2=16", "domain1/Nx3=16", "problem/radius=0.25"], [6]),
+    "ifront32hllc": ("ifront_hllc", "ifront.athinput",
+                     ["domain1/Nx1=32", "domain1/Nx2=16", "domain1/Nx3=16"], [4]),
     # three nested levels.  The reference's serial build segfaults below level 1 with ion RT, so these
     # come from its MPI branch run as one rank against oracle/mpi_stub (builds *_smr_mpi).  n_H lowered so the box
     # is optically thin-ish (tau ~ 0.3 per root cell) and non-trivial fluxes are handed down to both fine levels.
@@ -112,7 +117,8 @@ def make_units(seed=20261018):
     """Function-level vectors: reference lr_states()/fluxes()/Cons1D_to_Prim1D() on seeded random states."""
     dp = C.POINTER(C.c_double)
     P = lambda a: a.ctypes.data_as(dp)
-    for cfg, nscal in (("ifront", 1), ("blast", 0)):
+    for cfg, nscal in (("ifront", 1), ("blast", 0), ("ifront_hllc", 1), ("blast_hllc", 0)):
+        hllc = cfg.endswith("_hllc")
         ref = C.CDLL(os.path.join(REFDIR, cfg, "libref_units.so"))
         ref.ref_set_gamma.argtypes = [C.c_double]
         ref.ref_fluxes.argtypes = [dp, dp, dp, dp, C.c_double, dp]
@@ -149,7 +155,7 @@ def make_units(seed=20261018):
                 w[:] = w[0] + np.cumsum(0.02 * w, axis=0)
                 w[:, 0] = np.abs(w[:, 0]) + 0.1; w[:, 4] = np.abs(w[:, 4]) + 0.01
             ref.ref_lr_states(P(w), n, 0.01, 0.05, 3, n - 4, P(WL[t]), P(WR[t]))
-        path = os.path.join(HERE, f"units_nscal{nscal}.npz")
+        path = os.path.join(HERE, f"units_{'hllc_' if hllc else ''}nscal{nscal}.npz")
         np.savez_compressed(path, gamma=gam, nscal=nscal, Wl=Wl, Wr=Wr, Ul=Ul, Ur=Ur, eta=eta, F=F, W_of_Ul=Wb, cfast_Ul=cf,
                             pencil_W=W, pencil_Wl=WL, pencil_Wr=WR, pencil_dt=0.01, pencil_dx=0.05, pencil_il=3, pencil_iu=n - 4)
         print(path, os.path.getsize(path) // 1024, "KiB")
@@ -159,14 +165,15 @@ if __name__ == "__main__":
     spec = importlib.util.spec_from_file_location("build_ref", os.path.join(ROOT, "oracle", "build_ref.py"))
     br = importlib.util.module_from_spec(spec); spec.loader.exec_module(br)
     if os.path.isdir(os.path.join(br.REF, "src")):
-        for c in ("ifront", "ioniz_sphere", "blast", "ifront_smr", "blast_smr", "ifront_smr_mpi", "blast_smr_mpi"):
+        for c in ("ifront", "ioniz_sphere", "blast", "ifront_smr", "blast_smr", "ifront_smr_mpi", "blast_smr_mpi",
+                  "blast_hllc", "ifront_hllc"):
             br.build(c)
-        for c in ("ifront", "blast"):
+        for c in ("ifront", "blast", "ifront_hllc", "blast_hllc"):
             br.build_units(c)
     only = sys.argv[1:]
     if only:
         CASES = {k: v for k, v in CASES.items() if k in only}
         globals()["CASES"] = CASES
     make_runs()
-    if not only:
+    if not only or "units" in only:
         make_units()

@@ -36,7 +36,43 @@ def test_units_bit_exact(nscal):
         assert np.array_equal(Wr[il - 1:iu + 1], g["pencil_Wr"][t][il - 1:iu + 1])
 
 
+@pytest.mark.parametrize("nscal", [0, 1])
+def test_hllc_flux_bit_exact(nscal):
+    """rsolvers/hllc.c's fluxes() (reference object, oracle/_ref/*_hllc/libref_units.so) on the same seeded states"""
+    g = load_golden(f"units_hllc_nscal{nscal}")
+    n = len(g["Wl"])
+    c = lambda k: np.ascontiguousarray(g[k])
+    F = np.empty((n, 6))
+    ol.lib().orc_hllc_flux_batch(n, ol.P(c("Ul")), ol.P(c("Ur")), ol.P(c("Wl")), ol.P(c("Wr")), nscal, float(g["gamma"]), ol.P(F))
+    assert np.array_equal(F, g["F"])
+    roe = load_golden(f"units_nscal{nscal}")
+    assert np.array_equal(roe["Ul"], g["Ul"]) and not np.array_equal(roe["F"], g["F"]), "same inputs, a different solver"
+    # PLM steps 8-9 in their HLL-family form (lr_states_plm.c:257-293)
+    L = ol.lib()
+    il, iu = int(g["pencil_il"]), int(g["pencil_iu"])
+    L.orc_set_riemann_solver(1)
+    try:
+        for t in range(len(g["pencil_W"])):
+            Wp = np.ascontiguousarray(g["pencil_W"][t])
+            m = len(Wp)
+            Wl = np.zeros((m, 6)); Wr = np.zeros((m, 6))
+            L.orc_lr_states(ol.P(Wp), nscal, float(g["gamma"]), float(g["pencil_dt"]), float(g["pencil_dx"]), il, iu, ol.P(Wl), ol.P(Wr))
+            assert np.array_equal(Wl[il:iu + 2], g["pencil_Wl"][t][il:iu + 2])
+            assert np.array_equal(Wr[il - 1:iu + 1], g["pencil_Wr"][t][il - 1:iu + 1])
+    finally:
+        L.orc_set_riemann_solver(0)
+    assert not np.array_equal(roe["pencil_Wl"], g["pencil_Wl"])
+
+
 def oracle_run(case, log=None):
+    ol.lib().orc_set_riemann_solver(case.riemann)
+    try:
+        return _oracle_run(case, log)
+    finally:
+        ol.lib().orc_set_riemann_solver(0)
+
+
+def _oracle_run(case, log=None):
     grav = case.grav_fn()
     G = ol.OracleGrid(case.nx, case.xmin, case.xmax, case.gamma, case.nscal, case.bc, grav=grav)
     G.set_active(case.U0)
@@ -59,7 +95,7 @@ def oracle_run(case, log=None):
 
 
 @pytest.mark.parametrize("name", ["blast16_k1", "blast16_k6", "blastmix_k5", "ifront32_k1", "ifront32_k4",
-                                  "ioniz24_k1", "ioniz24_k3"])
+                                  "ioniz24_k1", "ioniz24_k3", "blast16hllc_k6", "ifront32hllc_k4"])
 def test_run_matches_reference_dump(name):
     case = Case(name)
     log = {}
