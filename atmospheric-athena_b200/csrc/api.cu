@@ -132,6 +132,7 @@ ab2_grid* ab2_grid_create(const ab2_grid_desc* d)
   g.st[0] = 1; g.st[1] = g.n[0]; g.st[2] = (long)g.n[0]*g.n[1];
   g.dx[0] = d->dx1; g.dx[1] = d->dx2; g.dx[2] = d->dx3;
   g.Gamma = d->gamma; g.Gamma_1 = d->gamma - 1.0;
+  g.riemann = AB2_RIEMANN_ROE;
   h->xmin[0] = d->x1min; h->xmin[1] = d->x2min; h->xmin[2] = d->x3min;
   const size_t ncell = (size_t)g.n[0]*g.n[1]*g.n[2];
   const int nvar = 5 + d->nscal;
@@ -279,6 +280,16 @@ int ab2_apply_fixed_cells(ab2_grid* h) { return hydro_apply_fixed(h); }
 // ---- static potential -------------------------------------------------------------------------------------
 // 1-D coordinate kinds per direction: the four argument forms the reference uses
 enum { CK_C = 0, CK_M = 1, CK_MH = 2, CK_PH = 3 };
+
+int ab2_set_riemann_solver(ab2_grid* h, int kind)
+{
+  if (!h || (kind != AB2_RIEMANN_ROE && kind != AB2_RIEMANN_HLLC)) {
+    ab2_set_error("[ab2_set_riemann_solver]: kind must be 0 (Roe) or 1 (HLLC)");
+    return -1;
+  }
+  h->g.riemann = kind;
+  return 0;
+}
 
 int ab2_set_static_grav_pot(ab2_grid* h, ab2_grav_pot_fn phi)
 {

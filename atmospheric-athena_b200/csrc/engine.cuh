@@ -26,12 +26,16 @@ __host__ __device__ inline int phi_mix(int d, int t, int plus)
   return PHI_MIX0 + d*4 + slot*2 + plus;
 }
 
+#define AB2_RIEMANN_ROE 0
+#define AB2_RIEMANN_HLLC 1
+
 struct GridDev {
   int nx[3];                 // active zones
   int n[3];                  // with ghosts
   long st[3];                // element strides: st[0]=1, st[1]=n1, st[2]=n1*n2
   double dx[3];
   double Gamma, Gamma_1;
+  int riemann;               // fluxes() of the build being replaced: 0 Roe + H-correction (roe.c), 1 HLLC (hllc.c)
   double* U[AB2_NVAR];       // conserved state, SoA [n3][n2][n1]
   double* Ul[3][AB2_NVAR];   // face states, PHYSICAL component order (d,M1,M2,M3,E,s), one set per face direction
   double* Ur[3][AB2_NVAR];

@@ -18,6 +18,11 @@
 #include "physics.cuh"
 
 #define NG AB2_NG
+#ifdef AB2_FORCE_ROE
+#define RIEMANN_OF(g) 0
+#else
+#define RIEMANN_OF(g) ((g).riemann)
+#endif
 
 // ---------------------------------------------------------------------------------------------------
 // sweep-order <-> physical-order register shuffles
@@ -98,7 +103,7 @@ __global__ void __launch_bounds__(A1_T, (AB2_LB_FIRST_X1*128)/A1_T) k_first_x1(G
     S6 Wm, Wp;
     Wm.d = sW[0][t-1]; Wm.x = sW[1][t-1]; Wm.y = sW[2][t-1]; Wm.z = sW[3][t-1]; Wm.e = sW[4][t-1]; Wm.s = sW[5][t-1];
     Wp.d = sW[0][t+1]; Wp.x = sW[1][t+1]; Wp.y = sW[2][t+1]; Wp.z = sW[3][t+1]; Wp.e = sW[4][t+1]; Wp.s = sW[5][t+1];
-    AB2_GUARDED(plm_cell<NS>(Wm, W0, Wp, dtodx, g.Gamma, Wl_next, Wr_this, ar));
+    AB2_GUARDED(plm_cell<NS>(Wm, W0, Wp, dtodx, g.Gamma, Wl_next, Wr_this, ar, RIEMANN_OF(g) != 0));
     if (GRAV) {   // integrate_3d_ctu.c:318-342
       const long cc = row + c;
       Wl_next.x -= dtodx*(g.phi[PHI_MH0][cc+1] - g.phi[PHI_M0][cc+1]);
@@ -112,7 +117,7 @@ __global__ void __launch_bounds__(A1_T, (AB2_LB_FIRST_X1*128)/A1_T) k_first_x1(G
     Wl.d = sL[0][t-1]; Wl.x = sL[1][t-1]; Wl.y = sL[2][t-1]; Wl.z = sL[3][t-1]; Wl.e = sL[4][t-1]; Wl.s = sL[5][t-1];
     S6 Ul, Ur, F;
     AB2_GUARDED(Ul = prim_to_cons<NS>(Wl, g.Gamma_1, ar); Ur = prim_to_cons<NS>(Wr_this, g.Gamma_1, ar);
-                roe_flux<NS>(Ul, Ur, Wl, Wr_this, 0.0, g.Gamma, g.Gamma_1, F, ar));
+                riemann_flux<NS>(RIEMANN_OF(g), Ul, Ur, Wl, Wr_this, 0.0, g.Gamma, g.Gamma_1, F, ar));
     store_sweep<0,NS>(g.Ul[0], row+c, Ul);
     store_sweep<0,NS>(g.Ur[0], row+c, Ur);
     store_sweep<0,NS>(g.F[0], row+c, F);
@@ -160,7 +165,7 @@ __global__ void __launch_bounds__(128, AB2_LB_FIRST) k_first_march(GridDev g, do
       phi_c = g.phi[PHI_C][cc]; phi_mh = g.phi[PHI_MH0+DIR][cc];
     }
     S6 Wp, Wl_next, Wr_this;
-    AB2_GUARDED(Wp = cons_to_prim<NS>(Ucur, g.Gamma_1, ar); plm_cell<NS>(Wm, W0, Wp, dtodx, g.Gamma, Wl_next, Wr_this, ar));
+    AB2_GUARDED(Wp = cons_to_prim<NS>(Ucur, g.Gamma_1, ar); plm_cell<NS>(Wm, W0, Wp, dtodx, g.Gamma, Wl_next, Wr_this, ar, RIEMANN_OF(g) != 0));
     if (GRAV) {   // integrate_3d_ctu.c:635-645, 819-829
       Wl_next.x -= dtodx*(phi_mh_p - phi_m_p);
       Wr_this.x -= dtodx*(phi_c - phi_mh);
@@ -168,7 +173,7 @@ __global__ void __launch_bounds__(128, AB2_LB_FIRST) k_first_march(GridDev g, do
     if (c >= fs) {
       S6 Ul, Ur, F;
       AB2_GUARDED(Ul = prim_to_cons<NS>(Wl_prev, g.Gamma_1, ar); Ur = prim_to_cons<NS>(Wr_this, g.Gamma_1, ar);
-                  roe_flux<NS>(Ul, Ur, Wl_prev, Wr_this, 0.0, g.Gamma, g.Gamma_1, F, ar));
+                  riemann_flux<NS>(RIEMANN_OF(g), Ul, Ur, Wl_prev, Wr_this, 0.0, g.Gamma, g.Gamma_1, F, ar));
       store_sweep<DIR,NS>(g.Ul[DIR], cc, Ul);
       store_sweep<DIR,NS>(g.Ur[DIR], cc, Ur);
       store_sweep<DIR,NS>(g.F[DIR], cc, F);
@@ -284,7 +289,7 @@ __global__ void __launch_bounds__(128, AB2_LB_FINAL) k_final(GridDev g, Box b)
   const S6 Ur = load_sweep<DIR,NS>(g.Ur[DIR], c);
   S6 F;
   AB2_GUARDED(const S6 Wl = cons_to_prim<NS>(Ul, g.Gamma_1, ar); const S6 Wr = cons_to_prim<NS>(Ur, g.Gamma_1, ar);
-              roe_flux<NS>(Ul, Ur, Wl, Wr, etah, g.Gamma, g.Gamma_1, F, ar));
+              riemann_flux<NS>(RIEMANN_OF(g), Ul, Ur, Wl, Wr, etah, g.Gamma, g.Gamma_1, F, ar));
   store_sweep<DIR,NS>(g.F[DIR], c, F);
 }
 

@@ -22,6 +22,16 @@ template <int NS> __global__ void k_unit_flux(int n, const double* Ul, const dou
   st6(F+6*t, f);
 }
 
+template <int NS> __global__ void k_unit_hllc(int n, const double* Ul, const double* Ur, const double* Wl, const double* Wr, double Gamma, double* F)
+{
+  const int t = blockIdx.x*blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  S6 f;
+  const S6 ul = ld6(Ul+6*t), ur = ld6(Ur+6*t), wl = ld6(Wl+6*t), wr = ld6(Wr+6*t);
+  AB2_GUARDED(hllc_flux<NS>(ul, ur, wl, wr, Gamma, Gamma-1.0, f, ar));
+  st6(F+6*t, f);
+}
+
 template <int NS> __global__ void k_unit_convert(int n, const double* in, double Gamma, int to_prim, double* out, double* cf)
 {
   const int t = blockIdx.x*blockDim.x + threadIdx.x;
@@ -35,7 +45,7 @@ template <int NS> __global__ void k_unit_convert(int n, const double* in, double
 }
 
 // one thread per (pencil, cell): cells il-1..iu+1 write Wl[i+1], Wr[i]  (lr_states_plm.c:96)
-template <int NS> __global__ void k_unit_plm(int npen, int n, const double* W, double Gamma, double dtodx, int il, int iu, double* Wl, double* Wr)
+template <int NS> __global__ void k_unit_plm(int npen, int n, const double* W, double Gamma, double dtodx, int il, int iu, double* Wl, double* Wr, bool hll)
 {
   const int t = blockIdx.x*blockDim.x + threadIdx.x;
   const int ncell = iu - il + 3;
@@ -44,8 +54,7 @@ template <int NS> __global__ void k_unit_plm(int npen, int n, const double* W, d
   const double* w = W + (size_t)pen*n*6;
   S6 wl, wr;
   const S6 wm = ld6(w+6*(i-1)), w0 = ld6(w+6*i), wp = ld6(w+6*(i+1));
-  { Arith<true> ar; plm_cell<NS>(wm, w0, wp, dtodx, Gamma, wl, wr, ar);
-    if (ar.bad) { Arith<false> ax; plm_cell<NS>(wm, w0, wp, dtodx, Gamma, wl, wr, ax); } }
+  AB2_GUARDED(plm_cell<NS>(wm, w0, wp, dtodx, Gamma, wl, wr, ar, hll));
   st6(Wl + ((size_t)pen*n + i+1)*6, wl);
   st6(Wr + ((size_t)pen*n + i)*6, wr);
 }
@@ -130,18 +139,38 @@ int ab2_unit_libm(int n, const double* x, const double* y, double* exp_x, double
   return 0;
 }
 
+static int unit_lr_states(int npencil, int n, const double* W, int nscal, double gamma, double dt, double dx,
+                          int il, int iu, double* Wl, double* Wr, bool hll);
 int ab2_unit_lr_states(int npencil, int n, const double* W, int nscal, double gamma, double dt, double dx,
                        int il, int iu, double* Wl, double* Wr)
+{ return unit_lr_states(npencil, n, W, nscal, gamma, dt, dx, il, iu, Wl, Wr, false); }
+int ab2_unit_lr_states_hll(int npencil, int n, const double* W, int nscal, double gamma, double dt, double dx,
+                           int il, int iu, double* Wl, double* Wr)
+{ return unit_lr_states(npencil, n, W, nscal, gamma, dt, dx, il, iu, Wl, Wr, true); }
+
+int ab2_unit_hllc_flux(int n, const double* Ul, const double* Ur, const double* Wl, const double* Wr,
+                       int nscal, double gamma, double* F)
+{
+  DevBuf a(6*n,Ul), b(6*n,Ur), c(6*n,Wl), d(6*n,Wr), f(6*n);
+  if (!a.p || !b.p || !c.p || !d.p || !f.p) { ab2_set_error("[ab2_unit_hllc_flux]: cudaMalloc failed"); return -1; }
+  if (nscal) k_unit_hllc<1><<<(n+127)/128,128>>>(n,a.p,b.p,c.p,d.p,gamma,f.p);
+  else k_unit_hllc<0><<<(n+127)/128,128>>>(n,a.p,b.p,c.p,d.p,gamma,f.p);
+  if (!ab2_check(cudaMemcpy(F, f.p, 6*n*sizeof(double), cudaMemcpyDeviceToHost), "unit hllc flux")) return -1;
+  return 0;
+}
+
+} // extern "C"
+
+static int unit_lr_states(int npencil, int n, const double* W, int nscal, double gamma, double dt, double dx,
+                          int il, int iu, double* Wl, double* Wr, bool hll)
 {
   const size_t tot = (size_t)npencil*n*6;
   DevBuf w(tot,W), l(tot), r(tot);
   if (!w.p || !l.p || !r.p) { ab2_set_error("[ab2_unit_lr_states]: cudaMalloc failed"); return -1; }
   const int nt = npencil*(iu-il+3);
-  if (nscal) k_unit_plm<1><<<(nt+127)/128,128>>>(npencil,n,w.p,gamma,dt/dx,il,iu,l.p,r.p);
-  else k_unit_plm<0><<<(nt+127)/128,128>>>(npencil,n,w.p,gamma,dt/dx,il,iu,l.p,r.p);
+  if (nscal) k_unit_plm<1><<<(nt+127)/128,128>>>(npencil,n,w.p,gamma,dt/dx,il,iu,l.p,r.p,hll);
+  else k_unit_plm<0><<<(nt+127)/128,128>>>(npencil,n,w.p,gamma,dt/dx,il,iu,l.p,r.p,hll);
   if (!ab2_check(cudaMemcpy(Wl, l.p, tot*sizeof(double), cudaMemcpyDeviceToHost), "unit plm")) return -1;
   if (!ab2_check(cudaMemcpy(Wr, r.p, tot*sizeof(double), cudaMemcpyDeviceToHost), "unit plm")) return -1;
   return 0;
 }
-
-} // extern "C"

@@ -65,7 +65,8 @@ def exchange_x3_ghosts(U, rank: int, world: int, bc_ix3: int, bc_ox3: int, dist=
 class Run:
     """MeshS + one DomainS + this rank's GridS, driven like main.c."""
 
-    def __init__(self, par, problem: str, device: int = 0, dist=None, U0: dict | None = None, torch_memory: bool | None = None):
+    def __init__(self, par, problem: str, device: int = 0, dist=None, U0: dict | None = None, torch_memory: bool | None = None,
+                 riemann: int = 0):
         self.par = par
         self.problem = problem
         self.dist = dist
@@ -96,6 +97,8 @@ class Run:
                 self.bc_local[5] = 0
         self.G = engine.Grid(self.nx, self.dx, self.xmin, self.gamma, self.nscal, device=device,
                              torch_memory=(self.world > 1) if torch_memory is None else torch_memory)
+        if riemann:
+            self.G.set_riemann_solver(riemann)       # the reference's --with-flux=hllc build
         self.time, self.dt, self.nstep = 0.0, 0.0, 0
         self.flux_i = p.par_getd("problem", "flux") if self.ion else 0.0
         self.rad_log = []

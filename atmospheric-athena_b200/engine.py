@@ -69,7 +69,8 @@ EXPORTS = ["ab2_last_error", "ab2_version", "ab2_device_count", "ab2_grid_create
            "ab2_unit_roe_flux", "ab2_unit_convert", "ab2_unit_lr_states", "ab2_unit_ieee", "ab2_unit_libm",
            "ab2_profile_enable", "ab2_profile_kernels", "ab2_profile_kernel_name", "ab2_profile_read",
            "ab2_smr_restrict_correct", "ab2_smr_ion_restrict", "ab2_smr_prolongate", "ab2_smr_ion_prolong",
-           "ab2_ion_radtransfer_3d_fine", "ab2_ion_coarse_time"]
+           "ab2_ion_radtransfer_3d_fine", "ab2_ion_coarse_time",
+           "ab2_set_riemann_solver", "ab2_unit_hllc_flux", "ab2_unit_lr_states_hll"]
 
 
 def build(verbose=False):
@@ -144,6 +145,9 @@ def lib():
     L.ab2_unit_roe_flux.argtypes = [C.c_int, dp, dp, dp, dp, C.c_int, C.c_double, dp, dp]
     L.ab2_unit_convert.argtypes = [C.c_int, dp, C.c_int, C.c_double, C.c_int, dp, dp]
     L.ab2_unit_lr_states.argtypes = [C.c_int, C.c_int, dp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, dp, dp]
+    L.ab2_unit_lr_states_hll.argtypes = L.ab2_unit_lr_states.argtypes
+    L.ab2_unit_hllc_flux.argtypes = [C.c_int, dp, dp, dp, dp, C.c_int, C.c_double, dp]
+    L.ab2_set_riemann_solver.argtypes = [vp, C.c_int]
     _lib = L
     return L
 
@@ -289,6 +293,10 @@ class Grid:
             return
         self._keep.append(fn)
         self._ck(lib().ab2_set_static_grav_pot(self.h, C.cast(fn, C.c_void_p)))
+
+    def set_riemann_solver(self, kind):
+        """0 = Roe + H-correction (rsolvers/roe.c, default), 1 = HLLC (rsolvers/hllc.c): the reference's --with-flux"""
+        self._ck(lib().ab2_set_riemann_solver(self.h, int(kind)))
 
     def integrate_3d_ctu(self, dt):
         self._ck(lib().ab2_integrate_3d_ctu(self.h, dt))

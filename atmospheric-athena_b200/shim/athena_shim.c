@@ -71,6 +71,11 @@ static Mirror *mirror_of(GridS *pG)
     mir[nmir].pG = pG;
     mir[nmir].h = ab2_grid_create(&d);
     if (mir[nmir].h == NULL) die("ab2_grid_create");
+#if defined(HLLC_FLUX)           /* the driver was configured --with-flux=hllc: rsolvers/hllc.c + lr_states_plm.c:257 */
+    if (ab2_set_riemann_solver(mir[nmir].h, 1) != 0) die("ab2_set_riemann_solver");
+#elif !defined(ROE_FLUX)
+#error "libathena_b200 replaces the Roe and HLLC solvers only"
+#endif
     mir[nmir].dev_valid = 0; mir[nmir].host_fresh = 1;
   }
   return &mir[nmir++];

@@ -100,6 +100,11 @@ int ab2_new_dt(ab2_grid* g, double cour_no, double dt_old, int nstep, double tim
 int ab2_set_static_grav_pot(ab2_grid* g, ab2_grav_pot_fn phi);
 /* integrate_3d_ctu (integrators/integrate_3d_ctu.c:110-3368) with GridS.dt = dt. */
 int ab2_integrate_3d_ctu(ab2_grid* g, double dt);
+/* The reference fixes its Riemann solver and the matching form of the PLM characteristic tracing at configure time
+ * (--with-flux, src/defs.h.in FLUX_DEF); the replacement library serves either build: kind 0 = Roe with H-correction
+ * and HLLE fallback (rsolvers/roe.c, the shipped configuration, default), kind 1 = HLLC (rsolvers/hllc.c:50-261 with
+ * lr_states_plm.c:257-293; no H-correction -- etah is defined in roe.c only).  Returns -1 for an unknown kind. */
+int ab2_set_riemann_solver(ab2_grid* g, int kind);
 /* Userwork_in_loop replay: a static list of cells (flat indices incl. ghosts) reset to fixed values
  * vals[6][n] every step, e.g. prob/ioniz_sphere.c:255-306. */
 int ab2_set_fixed_cells(ab2_grid* g, long n, const long* cells, const double* vals);
@@ -167,6 +172,12 @@ int ab2_unit_libm(int n, const double* x, const double* y, double* exp_x, double
 /* lr_states() of reconstruction/lr_states_plm.c:62-374 on npencil pencils of n cells */
 int ab2_unit_lr_states(int npencil, int n, const double* W, int nscal, double gamma, double dt, double dx,
                        int il, int iu, double* Wl, double* Wr);
+/* the same with steps 8-9 in the form an HLLE/HLLC/HLLD build compiles (lr_states_plm.c:257-293) */
+int ab2_unit_lr_states_hll(int npencil, int n, const double* W, int nscal, double gamma, double dt, double dx,
+                           int il, int iu, double* Wl, double* Wr);
+/* fluxes() of rsolvers/hllc.c:50-261 on n independent interfaces */
+int ab2_unit_hllc_flux(int n, const double* Ul, const double* Ur, const double* Wl, const double* Wr,
+                       int nscal, double gamma, double* F);
 
 #ifdef __cplusplus
 }

@@ -20,7 +20,7 @@ def main():
     ok = True
     for name in sys.argv[1:]:
         case = Case(name)
-        R = Run(case.par, case.build, device=local, dist=dist, U0=case.U0)
+        R = Run(case.par, case.problem, device=local, dist=dist, U0=case.U0, riemann=case.riemann)
         R.run(case.nsteps)
         mine = R.G.download_active()
         nv = 5 + case.nscal
@@ -29,7 +29,7 @@ def main():
         dist.all_gather(parts, loc)
         if rank == 0:
             full = torch.cat(parts, dim=1).cpu().numpy()
-            single = Run(case.par, case.build, device=local, dist=None, U0=case.U0)
+            single = Run(case.par, case.problem, device=local, dist=None, U0=case.U0, riemann=case.riemann)
             single.run(case.nsteps)
             ref = single.G.download_active()
             same = all(np.array_equal(full[n], ref[v], equal_nan=True) for n, v in enumerate(VARS[:nv]))

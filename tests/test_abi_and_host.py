@@ -68,6 +68,6 @@ def test_host_problem_generators_match_reference_t0(name):
     """csrc/problems.c (host C) reproduces the reference problem() output bit for bit (same libm)."""
     case = Case(name)
     dx = tuple((case.xmax[a] - case.xmin[a]) / case.nx[a] for a in range(3))
-    U = problems.problem(case.build, case.par, case.nx, case.xmin, dx)
+    U = problems.problem(case.problem, case.par, case.nx, case.xmin, dx)
     for v in case.U0:
         assert np.array_equal(U[v][4:-4, 4:-4, 4:-4], case.U0[v]), v
