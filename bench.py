@@ -157,6 +157,29 @@ def run_reference_cpu(workload, n, nsteps, instances):
     return total, wall, "reference"
 
 
+def run_dropin(workload, n, nsteps):
+    """The UNMODIFIED reference driver linked against libathena_b200 (build/dropin/<problem>/athena) on
+    the bench grid: the throughput a user of the reference sees after relinking -- the reference's own
+    `zone-cycles/wall-second` line (main.c:722: main-loop wall clock, host `U` uploaded before the first step and
+    downloaded for the final dump, coherence in between only where a writer fires).  None if the executable is absent."""
+    prob = WORKLOADS[workload][1]
+    exe = os.path.join(ROOT, "build", "dropin", prob, "athena")
+    if not os.path.exists(exe):
+        return None
+    tmp = tempfile.mkdtemp(prefix="ath_dropin_")
+    cmd = [exe, "-i", os.path.join(DECKS, WORKLOADS[workload][0]), "job/maxout=0", "job/num_domains=1",
+           f"domain1/Nx1={n}", f"domain1/Nx2={n}", f"domain1/Nx3={n}", f"time/nlim={nsteps}"]
+    t0 = time.time()
+    r = subprocess.run(cmd, cwd=tmp, capture_output=True, text=True)
+    wall = time.time() - t0
+    subprocess.run(["rm", "-rf", tmp])
+    m = re.search(r"zone-cycles/wall-second = (\S+)", r.stdout)
+    if r.returncode != 0 or not m:
+        return {"error": (r.stdout[-300:] + r.stderr[-300:]).strip()}
+    return {"value": float(m.group(1)), "unit": "zone-updates/s", "steps": nsteps, "process_wall_s": round(wall, 1),
+            "what": "unmodified reference driver + shim + libathena_b200, its own main-loop zone-cycles/wall-second"}
+
+
 def run_port_cpu(workload, n, nsteps):
     """Fallback when oracle/_ref is absent: the oracle port (oracle/athena_oracle.c), 1 thread."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -343,6 +366,11 @@ def gpu_arm(args):
         cpu = {"value": v, "unit": "zone-updates/s", "cores": 1, "kind": kind,
                "sample": f"{args.cpu_n}^3 zones, {args.cpu_steps} steps from t=0, serial reference build (gcc -O3, no MPI in this image), {wall:.1f} s"}
 
+    dropin = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        torch.cuda.synchronize()
+        dropin = run_dropin(args.workload, n, args.warmup + args.steps)
+
     if rank == 0:
         line = {
             "metric": "zone-updates/s per hydro+ion-RT step", "value": value, "unit": "zone-updates/s",
@@ -352,7 +380,7 @@ def gpu_arm(args):
                        "zones_per_gpu": zones_local, "parallelism": f"x3-slabs x{world}",
                        "ion_iterations_per_step": round(n_iter, 2), "l2": "working set >> L2 (state + scratch = "
                        f"{G.bytes_allocated / 2**30:.1f} GiB per GPU), no flush needed", "setup_s": round(t_setup, 1)},
-            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "kernels": ktab,
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "dropin": dropin, "kernels": ktab,
         }
         print(json.dumps(line))
     if world > 1:
