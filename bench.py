@@ -388,13 +388,91 @@ def gpu_arm(args):
     return 0
 
 
+def smr_arm(args):
+    """SURVEY 8d cfg 4: the SHIPPED 5-level ioniz_sphere deck (80^3/52^3/96^3/176^3/320^3 = 39.8 M zones, static
+    potential, Userwork reset, ion RT on every level), one GPU (driver.SmrRun) or every level cut on common x3 planes
+    over N GPUs (driver.SmrRunSlabs, balanced cuts).  Strong scaling: the deck is fixed."""
+    import torch
+    import torch.distributed as dist
+    from athena_b200.athinput import ParFile
+    from athena_b200.driver import SmrRun, SmrRunSlabs
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    par = ParFile.par_open(os.path.join(DECKS, "ioniz_sphere_hires.athinput"))
+    nlev = par.par_geti("job", "num_domains")
+    zones_total = sum(par.par_geti(f"domain{n + 1}", "Nx1") * par.par_geti(f"domain{n + 1}", "Nx2") * par.par_geti(f"domain{n + 1}", "Nx3")
+                      for n in range(nlev))
+    t_setup = time.time()
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+        R = SmrRunSlabs(par, "ioniz_sphere", None, dist, device=local, cuts="balanced")
+        grids = [L["G"] for L in R.levels if L is not None]
+        cuts = R.cuts
+    else:
+        R = SmrRun(par, "ioniz_sphere", None, device=local)
+        grids, cuts = R.grids, [0, par.par_geti("domain1", "Nx3")]
+    t_setup = time.time() - t_setup
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    for _ in range(args.warmup):
+        R.step()
+    barrier()
+    l0 = sum(G.kernel_launches for G in grids)
+    it0 = len(R.rad_log)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    w0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        R.step()
+    e1.record()
+    barrier()
+    w1 = time.time()
+    ms = e0.elapsed_time(e1)
+    launches = sum(G.kernel_launches for G in grids) - l0
+    if world > 1:
+        t = torch.tensor([ms, float(launches)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t[:1], op=dist.ReduceOp.MAX)
+        dist.all_reduce(t[1:], op=dist.ReduceOp.SUM)
+        ms, launches = float(t[0].item()), int(t[1].item())
+    clocks = sampler.summary(w0, w1) if sampler else None
+    its = [r[0] for r in R.rad_log[it0:]]
+    peak, peak_src = measured_peaks()
+    value = zones_total * args.steps / (ms * 1e-3)
+    n_iter = sum(its) / max(1, len(its))
+    b_alg = 128 + n_iter * 112                       # SURVEY 8(d): B_hydro (static potential) + n_iter * B_ion
+    if rank == 0:
+        line = {"metric": "zone-updates/s per hydro+ion-RT step", "value": value, "unit": "zone-updates/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"configs[3] ioniz_sphere SMR, shipped 5-level deck {zones_total} zones, steps {args.warmup}..{args.warmup + args.steps} from t=0",
+                           "parallelism": f"x3 cut planes at root layers {cuts}", "ion_iterations_per_level_step": round(n_iter, 2),
+                           "l2": "working set >> L2, no flush needed", "setup_s": round(t_setup, 1)},
+                "e2e": None, "gpu_launches": int(launches), "clocks": clocks,
+                "roofline": {"bound": "hbm", "kernel": "whole step", "achieved": round(value / world * b_alg / 1e9, 1), "peak": peak, "unit": "GB/s",
+                             "frac": round(value / world * b_alg / 1e9 / peak, 4), "traffic": None, "peak_source": peak_src,
+                             "note": "whole step at SURVEY 8(d) compulsory bytes per GPU; per-kernel rooflines are those of the unigrid workload"},
+                "cpu_baseline": None}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="ioniz_sphere", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="ioniz_sphere", choices=sorted(WORKLOADS) + ["ioniz_smr"])
     ap.add_argument("--n", "--size", dest="n", type=int, default=256, help="zones per direction per GPU (use --size under torchrun, whose own parser trips over --n)")
     ap.add_argument("--strong", action="store_true", help="--n is the GLOBAL cube size, cut into --gpus x3 slabs (strong scaling)")
     ap.add_argument("--e2e-steps", type=int, default=5)
@@ -404,6 +482,10 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         print("bench.py: note: fewer than 3 warm-up steps", file=sys.stderr)
+    if args.workload == "ioniz_smr":
+        if args.impl == "reference":
+            raise SystemExit("bench.py: the reference arm of the SMR deck is tests/golden/make_hires5_fingerprint.py (6 min per step on one core)")
+        return smr_arm(args)
     return reference_arm(args) if args.impl == "reference" else gpu_arm(args)
 
 
