@@ -133,3 +133,36 @@ def test_dropin_shipped_five_level_deck_matches_reference_fingerprint():
         for v in fp5.VARS:
             assert a[v]["shape"] == b[v]["shape"]
             assert a[v]["sha256"] == b[v]["sha256"], f"level {lev} {v}: sum {a[v]['sum']!r} vs {b[v]['sum']!r}, absmax {a[v]['absmax']!r} vs {b[v]['absmax']!r}"
+
+
+def test_dropin_restart_from_a_reference_dump():
+    """`athena -r <dump>` (main.c:388 restart_grids instead of problem()): the drop-in continues a run from a restart
+    dump written by the REFERENCE binary -- U and EdgeFlux from the file, the radiator plane and StaticGravPot from
+    problem_read_restart (ioniz_sphere.c:200-236), Userwork_in_loop discovered on an evolved state -- and ends where the
+    reference's own restarted run ends, bit for bit.  (ifront cannot be restarted in the reference itself: its
+    problem_read_restart does not restore the radiator plane and restart.c:284-294 is commented out.  Steps 2-3 only:
+    from step 4 on this under-resolved 24^3 planet puts NaN into U, after which the reference's new_dt depends on the
+    order it visits the cells.)"""
+    case = Case("ioniz24_k3")
+    ref = os.path.join(ROOT, "oracle", "_ref", case.build, "athena")
+    exe = os.path.join(ROOT, "build", "dropin", case.build, "athena")
+    if not (os.path.exists(ref) and os.path.exists(exe)):
+        pytest.skip("needs oracle/_ref and build/dropin")
+    deck = os.path.join(DECKS, str(case.gold["deck"]))
+    ov = [str(x) for x in case.gold["overrides"]]
+    with tempfile.TemporaryDirectory() as a, tempfile.TemporaryDirectory() as b, tempfile.TemporaryDirectory() as c:
+        r = subprocess.run([ref, "-i", deck, "time/nlim=1"] + ov, cwd=a, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-1000:]
+        dump = os.path.join(a, sorted(f for f in os.listdir(a) if f.endswith(".rst"))[-1])
+        out = {}
+        for tag, binary, cwd in (("ref", ref, b), ("b200", exe, c)):
+            r = subprocess.run([binary, "-r", dump, "time/nlim=3"], cwd=cwd, capture_output=True, text=True)
+            assert r.returncode == 0, tag + r.stdout[-1500:] + r.stderr[-1500:]
+            rst = sorted(f for f in os.listdir(cwd) if f.endswith(".rst"))
+            out[tag] = (read_restart(os.path.join(cwd, rst[-1])), [int(x) for x in re.findall(r"Radiation done in (\d+) iterations", r.stderr)])
+    (x, rad_x), (y, rad_y) = out["ref"], out["b200"]
+    assert x["nstep"] == y["nstep"] == 3 and rad_x == rad_y and len(rad_x) == 2
+    assert x["time"] == y["time"] and x["dt"] == y["dt"]
+    for v in x["grids"][0]:
+        assert not np.isnan(x["grids"][0][v]).any()
+        assert np.array_equal(x["grids"][0][v], y["grids"][0][v]), v
