@@ -283,8 +283,8 @@ enum { CK_C = 0, CK_M = 1, CK_MH = 2, CK_PH = 3 };
 
 int ab2_set_riemann_solver(ab2_grid* h, int kind)
 {
-  if (!h || (kind != AB2_RIEMANN_ROE && kind != AB2_RIEMANN_HLLC)) {
-    ab2_set_error("[ab2_set_riemann_solver]: kind must be 0 (Roe) or 1 (HLLC)");
+  if (!h || (kind != AB2_RIEMANN_ROE && kind != AB2_RIEMANN_HLLC && kind != AB2_RIEMANN_ROE_NOH)) {
+    ab2_set_error("[ab2_set_riemann_solver]: kind must be 0 (Roe + H-correction), 1 (HLLC) or 2 (Roe without H-correction)");
     return -1;
   }
   h->g.riemann = kind;

@@ -28,6 +28,7 @@ __host__ __device__ inline int phi_mix(int d, int t, int plus)
 
 #define AB2_RIEMANN_ROE 0
 #define AB2_RIEMANN_HLLC 1
+#define AB2_RIEMANN_ROE_NOH 2     // Roe, reference built without --enable-h-correction: etah = 0 in every solve
 
 struct GridDev {
   int nx[3];                 // active zones
@@ -35,7 +36,7 @@ struct GridDev {
   long st[3];                // element strides: st[0]=1, st[1]=n1, st[2]=n1*n2
   double dx[3];
   double Gamma, Gamma_1;
-  int riemann;               // fluxes() of the build being replaced: 0 Roe + H-correction (roe.c), 1 HLLC (hllc.c)
+  int riemann;               // fluxes() of the build being replaced: 0 Roe + H-correction (roe.c), 1 HLLC (hllc.c), 2 Roe without H-correction
   double* U[AB2_NVAR];       // conserved state, SoA [n3][n2][n1]
   double* Ul[3][AB2_NVAR];   // face states, PHYSICAL component order (d,M1,M2,M3,E,s), one set per face direction
   double* Ur[3][AB2_NVAR];

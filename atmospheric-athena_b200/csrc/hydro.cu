@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(A1_T, (AB2_LB_FIRST_X1*128)/A1_T) k_first_x1(G
     S6 Wm, Wp;
     Wm.d = sW[0][t-1]; Wm.x = sW[1][t-1]; Wm.y = sW[2][t-1]; Wm.z = sW[3][t-1]; Wm.e = sW[4][t-1]; Wm.s = sW[5][t-1];
     Wp.d = sW[0][t+1]; Wp.x = sW[1][t+1]; Wp.y = sW[2][t+1]; Wp.z = sW[3][t+1]; Wp.e = sW[4][t+1]; Wp.s = sW[5][t+1];
-    AB2_GUARDED(plm_cell<NS>(Wm, W0, Wp, dtodx, g.Gamma, Wl_next, Wr_this, ar, RIEMANN_OF(g) != 0));
+    AB2_GUARDED(plm_cell<NS>(Wm, W0, Wp, dtodx, g.Gamma, Wl_next, Wr_this, ar, RIEMANN_OF(g) == AB2_RIEMANN_HLLC));
     if (GRAV) {   // integrate_3d_ctu.c:318-342
       const long cc = row + c;
       Wl_next.x -= dtodx*(g.phi[PHI_MH0][cc+1] - g.phi[PHI_M0][cc+1]);
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(128, AB2_LB_FIRST) k_first_march(GridDev g, do
       phi_c = g.phi[PHI_C][cc]; phi_mh = g.phi[PHI_MH0+DIR][cc];
     }
     S6 Wp, Wl_next, Wr_this;
-    AB2_GUARDED(Wp = cons_to_prim<NS>(Ucur, g.Gamma_1, ar); plm_cell<NS>(Wm, W0, Wp, dtodx, g.Gamma, Wl_next, Wr_this, ar, RIEMANN_OF(g) != 0));
+    AB2_GUARDED(Wp = cons_to_prim<NS>(Ucur, g.Gamma_1, ar); plm_cell<NS>(Wm, W0, Wp, dtodx, g.Gamma, Wl_next, Wr_this, ar, RIEMANN_OF(g) == AB2_RIEMANN_HLLC));
     if (GRAV) {   // integrate_3d_ctu.c:635-645, 819-829
       Wl_next.x -= dtodx*(phi_mh_p - phi_m_p);
       Wr_this.x -= dtodx*(phi_c - phi_mh);
@@ -277,14 +277,17 @@ __global__ void __launch_bounds__(128, AB2_LB_FINAL) k_final(GridDev g, Box b)
   constexpr int A = (DIR == 0) ? 1 : 0;
   constexpr int B = (DIR == 2) ? 1 : 2;
   const long sd = g.st[DIR], sa = g.st[A], sb = g.st[B];
-  double etah = AB2_MAX(g.eta[A][c-sd], g.eta[A][c]);
-  etah = AB2_MAX(etah, g.eta[A][c-sd+sa]);
-  etah = AB2_MAX(etah, g.eta[A][c+sa]);
-  etah = AB2_MAX(etah, g.eta[B][c-sd]);
-  etah = AB2_MAX(etah, g.eta[B][c]);
-  etah = AB2_MAX(etah, g.eta[B][c-sd+sb]);
-  etah = AB2_MAX(etah, g.eta[B][c+sb]);
-  etah = AB2_MAX(etah, g.eta[DIR][c]);
+  double etah = 0.0;
+  if (RIEMANN_OF(g) == AB2_RIEMANN_ROE) {          // H-correction only where the reference compiles it in and the solver reads it
+    etah = AB2_MAX(g.eta[A][c-sd], g.eta[A][c]);
+    etah = AB2_MAX(etah, g.eta[A][c-sd+sa]);
+    etah = AB2_MAX(etah, g.eta[A][c+sa]);
+    etah = AB2_MAX(etah, g.eta[B][c-sd]);
+    etah = AB2_MAX(etah, g.eta[B][c]);
+    etah = AB2_MAX(etah, g.eta[B][c-sd+sb]);
+    etah = AB2_MAX(etah, g.eta[B][c+sb]);
+    etah = AB2_MAX(etah, g.eta[DIR][c]);
+  }
   const S6 Ul = load_sweep<DIR,NS>(g.Ul[DIR], c);
   const S6 Ur = load_sweep<DIR,NS>(g.Ur[DIR], c);
   S6 F;

@@ -75,6 +75,8 @@ static Mirror *mirror_of(GridS *pG)
     if (ab2_set_riemann_solver(mir[nmir].h, 1) != 0) die("ab2_set_riemann_solver");
 #elif !defined(ROE_FLUX)
 #error "libathena_b200 replaces the Roe and HLLC solvers only"
+#elif !defined(H_CORRECTION)     /* Roe, configured without --enable-h-correction: etah is never set */
+    if (ab2_set_riemann_solver(mir[nmir].h, 2) != 0) die("ab2_set_riemann_solver");
 #endif
     mir[nmir].dev_valid = 0; mir[nmir].host_fresh = 1;
   }

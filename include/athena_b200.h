@@ -103,7 +103,9 @@ int ab2_integrate_3d_ctu(ab2_grid* g, double dt);
 /* The reference fixes its Riemann solver and the matching form of the PLM characteristic tracing at configure time
  * (--with-flux, src/defs.h.in FLUX_DEF); the replacement library serves either build: kind 0 = Roe with H-correction
  * and HLLE fallback (rsolvers/roe.c, the shipped configuration, default), kind 1 = HLLC (rsolvers/hllc.c:50-261 with
- * lr_states_plm.c:257-293; no H-correction -- etah is defined in roe.c only).  Returns -1 for an unknown kind. */
+ * lr_states_plm.c:257-293; no H-correction -- etah is defined in roe.c only), kind 2 = Roe for a build configured
+ * WITHOUT --enable-h-correction (integrate_3d_ctu.c:2299-2426 compiled out, etah stays 0: the configuration of the
+ * reference's linear-wave convergence deck).  Returns -1 for an unknown kind. */
 int ab2_set_riemann_solver(ab2_grid* g, int kind);
 /* Userwork_in_loop replay: a static list of cells (flat indices incl. ghosts) reset to fixed values
  * vals[6][n] every step, e.g. prob/ioniz_sphere.c:255-306. */

@@ -146,7 +146,8 @@ static void esys_roe_adb_hyd(double v1, double v2, double v3, double h, double G
 /* ------------------------------------------------------------------------------------------------
  * lr_states_plm.c:62-374  (CARTESIAN: gamma_curv = 0 => opg = omg = beta = betai = 1)
  * ---------------------------------------------------------------------------------------------- */
-/* which Riemann solver the build is configured with: 0 = roe.c (--with-flux=roe), 1 = hllc.c (--with-flux=hllc).
+/* which Riemann solver the build is configured with: 0 = roe.c with --enable-h-correction, 1 = hllc.c (--with-flux=hllc),
+ * 2 = roe.c without H-correction (the integrator never sets etah, integrate_3d_ctu.c:2299-2426 compiled out).
  * It selects fluxes() AND the form of PLM steps 8-9 (lr_states_plm.c:257 vs :296). */
 static int orc_riemann = 0;
 
@@ -431,7 +432,7 @@ static void fluxes(const C1 Ul, const C1 Ur, const P1 Wl, const P1 Wr, int nscal
                    double Gamma, double Gamma_1, double etah, C1 *pFlux)
 {
   if (orc_riemann == 1) fluxes_hllc(Ul, Ur, Wl, Wr, nscal, Gamma, Gamma_1, pFlux);
-  else fluxes_roe(Ul, Ur, Wl, Wr, nscal, Gamma, Gamma_1, etah, pFlux);
+  else fluxes_roe(Ul, Ur, Wl, Wr, nscal, Gamma, Gamma_1, (orc_riemann == 2) ? 0.0 : etah, pFlux);   /* 2: built without H_CORRECTION, etah stays 0 (roe.c:33) */
 }
 
 /* ------------------------------------------------------------------------------------------------

@@ -86,7 +86,8 @@ void orc_bvals_ionrad(const OrcGrid *g, double flux_i, double *edgeflux);
 
 /* batch helpers for the unit tests: n independent interfaces / states, rows of 6 doubles */
 /* rsolvers/hllc.c:50-261; orc_set_riemann_solver(1) makes orc_integrate_3d_ctu use it (the reference's
- * --with-flux=hllc build, configured without H-correction: etah lives in roe.c), 0 = Roe (default). */
+ * --with-flux=hllc build, configured without H-correction: etah lives in roe.c), 0 = Roe + H-correction (default),
+ * 2 = Roe built without --enable-h-correction (etah stays 0). */
 void orc_hllc_flux_batch(int n, const double *Ul, const double *Ur, const double *Wl, const double *Wr,
                          int nscal, double gamma, double *F);
 void orc_set_riemann_solver(int kind);

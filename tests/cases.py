@@ -36,8 +36,9 @@ class Case:
         self.par = par_for(self.gold)
         p = self.par
         self.build = str(self.gold["build"])
-        self.riemann = 1 if self.build.endswith("_hllc") else 0          # 0 Roe + H-correction, 1 HLLC (reference --with-flux=hllc)
-        self.problem = self.build.replace("_hllc", "")
+        # 0 Roe + H-correction, 1 HLLC (reference --with-flux=hllc), 2 Roe built without --enable-h-correction
+        self.riemann = 1 if self.build.endswith("_hllc") else (2 if self.build.endswith("_noh") else 0)
+        self.problem = self.build.replace("_hllc", "").replace("_noh", "")
         self.nx = tuple(p.par_geti("domain1", f"Nx{a}") for a in (1, 2, 3))
         self.xmin = tuple(p.par_getd("domain1", f"x{a}min") for a in (1, 2, 3))
         self.xmax = tuple(p.par_getd("domain1", f"x{a}max") for a in (1, 2, 3))

@@ -54,6 +54,8 @@ CASES = {
     # the reference configured --with-flux=hllc (no H-correction: etah is Roe-only)
     "blast16hllc": ("blast_hllc", "blast.athinput",
                     ["domain1/Nx1=16", "domain1/Nx2=16", "domain1/Nx3=16", "problem/radius=0.25"], [6]),
+    "blast16noh": ("blast_noh", "blast.athinput",
+                   ["domain1/Nx1=16", "domain1/Nx2=16", "domain1/Nx3=16", "problem/radius=0.25"], [6]),
     "ifront32hllc": ("ifront_hllc", "ifront.athinput",
                      ["domain1/Nx1=32", "domain1/Nx2=16", "domain1/Nx3=16"], [4]),
     # three nested levels.  The reference's serial build segfaults below level 1 with ion RT, so these
@@ -166,7 +168,7 @@ if __name__ == "__main__":
     br = importlib.util.module_from_spec(spec); spec.loader.exec_module(br)
     if os.path.isdir(os.path.join(br.REF, "src")):
         for c in ("ifront", "ioniz_sphere", "blast", "ifront_smr", "blast_smr", "ifront_smr_mpi", "blast_smr_mpi",
-                  "blast_hllc", "ifront_hllc"):
+                  "blast_hllc", "ifront_hllc", "blast_noh"):
             br.build(c)
         for c in ("ifront", "blast", "ifront_hllc", "blast_hllc"):
             br.build_units(c)

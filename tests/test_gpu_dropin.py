@@ -29,7 +29,7 @@ def run_dropin(case):
     return d1, rad, r
 
 
-@pytest.mark.parametrize("name", ["blast16_k6", "blastmix_k5", "blast16hllc_k6"])
+@pytest.mark.parametrize("name", ["blast16_k6", "blastmix_k5", "blast16hllc_k6", "blast16noh_k6"])
 def test_dropin_hydro_bit_exact(name):
     case = Case(name)
     d1, _, _ = run_dropin(case)
@@ -166,3 +166,31 @@ def test_dropin_restart_from_a_reference_dump():
     for v in x["grids"][0]:
         assert not np.isnan(x["grids"][0][v]).any()
         assert np.array_equal(x["grids"][0][v], y["grids"][0][v]), v
+
+
+# The reference's own (and only) automated check, SURVEY section 4: linear-wave L1 convergence.  prob/linear_wave3d.c stores
+# the eigenmode it starts from and writes the L1 error after 5 periods in Userwork_after_loop.  Values below are what the
+# REFERENCE binary (oracle/_ref/linwave_noh: the deck's own configuration, Roe without H-correction, NSCALARS=1) writes
+# into LinWave-errors.0.dat for the two grids: Nx1 Nx2 Nx3 RMS d M1 M2 M3 E.
+LINWAVE_REFERENCE = {
+    16: "32  16  16  4.293960e-05  2.076469e-05  7.037402e-06  1.401739e-05  1.401739e-05  3.114703e-05",
+    32: "64  32  32  1.225627e-05  5.928812e-06  1.990201e-06  4.000947e-06  4.000947e-06  8.893219e-06",
+}
+
+
+def test_dropin_linear_wave_convergence_known_answer():
+    exe = os.path.join(ROOT, "build", "dropin", "linwave_noh", "athena")
+    if not os.path.exists(exe):
+        pytest.skip("needs build/dropin/linwave_noh")
+    rms = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        for n in (16, 32):
+            r = subprocess.run([exe, "-i", os.path.join(DECKS, "linear_wave3d.athinput"), f"domain1/Nx1={2 * n}", f"domain1/Nx2={n}",
+                                f"domain1/Nx3={n}"], cwd=tmp, capture_output=True, text=True)
+            assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+        rows = [ln.split() for ln in open(os.path.join(tmp, "LinWave-errors.0.dat")) if not ln.startswith("#")]
+    assert len(rows) == 2
+    for row, n in zip(rows, (16, 32)):
+        assert row == LINWAVE_REFERENCE[n].split(), f"N={n}: {row}"       # the very digits the reference prints
+        rms[n] = float(row[3])
+    assert rms[16] / rms[32] > 3.3, "second-order convergence of the sound wave (the reference reaches 3.5 on these grids)"

@@ -134,7 +134,7 @@ def test_hllc_units_bit_exact(nscal):
     assert np.array_equal(Wr[:, il - 1:iu + 1], g["pencil_Wr"][:, il - 1:iu + 1])
 
 
-@pytest.mark.parametrize("name", ["blast16_k1", "blast16_k6", "blastmix_k5", "blast16hllc_k6"])
+@pytest.mark.parametrize("name", ["blast16_k1", "blast16_k6", "blastmix_k5", "blast16hllc_k6", "blast16noh_k6"])
 def test_hydro_bit_exact_vs_reference(name):
     case = Case(name)
     R = gpu_run(case)
