@@ -62,13 +62,13 @@ template <int DIR, int NS> __device__ __forceinline__ S6 sweep_from_phys(const d
 // instead of 3 tiles of 128, 68 % busy)
 // minimum resident blocks per SM (register caps), tuned on B200 at 256^3 (profiles/r1_tuning.md)
 #ifndef AB2_LB_FIRST
-#define AB2_LB_FIRST 3
+#define AB2_LB_FIRST 2
 #endif
 #ifndef AB2_LB_FIRST_X1
 #define AB2_LB_FIRST_X1 4
 #endif
 #ifndef AB2_LB_FINAL
-#define AB2_LB_FINAL 4
+#define AB2_LB_FINAL 5
 #endif
 #ifndef AB2_LB_CORRECT
 #define AB2_LB_CORRECT 6
