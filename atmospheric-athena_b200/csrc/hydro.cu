@@ -71,10 +71,10 @@ template <int DIR, int NS> __device__ __forceinline__ S6 sweep_from_phys(const d
 #define AB2_LB_FINAL 5
 #endif
 #ifndef AB2_LB_CORRECT
-#define AB2_LB_CORRECT 6
+#define AB2_LB_CORRECT 4
 #endif
 #ifndef AB2_LB_UPDATE
-#define AB2_LB_UPDATE 1
+#define AB2_LB_UPDATE 5
 #endif
 template <int NS, bool GRAV, int A1_T>
 __global__ void __launch_bounds__(A1_T, (AB2_LB_FIRST_X1*128)/A1_T) k_first_x1(GridDev g, double dt)
