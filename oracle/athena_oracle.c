@@ -151,8 +151,18 @@ static void esys_roe_adb_hyd(double v1, double v2, double v3, double h, double G
  * It selects fluxes() AND the form of PLM steps 8-9 (lr_states_plm.c:257 vs :296). */
 static int orc_riemann = 0;
 
+static int orc_order = 2;      /* 2 = lr_states_plm.c (SECOND_ORDER_CHAR), 3 = lr_states_ppm.c (THIRD_ORDER_CHAR) */
+static void lr_states_ppm(const P1 W[], int nscal, double Gamma, double dt, double dx, int il, int iu, P1 Wl[], P1 Wr[]);
+static void lr_states_plm(const P1 W[], int nscal, double Gamma, double dt, double dx, int il, int iu, P1 Wl[], P1 Wr[]);
 static void lr_states(const P1 W[], int nscal, double Gamma, double dt, double dx, int il, int iu,
                       P1 Wl[], P1 Wr[])
+{
+  if (orc_order == 3) lr_states_ppm(W, nscal, Gamma, dt, dx, il, iu, Wl, Wr);
+  else lr_states_plm(W, nscal, Gamma, dt, dx, il, iu, Wl, Wr);
+}
+
+static void lr_states_plm(const P1 W[], int nscal, double Gamma, double dt, double dx, int il, int iu,
+                          P1 Wl[], P1 Wr[])
 {
   int i, n, m;
   const int NV = NWAVE + nscal;
@@ -292,6 +302,191 @@ void orc_lr_states(const double (*W)[6], int nscal, double gamma, double dt, dou
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * lr_states_ppm.c:67-651 (THIRD_ORDER_CHAR, the reference's --with-order=3; HYDRO, ADIABATIC, CARTESIAN, CTU)
+ * ---------------------------------------------------------------------------------------------- */
+#define FOUR_3RDS 1.333333333333333          /* defs.h.in:159 (sic: 16 digits) */
+#define TWO_3RDS  0.6666666666666667         /* defs.h.in:158 */
+
+/* Steps 1-5 (== 8-12): eigensystem of cell i and its monotonised characteristic slopes, back in primitive variables */
+static void ppm_tvd_slope(const P1 W[], int i, int nscal, double Gamma, double ev[NWAVE],
+                          double rem[NWAVE][NWAVE], double lem[NWAVE][NWAVE], double dWm[NWAVE+1])
+{
+  const int NV = NWAVE + nscal;
+  const double *pWm = (const double*)&W[i-1], *pW0 = (const double*)&W[i], *pWp = (const double*)&W[i+1];
+  double dWc[NWAVE+1], dWl[NWAVE+1], dWr[NWAVE+1], dWg[NWAVE+1];
+  double dac[NWAVE+1], dal[NWAVE+1], dar[NWAVE+1], dag[NWAVE+1], da[NWAVE+1];
+  double lim_slope1, lim_slope2;
+  int n, m;
+  esys_prim_adb_hyd(W[i].d, W[i].Vx, Gamma*W[i].P, ev, rem, lem);
+  for (n=0; n<NV; n++) {                                                        /* :130-150 */
+    dWc[n] = pWp[n] - pWm[n];
+    dWl[n] = pW0[n] - pWm[n];
+    dWr[n] = pWp[n] - pW0[n];
+    if (dWl[n]*dWr[n] > 0.0) dWg[n] = 2.0*dWl[n]*dWr[n]/(dWl[n]+dWr[n]);
+    else dWg[n] = 0.0;
+  }
+  for (n=0; n<NWAVE; n++) {                                                     /* :156-167 */
+    dac[n] = lem[n][0]*dWc[0];
+    dal[n] = lem[n][0]*dWl[0];
+    dar[n] = lem[n][0]*dWr[0];
+    dag[n] = lem[n][0]*dWg[0];
+    for (m=1; m<NWAVE; m++) {
+      dac[n] += lem[n][m]*dWc[m];
+      dal[n] += lem[n][m]*dWl[m];
+      dar[n] += lem[n][m]*dWr[m];
+      dag[n] += lem[n][m]*dWg[m];
+    }
+  }
+  for (n=NWAVE; n<NV; n++) { dac[n] = dWc[n]; dal[n] = dWl[n]; dar[n] = dWr[n]; dag[n] = dWg[n]; }
+  for (n=0; n<NV; n++) {                                                        /* :184-191 */
+    da[n] = 0.0;
+    if (dal[n]*dar[n] > 0.0) {
+      lim_slope1 = MIN(    fabs(dal[n]),fabs(dar[n]));
+      lim_slope2 = MIN(0.5*fabs(dac[n]),fabs(dag[n]));
+      da[n] = SIGN(dac[n])*MIN(2.0*lim_slope1,lim_slope2);
+    }
+  }
+  for (n=0; n<NWAVE; n++) {                                                     /* :196-201 */
+    dWm[n] = da[0]*rem[n][0];
+    for (m=1; m<NWAVE; m++) dWm[n] += da[m]*rem[n][m];
+  }
+  for (n=NWAVE; n<NV; n++) dWm[n] = da[n];
+}
+
+static void lr_states_ppm(const P1 W[], int nscal, double Gamma, double dt, double dx, int il, int iu,
+                          P1 Wl[], P1 Wr[])
+{
+  const int NV = NWAVE + nscal;
+  const double dtodx = dt/dx;
+  double ev[NWAVE], rem[NWAVE][NWAVE], lem[NWAVE][NWAVE];
+  double ev_ip1[NWAVE], rem_ip1[NWAVE][NWAVE], lem_ip1[NWAVE][NWAVE];
+  double Wlv[NWAVE+1], Wrv[NWAVE+1], dW[NWAVE+1], W6[NWAVE+1];
+  /* The reference allocates both work arrays as nmax x NWAVE (lr_states_ppm.c:697-701) but indexes them up to
+   * NWAVE+NSCALARS: in the contiguous block of calloc_2d_array, entry [i][NWAVE] IS entry [i+1][0].  With a passive
+   * scalar its slope and face value therefore alias the next cell's density entries; the net effect per cell i is
+   *   Wlv[scalar] = density face value at i+1/2,   Wrv[scalar] = .5(s[i+1]+s[i]) - (ds(i+1) - dd(i+1))/6,
+   * which the monotonicity step mostly flattens to first order.  Reproduced by using the same flat NWAVE-stride layout. */
+  double *dWm_flat = calloc((size_t)(iu+5)*NWAVE, sizeof(double));
+  double *Wim1h_flat = calloc((size_t)(iu+5)*NWAVE, sizeof(double));
+#define dWm(i) (dWm_flat + (size_t)(i)*NWAVE)
+#define Wim1h(i) (Wim1h_flat + (size_t)(i)*NWAVE)
+  double qa, qb, qc, qx1, qx2;
+  double *pWl, *pWr;
+  int i, n, m;
+
+  for (n=0; n<NWAVE; n++) for (m=0; m<NWAVE; m++) { rem[n][m] = lem[n][m] = rem_ip1[n][m] = lem_ip1[n][m] = 0.0; }
+  for (i=il-2; i<=il-1; i++) ppm_tvd_slope(W, i, nscal, Gamma, ev, rem, lem, dWm(i));       /* :107-253 */
+  {                                                                                         /* :259-271 */
+    const double *p1 = (const double*)&W[il-1], *p2 = (const double*)&W[il-2];
+    for (n=0; n<NV; n++) Wim1h(il-1)[n] = .5*(p1[n]+p2[n]) - (dWm(il-1)[n]-dWm(il-2)[n])/6.;
+  }
+  for (i=il-1; i<=iu+1; i++) {
+    const double *pWm = (const double*)&W[i-1], *pW0 = (const double*)&W[i], *pWp = (const double*)&W[i+1];
+    ppm_tvd_slope(W, i+1, nscal, Gamma, ev_ip1, rem_ip1, lem_ip1, dWm(i+1));                /* :287-427 */
+    for (n=0; n<NV; n++) Wim1h(i+1)[n] = 0.5*(pWp[n]+pW0[n]) - (dWm(i+1)[n]-dWm(i)[n])/6.0; /* :434-446 */
+
+    for (n=0; n<NV; n++) { Wlv[n] = Wim1h(i)[n]; Wrv[n] = Wim1h(i+1)[n]; }                  /* :451-454 */
+    for (n=0; n<NV; n++) {                                                                  /* :465-477, gamma_curv = 0 */
+      qa = (Wrv[n]-pW0[n])*(pW0[n]-Wlv[n]);
+      qb = Wrv[n]-Wlv[n];
+      qc = 6.0*(pW0[n] - 0.5*(Wlv[n]*(1.0-0.0) + Wrv[n]*(1.0+0.0)));
+      if (qa <= 0.0) {
+        Wlv[n] = pW0[n];
+        Wrv[n] = pW0[n];
+      } else if ((qb*qc) > (qb*qb)) {
+        Wlv[n] = (6.0*pW0[n] - Wrv[n]*(4.0+3.0*0.0))/(2.0-3.0*0.0);
+      } else if ((qb*qc) < -(qb*qb)) {
+        Wrv[n] = (6.0*pW0[n] - Wlv[n]*(4.0-3.0*0.0))/(2.0+3.0*0.0);
+      }
+    }
+    for (n=0; n<NV; n++) {                                                                  /* :479-484 */
+      Wlv[n] = MAX(MIN(pW0[n],pWm[n]),Wlv[n]);
+      Wlv[n] = MIN(MAX(pW0[n],pWm[n]),Wlv[n]);
+      Wrv[n] = MAX(MIN(pW0[n],pWp[n]),Wrv[n]);
+      Wrv[n] = MIN(MAX(pW0[n],pWp[n]),Wrv[n]);
+    }
+    for (n=0; n<NV; n++) {                                                                  /* :489-492 */
+      dW[n] = Wrv[n] - Wlv[n];
+      W6[n] = 6.0*(pW0[n] - 0.5*(Wlv[n]*(1.0-0.0) + Wrv[n]*(1.0+0.0)));
+    }
+    pWl = (double*)&Wl[i+1];
+    pWr = (double*)&Wr[i];
+
+    if (orc_riemann == 1) {                                                                 /* :510-553 HLL-family form */
+      for (n=0; n<NWAVE; n++) { pWl[n] = Wrv[n]; pWr[n] = Wlv[n]; }
+      for (n=0; n<NWAVE; n++) {
+        qa = 0.0;
+        if (ev[n] > 0.0) {
+          qx1 = 0.5*dtodx*ev[n];
+          qb  = qx1;
+          qc  = FOUR_3RDS*SQR(qx1);
+          for (m=0; m<NWAVE; m++) qa += lem[n][m]*(qb*(dW[m]-W6[m]) + qc*W6[m]);
+          for (m=0; m<NWAVE; m++) pWl[m] -= qa*rem[m][n];
+        }
+        qa = 0.0;
+        if (ev[n] < 0.0) {
+          qx2 = 0.5*dtodx*ev[n];
+          qb  = qx2;
+          qc  = FOUR_3RDS*SQR(qx2);
+          for (m=0; m<NWAVE; m++) qa += lem[n][m]*(qb*(dW[m]+W6[m]) + qc*W6[m]);
+          for (m=0; m<NWAVE; m++) pWr[m] -= qa*rem[m][n];
+        }
+      }
+      Wl[i+1].r = 0.0; Wr[i].r = 0.0;            /* scalar never written by this branch, see lr_states() above */
+    } else {
+      qx1 = 0.5*MAX(ev[NWAVE-1],0.0)*dtodx;                                                 /* :557-577, qxx = 0 */
+      for (n=0; n<NV; n++)
+        pWl[n] = Wrv[n] - qx1*(dW[n] - (1.0-FOUR_3RDS*qx1)*W6[n]) + 0.0*(dW[n] - (1.0-2.0*qx1)*W6[n]);
+      qx2 = -0.5*MIN(ev[0],0.0)*dtodx;
+      for (n=0; n<NV; n++)
+        pWr[n] = Wlv[n] + qx2*(dW[n] + (1.0-FOUR_3RDS*qx2)*W6[n]) + 0.0*(dW[n] + (1.0-2.0*qx2)*W6[n]);
+
+      for (n=0; n<NWAVE; n++) {                                                             /* :586-606 */
+        if (ev[n] >= 0.0) {
+          qa  = 0.0;
+          qx1 = 0.5*dtodx*ev[NWAVE-1];
+          qx2 = 0.5*dtodx*ev[n];
+          qb  = qx1 - qx2;
+          qc  = FOUR_3RDS*(SQR(qx1) - SQR(qx2));
+          for (m=0; m<NWAVE; m++) qa += lem[n][m]*(qb*(dW[m]-W6[m]) + qc*W6[m]);
+          for (m=0; m<NWAVE; m++) pWl[m] += qa*rem[m][n];
+        }
+      }
+      for (n=0; n<NWAVE; n++) {                                                             /* :608-628 */
+        if (ev[n] <= 0.0) {
+          qa = 0.0;
+          qx1 = 0.5*dtodx*ev[0];
+          qx2 = 0.5*dtodx*ev[n];
+          qb  = qx1 - qx2;
+          qc  = FOUR_3RDS*(SQR(qx1) - SQR(qx2));
+          for (m=0; m<NWAVE; m++) qa += lem[n][m]*(qb*(dW[m]+W6[m]) + qc*W6[m]);
+          for (m=0; m<NWAVE; m++) pWr[m] += qa*rem[m][n];
+        }
+      }
+      for (n=NWAVE; n<NV; n++) {                                                            /* :631-641 (its dW[m], m == NWAVE, is dW[n]) */
+        if (W[i].Vx > 0.) {
+          qb = 0.5*dtodx*(ev[NWAVE-1]-W[i].Vx);
+          qc = 0.5*dtodx*dtodx*TWO_3RDS*(SQR(ev[NWAVE-1]) - SQR(W[i].Vx));
+          pWl[n] += qb*(dW[NWAVE]-W6[NWAVE]) + qc*W6[NWAVE];
+        } else if (W[i].Vx < 0.) {
+          qb = 0.5*dtodx*(ev[0]-W[i].Vx);
+          qc = 0.5*dtodx*dtodx*TWO_3RDS*(ev[0]*ev[0] - W[i].Vx*W[i].Vx);
+          pWr[n] += qb*(dW[NWAVE]+W6[NWAVE]) + qc*W6[NWAVE];
+        }
+      }
+      if (!nscal) { Wl[i+1].r = 0.0; Wr[i].r = 0.0; }
+    }
+    for (m=0; m<NWAVE; m++) {                                                               /* :648-654 */
+      ev[m] = ev_ip1[m];
+      for (n=0; n<NWAVE; n++) { rem[m][n] = rem_ip1[m][n]; lem[m][n] = lem_ip1[m][n]; }
+    }
+  }
+  free(dWm_flat); free(Wim1h_flat);
+#undef dWm
+#undef Wim1h
+}
+
+/* ------------------------------------------------------------------------------------------------
  * hlle.c:62-268 (HYDRO, ADIABATIC)
  * ---------------------------------------------------------------------------------------------- */
 static void flux_hlle(const C1 Ul, const C1 Ur, const P1 Wl, const P1 Wr, int nscal,
@@ -425,6 +620,7 @@ static void fluxes_hllc(const C1 Ul, const C1 Ur, const P1 Wl, const P1 Wr, int 
 }
 
 void orc_set_riemann_solver(int kind) { orc_riemann = kind; }
+void orc_set_reconstruction(int order) { orc_order = order; }
 
 static void fluxes_roe(const C1 Ul, const C1 Ur, const P1 Wl, const P1 Wr, int nscal,
                        double Gamma, double Gamma_1, double etah, C1 *pFlux);

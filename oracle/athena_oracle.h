@@ -91,6 +91,9 @@ void orc_bvals_ionrad(const OrcGrid *g, double flux_i, double *edgeflux);
 void orc_hllc_flux_batch(int n, const double *Ul, const double *Ur, const double *Wl, const double *Wr,
                          int nscal, double gamma, double *F);
 void orc_set_riemann_solver(int kind);
+/* lr_states(): 2 = reconstruction/lr_states_plm.c (default), 3 = reconstruction/lr_states_ppm.c:67-651 (--with-order=3).
+ * PPM reads W over [il-3, iu+3]. */
+void orc_set_reconstruction(int order);
 void orc_roe_flux_batch(int n, const double *Ul, const double *Ur, const double *Wl, const double *Wr,
                         int nscal, double gamma, const double *etah, double *F);
 void orc_prim_to_cons_batch(int n, const double *W, int nscal, double gamma, double *U);

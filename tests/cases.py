@@ -38,7 +38,8 @@ class Case:
         self.build = str(self.gold["build"])
         # 0 Roe + H-correction, 1 HLLC (reference --with-flux=hllc), 2 Roe built without --enable-h-correction
         self.riemann = 1 if self.build.endswith("_hllc") else (2 if self.build.endswith("_noh") else 0)
-        self.problem = self.build.replace("_hllc", "").replace("_noh", "")
+        self.order = 3 if "_ppm" in self.build else 2                    # lr_states_plm.c / lr_states_ppm.c (--with-order)
+        self.problem = self.build.replace("_hllc", "").replace("_noh", "").replace("_ppm", "")
         self.nx = tuple(p.par_geti("domain1", f"Nx{a}") for a in (1, 2, 3))
         self.xmin = tuple(p.par_getd("domain1", f"x{a}min") for a in (1, 2, 3))
         self.xmax = tuple(p.par_getd("domain1", f"x{a}max") for a in (1, 2, 3))

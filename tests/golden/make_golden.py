@@ -54,6 +54,13 @@ CASES = {
     # the reference configured --with-flux=hllc (no H-correction: etah is Roe-only)
     "blast16hllc": ("blast_hllc", "blast.athinput",
                     ["domain1/Nx1=16", "domain1/Nx2=16", "domain1/Nx3=16", "problem/radius=0.25"], [6]),
+    # --with-order=3 (PPM, characteristic variables)
+    "blast16ppm": ("blast_ppm", "blast.athinput",
+                   ["domain1/Nx1=16", "domain1/Nx2=16", "domain1/Nx3=16", "problem/radius=0.25"], [6]),
+    "ifront32ppm": ("ifront_ppm", "ifront.athinput",
+                    ["domain1/Nx1=32", "domain1/Nx2=16", "domain1/Nx3=16"], [4]),
+    "blast16ppmhllc": ("blast_ppm_hllc", "blast.athinput",
+                       ["domain1/Nx1=16", "domain1/Nx2=16", "domain1/Nx3=16", "problem/radius=0.25"], [6]),
     "blast16noh": ("blast_noh", "blast.athinput",
                    ["domain1/Nx1=16", "domain1/Nx2=16", "domain1/Nx3=16", "problem/radius=0.25"], [6]),
     "ifront32hllc": ("ifront_hllc", "ifront.athinput",
@@ -119,8 +126,11 @@ def make_units(seed=20261018):
     """Function-level vectors: reference lr_states()/fluxes()/Cons1D_to_Prim1D() on seeded random states."""
     dp = C.POINTER(C.c_double)
     P = lambda a: a.ctypes.data_as(dp)
-    for cfg, nscal in (("ifront", 1), ("blast", 0), ("ifront_hllc", 1), ("blast_hllc", 0)):
+    for cfg, nscal in (("ifront", 1), ("blast", 0), ("ifront_hllc", 1), ("blast_hllc", 0), ("ifront_ppm", 1), ("blast_ppm", 0),
+                       ("blast_ppm_hllc", 0)):
         hllc = cfg.endswith("_hllc")
+        tag = {"ifront": "", "blast": "", "ifront_hllc": "hllc_", "blast_hllc": "hllc_", "ifront_ppm": "ppm_", "blast_ppm": "ppm_",
+               "blast_ppm_hllc": "ppm_hllc_"}[cfg]
         ref = C.CDLL(os.path.join(REFDIR, cfg, "libref_units.so"))
         ref.ref_set_gamma.argtypes = [C.c_double]
         ref.ref_fluxes.argtypes = [dp, dp, dp, dp, C.c_double, dp]
@@ -157,7 +167,7 @@ def make_units(seed=20261018):
                 w[:] = w[0] + np.cumsum(0.02 * w, axis=0)
                 w[:, 0] = np.abs(w[:, 0]) + 0.1; w[:, 4] = np.abs(w[:, 4]) + 0.01
             ref.ref_lr_states(P(w), n, 0.01, 0.05, 3, n - 4, P(WL[t]), P(WR[t]))
-        path = os.path.join(HERE, f"units_{'hllc_' if hllc else ''}nscal{nscal}.npz")
+        path = os.path.join(HERE, f"units_{tag}nscal{nscal}.npz")
         np.savez_compressed(path, gamma=gam, nscal=nscal, Wl=Wl, Wr=Wr, Ul=Ul, Ur=Ur, eta=eta, F=F, W_of_Ul=Wb, cfast_Ul=cf,
                             pencil_W=W, pencil_Wl=WL, pencil_Wr=WR, pencil_dt=0.01, pencil_dx=0.05, pencil_il=3, pencil_iu=n - 4)
         print(path, os.path.getsize(path) // 1024, "KiB")
@@ -168,9 +178,9 @@ if __name__ == "__main__":
     br = importlib.util.module_from_spec(spec); spec.loader.exec_module(br)
     if os.path.isdir(os.path.join(br.REF, "src")):
         for c in ("ifront", "ioniz_sphere", "blast", "ifront_smr", "blast_smr", "ifront_smr_mpi", "blast_smr_mpi",
-                  "blast_hllc", "ifront_hllc", "blast_noh"):
+                  "blast_hllc", "ifront_hllc", "blast_noh", "blast_ppm", "ifront_ppm", "blast_ppm_hllc"):
             br.build(c)
-        for c in ("ifront", "blast", "ifront_hllc", "blast_hllc"):
+        for c in ("ifront", "blast", "ifront_hllc", "blast_hllc", "ifront_ppm", "blast_ppm", "blast_ppm_hllc"):
             br.build_units(c)
     only = sys.argv[1:]
     if only:

@@ -63,6 +63,7 @@ def lib():
         L.orc_roe_flux_batch.argtypes = [C.c_int, dp, dp, dp, dp, C.c_int, C.c_double, dp, dp]
         L.orc_hllc_flux_batch.argtypes = [C.c_int, dp, dp, dp, dp, C.c_int, C.c_double, dp]
         L.orc_set_riemann_solver.argtypes = [C.c_int]
+        L.orc_set_reconstruction.argtypes = [C.c_int]
         L.orc_prim_to_cons_batch.argtypes = [C.c_int, dp, C.c_int, C.c_double, dp]
         L.orc_cons_to_prim_batch.argtypes = [C.c_int, dp, C.c_int, C.c_double, dp]
         L.orc_ion_derived.argtypes = [C.POINTER(OrcIonPar), C.c_double, C.c_double, C.c_double]

@@ -64,12 +64,36 @@ def test_hllc_flux_bit_exact(nscal):
     assert not np.array_equal(roe["pencil_Wl"], g["pencil_Wl"])
 
 
+@pytest.mark.parametrize("tag,nscal,riemann", [("ppm_", 0, 0), ("ppm_", 1, 0), ("ppm_hllc_", 0, 1)])
+def test_ppm_lr_states_bit_exact(tag, nscal, riemann):
+    """reconstruction/lr_states_ppm.c (reference object built with THIRD_ORDER_CHAR) on the seeded pencils, in its CTU and
+    its HLL-family form"""
+    g = load_golden(f"units_{tag}nscal{nscal}")
+    L = ol.lib()
+    il, iu = int(g["pencil_il"]), int(g["pencil_iu"])
+    L.orc_set_reconstruction(3); L.orc_set_riemann_solver(riemann)
+    try:
+        for t in range(len(g["pencil_W"])):
+            Wp = np.ascontiguousarray(g["pencil_W"][t])
+            m = len(Wp)
+            Wl = np.zeros((m, 6)); Wr = np.zeros((m, 6))
+            L.orc_lr_states(ol.P(Wp), nscal, float(g["gamma"]), float(g["pencil_dt"]), float(g["pencil_dx"]), il, iu, ol.P(Wl), ol.P(Wr))
+            assert np.array_equal(Wl[il:iu + 2], g["pencil_Wl"][t][il:iu + 2])
+            assert np.array_equal(Wr[il - 1:iu + 1], g["pencil_Wr"][t][il - 1:iu + 1])
+    finally:
+        L.orc_set_reconstruction(2); L.orc_set_riemann_solver(0)
+    plm = load_golden(f"units_{'hllc_' if riemann else ''}nscal{nscal}")
+    assert np.array_equal(plm["pencil_W"], g["pencil_W"]) and not np.array_equal(plm["pencil_Wl"], g["pencil_Wl"])
+
+
 def oracle_run(case, log=None):
     ol.lib().orc_set_riemann_solver(case.riemann)
+    ol.lib().orc_set_reconstruction(case.order)
     try:
         return _oracle_run(case, log)
     finally:
         ol.lib().orc_set_riemann_solver(0)
+        ol.lib().orc_set_reconstruction(2)
 
 
 def _oracle_run(case, log=None):
@@ -95,7 +119,8 @@ def _oracle_run(case, log=None):
 
 
 @pytest.mark.parametrize("name", ["blast16_k1", "blast16_k6", "blastmix_k5", "ifront32_k1", "ifront32_k4",
-                                  "ioniz24_k1", "ioniz24_k3", "blast16hllc_k6", "ifront32hllc_k4", "blast16noh_k6"])
+                                  "ioniz24_k1", "ioniz24_k3", "blast16hllc_k6", "ifront32hllc_k4", "blast16noh_k6",
+                                  "blast16ppm_k6", "ifront32ppm_k4", "blast16ppmhllc_k6"])
 def test_run_matches_reference_dump(name):
     case = Case(name)
     log = {}
