@@ -133,6 +133,7 @@ ab2_grid* ab2_grid_create(const ab2_grid_desc* d)
   g.dx[0] = d->dx1; g.dx[1] = d->dx2; g.dx[2] = d->dx3;
   g.Gamma = d->gamma; g.Gamma_1 = d->gamma - 1.0;
   g.riemann = AB2_RIEMANN_ROE;
+  g.order = 2;
   h->xmin[0] = d->x1min; h->xmin[1] = d->x2min; h->xmin[2] = d->x3min;
   const size_t ncell = (size_t)g.n[0]*g.n[1]*g.n[2];
   const int nvar = 5 + d->nscal;
@@ -288,6 +289,16 @@ int ab2_set_riemann_solver(ab2_grid* h, int kind)
     return -1;
   }
   h->g.riemann = kind;
+  return 0;
+}
+
+int ab2_set_reconstruction(ab2_grid* h, int order)
+{
+  if (!h || (order != 2 && order != 3)) {
+    ab2_set_error("[ab2_set_reconstruction]: order must be 2 (PLM) or 3 (PPM), both in characteristic variables");
+    return -1;
+  }
+  h->g.order = order;
   return 0;
 }
 

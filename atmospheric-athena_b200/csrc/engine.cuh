@@ -36,6 +36,7 @@ struct GridDev {
   long st[3];                // element strides: st[0]=1, st[1]=n1, st[2]=n1*n2
   double dx[3];
   double Gamma, Gamma_1;
+  int order;                 // lr_states(): 2 = PLM (lr_states_plm.c), 3 = PPM (lr_states_ppm.c), the reference's --with-order
   int riemann;               // fluxes() of the build being replaced: 0 Roe + H-correction (roe.c), 1 HLLC (hllc.c), 2 Roe without H-correction
   double* U[AB2_NVAR];       // conserved state, SoA [n3][n2][n1]
   double* Ul[3][AB2_NVAR];   // face states, PHYSICAL component order (d,M1,M2,M3,E,s), one set per face direction

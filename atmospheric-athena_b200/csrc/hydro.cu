@@ -198,6 +198,74 @@ __device__ __forceinline__ bool box_cell(const Box& b, int& i, int& j, int& k)
   return true;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Pass A with PPM (reference built --with-order=3): three plain one-thread-per-cell kernels per sweep direction instead
+// of the fused PLM kernels.  The slopes of a direction live in that direction's flux arrays until the flux kernel
+// overwrites them; the face-state arrays carry PRIMITIVE states between the second and third kernel because the
+// reference hands the primitive L/R states themselves to fluxes() in this pass (integrate_3d_ctu.c:248-300).
+// ---------------------------------------------------------------------------------------------------
+template <int DIR, int NS>
+__global__ void __launch_bounds__(128) k_ppm_slope(GridDev g, Box b)
+{
+  int i,j,k; if (!box_cell(b,i,j,k)) return;
+  const long c = (long)k*g.st[2] + (long)j*g.st[1] + i;
+  const long sd = g.st[DIR];
+  const S6 Um = load_sweep<DIR,NS>(g.U, c-sd), U0 = load_sweep<DIR,NS>(g.U, c), Up = load_sweep<DIR,NS>(g.U, c+sd);
+  double dWm[6];
+  AB2_GUARDED(const S6 Wm = cons_to_prim<NS>(Um, g.Gamma_1, ar); const S6 W0 = cons_to_prim<NS>(U0, g.Gamma_1, ar);
+              const S6 Wp = cons_to_prim<NS>(Up, g.Gamma_1, ar);
+              const PrimEig e = prim_eig(W0, g.Gamma, ar);
+              ppm_slope<NS>(Wm, W0, Wp, e, dWm, ar));
+  S6 d; d.d = dWm[0]; d.x = dWm[1]; d.y = dWm[2]; d.z = dWm[3]; d.e = dWm[4]; d.s = dWm[5];
+  store_sweep<DIR,NS>(g.F[DIR], c, d);
+}
+
+template <int DIR, int NS, bool GRAV>
+__global__ void __launch_bounds__(128) k_ppm_states(GridDev g, Box b, double dt)
+{
+  int i,j,k; if (!box_cell(b,i,j,k)) return;
+  const long c = (long)k*g.st[2] + (long)j*g.st[1] + i;
+  const long sd = g.st[DIR];
+  const double dtodx = dt/g.dx[DIR];
+  const S6 Um = load_sweep<DIR,NS>(g.U, c-sd), U0 = load_sweep<DIR,NS>(g.U, c), Up = load_sweep<DIR,NS>(g.U, c+sd);
+  const S6 dm = load_sweep<DIR,NS>(g.F[DIR], c-sd), d0 = load_sweep<DIR,NS>(g.F[DIR], c), dp = load_sweep<DIR,NS>(g.F[DIR], c+sd);
+  S6 Wl_next, Wr_this;
+  AB2_GUARDED(
+    const S6 Wm = cons_to_prim<NS>(Um, g.Gamma_1, ar); const S6 W0 = cons_to_prim<NS>(U0, g.Gamma_1, ar);
+    const S6 Wp = cons_to_prim<NS>(Up, g.Gamma_1, ar);
+    const PrimEig e = prim_eig(W0, g.Gamma, ar);
+    double Fl[6]; double Fr[6];
+    Fl[0] = ppm_face(W0.d, Wm.d, d0.d, dm.d, ar); Fr[0] = ppm_face(Wp.d, W0.d, dp.d, d0.d, ar);
+    Fl[1] = ppm_face(W0.x, Wm.x, d0.x, dm.x, ar); Fr[1] = ppm_face(Wp.x, W0.x, dp.x, d0.x, ar);
+    Fl[2] = ppm_face(W0.y, Wm.y, d0.y, dm.y, ar); Fr[2] = ppm_face(Wp.y, W0.y, dp.y, d0.y, ar);
+    Fl[3] = ppm_face(W0.z, Wm.z, d0.z, dm.z, ar); Fr[3] = ppm_face(Wp.z, W0.z, dp.z, d0.z, ar);
+    Fl[4] = ppm_face(W0.e, Wm.e, d0.e, dm.e, ar); Fr[4] = ppm_face(Wp.e, W0.e, dp.e, d0.e, ar);
+    // the scalar entries as the reference's aliased work arrays hold them (physics.cuh, "PPM")
+    Fl[5] = NS ? Fr[0] : 0.0;
+    Fr[5] = NS ? ppm_face(Wp.s, W0.s, dp.s, dp.d, ar) : 0.0;
+    ppm_cell<NS>(Wm, W0, Wp, Fl, Fr, e, dtodx, Wl_next, Wr_this, RIEMANN_OF(g) == AB2_RIEMANN_HLLC));
+  if (GRAV) {   // integrate_3d_ctu.c:318-342, 635-645, 819-829
+    Wl_next.x -= dtodx*(g.phi[PHI_MH0+DIR][c+sd] - g.phi[PHI_M0+DIR][c+sd]);
+    Wr_this.x -= dtodx*(g.phi[PHI_C][c] - g.phi[PHI_MH0+DIR][c]);
+  }
+  store_sweep<DIR,NS>(g.Ul[DIR], c+sd, Wl_next);      // primitive for now; k_ppm_flux converts in place
+  store_sweep<DIR,NS>(g.Ur[DIR], c, Wr_this);
+}
+
+template <int DIR, int NS>
+__global__ void __launch_bounds__(128, AB2_LB_FINAL) k_ppm_flux(GridDev g, Box b)
+{
+  int i,j,k; if (!box_cell(b,i,j,k)) return;
+  const long c = (long)k*g.st[2] + (long)j*g.st[1] + i;
+  const S6 Wl = load_sweep<DIR,NS>(g.Ul[DIR], c), Wr = load_sweep<DIR,NS>(g.Ur[DIR], c);
+  S6 Ul, Ur, F;
+  AB2_GUARDED(Ul = prim_to_cons<NS>(Wl, g.Gamma_1, ar); Ur = prim_to_cons<NS>(Wr, g.Gamma_1, ar);
+              riemann_flux<NS>(RIEMANN_OF(g), Ul, Ur, Wl, Wr, 0.0, g.Gamma, g.Gamma_1, F, ar));
+  store_sweep<DIR,NS>(g.Ul[DIR], c, Ul);
+  store_sweep<DIR,NS>(g.Ur[DIR], c, Ur);
+  store_sweep<DIR,NS>(g.F[DIR], c, F);
+}
+
 // Pass B: integrate_3d_ctu.c:2104-2125 (active zones are all the update needs)
 __global__ void k_dhalf(GridDev g, Box b, double dt)
 {
@@ -484,7 +552,29 @@ static int integrate_impl(ab2_grid* h, double dt)
   auto seg_for = [](int nf) { const int ns = (nf + 31)/32; return (nf + ns-1)/ns; };
 
   // Pass A
-  {
+  if (g.order == 3) {
+    for (int d=0; d<3; d++) {
+      Box bs, bc, bf;      // slopes on [l-1,u+1], states from cells [l,u], faces [l+1,u] along d; [l,u] transversally
+      for (int a=0; a<3; a++) {
+        bs.lo[a] = (a == d) ? l[a]-1 : l[a]; bs.hi[a] = (a == d) ? u[a]+1 : u[a];
+        bc.lo[a] = l[a];                     bc.hi[a] = u[a];
+        bf.lo[a] = (a == d) ? l[a]+1 : l[a]; bf.hi[a] = u[a];
+      }
+      if (d == 0) {
+        AB2_LAUNCH(h, KID_FIRST_X1, (k_ppm_slope<0,NS><<<box_grid(bs,128), 128, 0, st>>>(g, bs)));
+        AB2_LAUNCH(h, KID_FIRST_X1, (k_ppm_states<0,NS,GRAV><<<box_grid(bc,128), 128, 0, st>>>(g, bc, dt)));
+        AB2_LAUNCH(h, KID_FIRST_X1, (k_ppm_flux<0,NS><<<box_grid(bf,128), 128, 0, st>>>(g, bf)));
+      } else if (d == 1) {
+        AB2_LAUNCH(h, KID_FIRST_X2, (k_ppm_slope<1,NS><<<box_grid(bs,128), 128, 0, st>>>(g, bs)));
+        AB2_LAUNCH(h, KID_FIRST_X2, (k_ppm_states<1,NS,GRAV><<<box_grid(bc,128), 128, 0, st>>>(g, bc, dt)));
+        AB2_LAUNCH(h, KID_FIRST_X2, (k_ppm_flux<1,NS><<<box_grid(bf,128), 128, 0, st>>>(g, bf)));
+      } else {
+        AB2_LAUNCH(h, KID_FIRST_X3, (k_ppm_slope<2,NS><<<box_grid(bs,128), 128, 0, st>>>(g, bs)));
+        AB2_LAUNCH(h, KID_FIRST_X3, (k_ppm_states<2,NS,GRAV><<<box_grid(bc,128), 128, 0, st>>>(g, bc, dt)));
+        AB2_LAUNCH(h, KID_FIRST_X3, (k_ppm_flux<2,NS><<<box_grid(bf,128), 128, 0, st>>>(g, bf)));
+      }
+    }
+  } else {
     const int nf = g.nx[0]+4;
     int bestT = 128; double bestw = 1e30;
     for (int T : {64, 96, 128, 160, 192, 256}) {          // least padded tile width

@@ -59,6 +59,33 @@ template <int NS> __global__ void k_unit_plm(int npen, int n, const double* W, d
   st6(Wr + ((size_t)pen*n + i)*6, wr);
 }
 
+// PPM: one thread per (pencil, cell i in [il-1, iu+1]); slopes of i-1, i, i+1 are recomputed per thread
+template <int NS> __global__ void k_unit_ppm(int npen, int n, const double* W, double Gamma, double dtodx, int il, int iu, double* Wl, double* Wr, bool hll)
+{
+  const int t = blockIdx.x*blockDim.x + threadIdx.x;
+  const int ncell = iu - il + 3;
+  if (t >= npen*ncell) return;
+  const int pen = t / ncell, i = il - 1 + t % ncell;
+  const double* w = W + (size_t)pen*n*6;
+  S6 wl, wr;
+  const S6 wmm = ld6(w+6*(i-2)), wm = ld6(w+6*(i-1)), w0 = ld6(w+6*i), wp = ld6(w+6*(i+1)), wpp = ld6(w+6*(i+2));
+  AB2_GUARDED(
+    double dm[6]; double d0[6]; double dp[6];
+    const PrimEig em = prim_eig(wm, Gamma, ar); const PrimEig e0 = prim_eig(w0, Gamma, ar); const PrimEig ep = prim_eig(wp, Gamma, ar);
+    ppm_slope<NS>(wmm, wm, w0, em, dm, ar); ppm_slope<NS>(wm, w0, wp, e0, d0, ar); ppm_slope<NS>(w0, wp, wpp, ep, dp, ar);
+    double Fl[6]; double Fr[6];
+    Fl[0] = ppm_face(w0.d, wm.d, d0[0], dm[0], ar); Fr[0] = ppm_face(wp.d, w0.d, dp[0], d0[0], ar);
+    Fl[1] = ppm_face(w0.x, wm.x, d0[1], dm[1], ar); Fr[1] = ppm_face(wp.x, w0.x, dp[1], d0[1], ar);
+    Fl[2] = ppm_face(w0.y, wm.y, d0[2], dm[2], ar); Fr[2] = ppm_face(wp.y, w0.y, dp[2], d0[2], ar);
+    Fl[3] = ppm_face(w0.z, wm.z, d0[3], dm[3], ar); Fr[3] = ppm_face(wp.z, w0.z, dp[3], d0[3], ar);
+    Fl[4] = ppm_face(w0.e, wm.e, d0[4], dm[4], ar); Fr[4] = ppm_face(wp.e, w0.e, dp[4], d0[4], ar);
+    Fl[5] = NS ? Fr[0] : 0.0;
+    Fr[5] = NS ? ppm_face(wp.s, w0.s, dp[5], dp[0], ar) : 0.0;
+    ppm_cell<NS>(wm, w0, wp, Fl, Fr, e0, dtodx, wl, wr, hll));
+  st6(Wl + ((size_t)pen*n + i+1)*6, wl);
+  st6(Wr + ((size_t)pen*n + i)*6, wr);
+}
+
 // raw check of Arith<true>: out[0..n) = fast a/b (or NaN-tagged when the range test rejects), out2 = a/b; same for sqrt
 __global__ void k_unit_ieee(int n, const double* a, const double* b, double* qf, double* qe, double* sf, double* se, int* nbad)
 {
@@ -147,6 +174,20 @@ int ab2_unit_lr_states(int npencil, int n, const double* W, int nscal, double ga
 int ab2_unit_lr_states_hll(int npencil, int n, const double* W, int nscal, double gamma, double dt, double dx,
                            int il, int iu, double* Wl, double* Wr)
 { return unit_lr_states(npencil, n, W, nscal, gamma, dt, dx, il, iu, Wl, Wr, true); }
+
+int ab2_unit_lr_states_ppm(int npencil, int n, const double* W, int nscal, double gamma, double dt, double dx,
+                           int il, int iu, int hll, double* Wl, double* Wr)
+{
+  const size_t tot = (size_t)npencil*n*6;
+  DevBuf w(tot,W), l(tot), r(tot);
+  if (!w.p || !l.p || !r.p) { ab2_set_error("[ab2_unit_lr_states_ppm]: cudaMalloc failed"); return -1; }
+  const int nt = npencil*(iu-il+3);
+  if (nscal) k_unit_ppm<1><<<(nt+127)/128,128>>>(npencil,n,w.p,gamma,dt/dx,il,iu,l.p,r.p,hll != 0);
+  else k_unit_ppm<0><<<(nt+127)/128,128>>>(npencil,n,w.p,gamma,dt/dx,il,iu,l.p,r.p,hll != 0);
+  if (!ab2_check(cudaMemcpy(Wl, l.p, tot*sizeof(double), cudaMemcpyDeviceToHost), "unit ppm")) return -1;
+  if (!ab2_check(cudaMemcpy(Wr, r.p, tot*sizeof(double), cudaMemcpyDeviceToHost), "unit ppm")) return -1;
+  return 0;
+}
 
 int ab2_unit_hllc_flux(int n, const double* Ul, const double* Ur, const double* Wl, const double* Wr,
                        int nscal, double gamma, double* F)

@@ -66,7 +66,7 @@ class Run:
     """MeshS + one DomainS + this rank's GridS, driven like main.c."""
 
     def __init__(self, par, problem: str, device: int = 0, dist=None, U0: dict | None = None, torch_memory: bool | None = None,
-                 riemann: int = 0):
+                 riemann: int = 0, order: int = 2):
         self.par = par
         self.problem = problem
         self.dist = dist
@@ -99,6 +99,8 @@ class Run:
                              torch_memory=(self.world > 1) if torch_memory is None else torch_memory)
         if riemann:
             self.G.set_riemann_solver(riemann)       # the reference's --with-flux=hllc build
+        if order != 2:
+            self.G.set_reconstruction(order)         # --with-order=3
         self.time, self.dt, self.nstep = 0.0, 0.0, 0
         self.flux_i = p.par_getd("problem", "flux") if self.ion else 0.0
         self.rad_log = []

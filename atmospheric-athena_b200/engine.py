@@ -70,7 +70,8 @@ EXPORTS = ["ab2_last_error", "ab2_version", "ab2_device_count", "ab2_grid_create
            "ab2_profile_enable", "ab2_profile_kernels", "ab2_profile_kernel_name", "ab2_profile_read",
            "ab2_smr_restrict_correct", "ab2_smr_ion_restrict", "ab2_smr_prolongate", "ab2_smr_ion_prolong",
            "ab2_ion_radtransfer_3d_fine", "ab2_ion_coarse_time",
-           "ab2_set_riemann_solver", "ab2_unit_hllc_flux", "ab2_unit_lr_states_hll"]
+           "ab2_set_riemann_solver", "ab2_unit_hllc_flux", "ab2_unit_lr_states_hll",
+           "ab2_set_reconstruction", "ab2_unit_lr_states_ppm"]
 
 
 def build(verbose=False):
@@ -148,6 +149,8 @@ def lib():
     L.ab2_unit_lr_states_hll.argtypes = L.ab2_unit_lr_states.argtypes
     L.ab2_unit_hllc_flux.argtypes = [C.c_int, dp, dp, dp, dp, C.c_int, C.c_double, dp]
     L.ab2_set_riemann_solver.argtypes = [vp, C.c_int]
+    L.ab2_set_reconstruction.argtypes = [vp, C.c_int]
+    L.ab2_unit_lr_states_ppm.argtypes = [C.c_int, C.c_int, dp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, dp, dp]
     _lib = L
     return L
 
@@ -297,6 +300,10 @@ class Grid:
     def set_riemann_solver(self, kind):
         """0 = Roe + H-correction (rsolvers/roe.c, default), 1 = HLLC (rsolvers/hllc.c): the reference's --with-flux"""
         self._ck(lib().ab2_set_riemann_solver(self.h, int(kind)))
+
+    def set_reconstruction(self, order):
+        """2 = PLM (lr_states_plm.c, default), 3 = PPM (lr_states_ppm.c): the reference's --with-order"""
+        self._ck(lib().ab2_set_reconstruction(self.h, int(order)))
 
     def integrate_3d_ctu(self, dt):
         self._ck(lib().ab2_integrate_3d_ctu(self.h, dt))

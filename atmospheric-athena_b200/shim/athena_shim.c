@@ -71,6 +71,11 @@ static Mirror *mirror_of(GridS *pG)
     mir[nmir].pG = pG;
     mir[nmir].h = ab2_grid_create(&d);
     if (mir[nmir].h == NULL) die("ab2_grid_create");
+#if defined(THIRD_ORDER_CHAR)    /* --with-order=3: reconstruction/lr_states_ppm.c */
+    if (ab2_set_reconstruction(mir[nmir].h, 3) != 0) die("ab2_set_reconstruction");
+#elif !defined(SECOND_ORDER_CHAR)
+#error "libathena_b200 replaces the characteristic PLM and PPM reconstructions only (--with-order=2 or 3)"
+#endif
 #if defined(HLLC_FLUX)           /* the driver was configured --with-flux=hllc: rsolvers/hllc.c + lr_states_plm.c:257 */
     if (ab2_set_riemann_solver(mir[nmir].h, 1) != 0) die("ab2_set_riemann_solver");
 #elif !defined(ROE_FLUX)

@@ -266,7 +266,7 @@ def gpu_arm(args):
     par = make_par(args.workload, n, nx3_global)
     prob = WORKLOADS[args.workload][1]
     t_setup = time.time()
-    R = Run(par, prob, device=local, dist=d, torch_memory=True)
+    R = Run(par, prob, device=local, dist=d, torch_memory=True, riemann=args.riemann, order=args.order)
     t_setup = time.time() - t_setup
     G = R.G
     zones_local = R.zones
@@ -380,6 +380,7 @@ def gpu_arm(args):
             "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{WORKLOADS[args.workload][2]} {n}x{n}x{nx3_global}, steps {args.warmup}..{args.warmup + args.steps} from t=0",
                        "zones_per_gpu": zones_local, "parallelism": f"x3-slabs x{world}",
+                       "variant": {"order": args.order, "riemann": args.riemann},
                        "ion_iterations_per_step": round(n_iter, 2), "l2": "working set >> L2 (state + scratch = "
                        f"{G.bytes_allocated / 2**30:.1f} GiB per GPU), no flush needed", "setup_s": round(t_setup, 1)},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "dropin": dropin, "kernels": ktab,
@@ -476,6 +477,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="ioniz_sphere", choices=sorted(WORKLOADS) + ["ioniz_smr"])
     ap.add_argument("--n", "--size", dest="n", type=int, default=256, help="zones per direction per GPU (use --size under torchrun, whose own parser trips over --n)")
+    ap.add_argument("--order", type=int, default=2, choices=[2, 3], help="reconstruction: 2 PLM (the shipped configuration), 3 PPM")
+    ap.add_argument("--riemann", type=int, default=0, choices=[0, 1, 2], help="0 Roe + H-correction (shipped), 1 HLLC, 2 Roe without H-correction")
     ap.add_argument("--strong", action="store_true", help="--n is the GLOBAL cube size, cut into --gpus x3 slabs (strong scaling)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-n", type=int, default=64, help="grid of the bounded CPU sample")

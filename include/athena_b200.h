@@ -107,6 +107,9 @@ int ab2_integrate_3d_ctu(ab2_grid* g, double dt);
  * WITHOUT --enable-h-correction (integrate_3d_ctu.c:2299-2426 compiled out, etah stays 0: the configuration of the
  * reference's linear-wave convergence deck).  Returns -1 for an unknown kind. */
 int ab2_set_riemann_solver(ab2_grid* g, int kind);
+/* The reference's --with-order (defs.h ACCURACY): 2 = SECOND_ORDER_CHAR, reconstruction/lr_states_plm.c (default);
+ * 3 = THIRD_ORDER_CHAR, reconstruction/lr_states_ppm.c:67-651 (PPM in characteristic variables). */
+int ab2_set_reconstruction(ab2_grid* g, int order);
 /* Userwork_in_loop replay: a static list of cells (flat indices incl. ghosts) reset to fixed values
  * vals[6][n] every step, e.g. prob/ioniz_sphere.c:255-306. */
 int ab2_set_fixed_cells(ab2_grid* g, long n, const long* cells, const double* vals);
@@ -177,6 +180,9 @@ int ab2_unit_lr_states(int npencil, int n, const double* W, int nscal, double ga
 /* the same with steps 8-9 in the form an HLLE/HLLC/HLLD build compiles (lr_states_plm.c:257-293) */
 int ab2_unit_lr_states_hll(int npencil, int n, const double* W, int nscal, double gamma, double dt, double dx,
                            int il, int iu, double* Wl, double* Wr);
+/* lr_states() of reconstruction/lr_states_ppm.c:67-651; hll != 0: steps 18-19 in the form an HLL-family build compiles */
+int ab2_unit_lr_states_ppm(int npencil, int n, const double* W, int nscal, double gamma, double dt, double dx,
+                           int il, int iu, int hll, double* Wl, double* Wr);
 /* fluxes() of rsolvers/hllc.c:50-261 on n independent interfaces */
 int ab2_unit_hllc_flux(int n, const double* Ul, const double* Ur, const double* Wl, const double* Wr,
                        int nscal, double gamma, double* F);

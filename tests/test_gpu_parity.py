@@ -103,7 +103,7 @@ def test_glibc_math_matches_host_libm_bit_for_bit():
 
 def gpu_run(case):
     from athena_b200.driver import Run
-    R = Run(case.par, case.problem, device=0, U0=case.U0, riemann=case.riemann)
+    R = Run(case.par, case.problem, device=0, U0=case.U0, riemann=case.riemann, order=case.order)
     assert R.dt == float(case.gold["dt0"]), "first new_dt must be bit-identical (max is order independent)"
     R.run(case.nsteps)
     return R
@@ -134,7 +134,23 @@ def test_hllc_units_bit_exact(nscal):
     assert np.array_equal(Wr[:, il - 1:iu + 1], g["pencil_Wr"][:, il - 1:iu + 1])
 
 
-@pytest.mark.parametrize("name", ["blast16_k1", "blast16_k6", "blastmix_k5", "blast16hllc_k6", "blast16noh_k6"])
+@pytest.mark.parametrize("tag,nscal,hll", [("ppm_", 0, 0), ("ppm_", 1, 0), ("ppm_hllc_", 0, 1)])
+def test_ppm_units_bit_exact(tag, nscal, hll):
+    """reconstruction/lr_states_ppm.c (the reference's object built with THIRD_ORDER_CHAR) on the seeded pencils, incl. the
+    passive scalar as the reference's aliased work arrays treat it, and the HLL-family form of the tracing"""
+    g = load_golden(f"units_{tag}nscal{nscal}")
+    L = engine().lib()
+    il, iu = int(g["pencil_il"]), int(g["pencil_iu"])
+    Wp = np.ascontiguousarray(g["pencil_W"])
+    npen, m = Wp.shape[:2]
+    Wl = np.zeros_like(Wp); Wr = np.zeros_like(Wp)
+    assert L.ab2_unit_lr_states_ppm(npen, m, P(Wp), nscal, float(g["gamma"]), float(g["pencil_dt"]), float(g["pencil_dx"]), il, iu, hll, P(Wl), P(Wr)) == 0
+    assert np.array_equal(Wl[:, il:iu + 2], g["pencil_Wl"][:, il:iu + 2])
+    assert np.array_equal(Wr[:, il - 1:iu + 1], g["pencil_Wr"][:, il - 1:iu + 1])
+
+
+@pytest.mark.parametrize("name", ["blast16_k1", "blast16_k6", "blastmix_k5", "blast16hllc_k6", "blast16noh_k6", "blast16ppm_k6",
+                                  "blast16ppmhllc_k6"])
 def test_hydro_bit_exact_vs_reference(name):
     case = Case(name)
     R = gpu_run(case)
@@ -145,7 +161,7 @@ def test_hydro_bit_exact_vs_reference(name):
         assert np.array_equal(out[v], case.U1[v]), f"{name}:{v} max abs diff {np.abs(out[v]-case.U1[v]).max()}"
 
 
-@pytest.mark.parametrize("name", ["ifront32_k1", "ifront32_k4", "ioniz24_k1", "ioniz24_k3", "ifront32hllc_k4"])
+@pytest.mark.parametrize("name", ["ifront32_k1", "ifront32_k4", "ioniz24_k1", "ioniz24_k3", "ifront32hllc_k4", "ifront32ppm_k4"])
 def test_ion_hydro_bit_exact_vs_reference(name):
     """stricter than north_star asks: with the host libm's exp/pow restated on the device (csrc/glibc_math.cuh) the
     hydro + ion-RT step reproduces the reference's dump to the last bit, EdgeFlux and sub-cycle counts included"""
