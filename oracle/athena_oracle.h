@@ -8,7 +8,10 @@
  * written by the reference's own serial build (oracle/_ref, built by oracle/build_ref.py from the
  * sources where they lie under /root/reference) -- committed as tests/golden/ *.npz together with the
  * generating script tests/golden/make_golden.py -- and against function-level vectors produced by the
- * reference's own lr_states()/fluxes() objects (tests/golden/units_*.npz).
+ * reference's own lr_states()/fluxes() objects (tests/golden/units_*.npz).  Also pinned the same way: the SMR
+ * functions on 2- and 3-level nests (the 3-level dumps come from the reference's MPI branch run as one rank against
+ * oracle/mpi_stub -- its serial build segfaults there), the HLLC solver with the HLL-family PLM tracing, Roe without
+ * H-correction, and PPM (lr_states_ppm.c) including the reference's work-array aliasing for the passive scalar.
  *
  * Data layout: SoA.  One double array per conserved variable, extents [n3][n2][n1] INCLUDING ghost
  * zones (n = Nx + 2*4 in every direction), i fastest.  Variable order: d, M1, M2, M3, E, s0.
