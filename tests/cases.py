@@ -23,6 +23,15 @@ def load_golden(name):
     return np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
 
 
+def load_units(tag, nscal):
+    """Function-level vectors of a reference build: the seeded inputs live in units_nscal<N>.npz, a variant build's file
+    (tag "hllc_", "ppm_", "ppm_hllc_") holds only the outputs that differ (F, pencil_Wl, pencil_Wr)."""
+    g = dict(load_golden(f"units_nscal{nscal}"))
+    if tag:
+        g.update(dict(load_golden(f"units_{tag}nscal{nscal}")))
+    return g
+
+
 def par_for(gold):
     par = ParFile.par_open(os.path.join(DECKS, str(gold["deck"])))
     par.par_cmdline([str(x) for x in gold["overrides"]])

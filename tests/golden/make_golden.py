@@ -168,8 +168,11 @@ def make_units(seed=20261018):
                 w[:, 0] = np.abs(w[:, 0]) + 0.1; w[:, 4] = np.abs(w[:, 4]) + 0.01
             ref.ref_lr_states(P(w), n, 0.01, 0.05, 3, n - 4, P(WL[t]), P(WR[t]))
         path = os.path.join(HERE, f"units_{tag}nscal{nscal}.npz")
-        np.savez_compressed(path, gamma=gam, nscal=nscal, Wl=Wl, Wr=Wr, Ul=Ul, Ur=Ur, eta=eta, F=F, W_of_Ul=Wb, cfast_Ul=cf,
-                            pencil_W=W, pencil_Wl=WL, pencil_Wr=WR, pencil_dt=0.01, pencil_dx=0.05, pencil_il=3, pencil_iu=n - 4)
+        if tag:         # a variant build sees the same seeded inputs: keep only what it computes differently (cases.load_units merges)
+            np.savez_compressed(path, F=F, pencil_Wl=WL, pencil_Wr=WR)
+        else:
+            np.savez_compressed(path, gamma=gam, nscal=nscal, Wl=Wl, Wr=Wr, Ul=Ul, Ur=Ur, eta=eta, F=F, W_of_Ul=Wb, cfast_Ul=cf,
+                                pencil_W=W, pencil_Wl=WL, pencil_Wr=WR, pencil_dt=0.01, pencil_dx=0.05, pencil_il=3, pencil_iu=n - 4)
         print(path, os.path.getsize(path) // 1024, "KiB")
 
 

@@ -8,7 +8,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from cases import Case, load_golden, VARS
+from cases import Case, load_golden, load_units, VARS
 
 pytestmark = pytest.mark.gpu
 
@@ -117,7 +117,7 @@ def rel_err(a, b):
 @pytest.mark.parametrize("nscal", [0, 1])
 def test_hllc_units_bit_exact(nscal):
     """rsolvers/hllc.c fluxes() and the HLL-family form of PLM steps 8-9, against the reference's own objects"""
-    g = load_golden(f"units_hllc_nscal{nscal}")
+    g = load_units("hllc_", nscal)
     L = engine().lib()
     gam = float(g["gamma"])
     n = len(g["Wl"])
@@ -138,7 +138,7 @@ def test_hllc_units_bit_exact(nscal):
 def test_ppm_units_bit_exact(tag, nscal, hll):
     """reconstruction/lr_states_ppm.c (the reference's object built with THIRD_ORDER_CHAR) on the seeded pencils, incl. the
     passive scalar as the reference's aliased work arrays treat it, and the HLL-family form of the tracing"""
-    g = load_golden(f"units_{tag}nscal{nscal}")
+    g = load_units(tag, nscal)
     L = engine().lib()
     il, iu = int(g["pencil_il"]), int(g["pencil_iu"])
     Wp = np.ascontiguousarray(g["pencil_W"])
