@@ -40,6 +40,11 @@ CASES = {
                   "domain1/x2min=-0.3", "domain1/x2max=0.3", "domain1/x3min=-0.4", "domain1/x3max=0.4",
                   "domain1/bc_ix1=1", "domain1/bc_ox1=2", "domain1/bc_ix2=2", "domain1/bc_ox2=1",
                   "domain1/bc_ix3=1", "domain1/bc_ox3=2"], [5]),
+    # smallest Grids the 3D CTU path accepts (4 zones = one ghost width per direction), all three extents different
+    "blasttiny": ("blast", "blast.athinput",
+                  ["domain1/Nx1=8", "domain1/Nx2=4", "domain1/Nx3=6", "problem/radius=0.3"], [5]),
+    "ifronttiny": ("ifront", "ifront.athinput",
+                   ["domain1/Nx1=5", "domain1/Nx2=4", "domain1/Nx3=7"], [3]),
     "ifront32": ("ifront", "ifront.athinput",
                  ["domain1/Nx1=32", "domain1/Nx2=16", "domain1/Nx3=16"], [1, 4]),
     "ioniz24": ("ioniz_sphere", "ioniz_sphere.athinput",

@@ -150,7 +150,7 @@ def test_ppm_units_bit_exact(tag, nscal, hll):
 
 
 @pytest.mark.parametrize("name", ["blast16_k1", "blast16_k6", "blastmix_k5", "blast16hllc_k6", "blast16noh_k6", "blast16ppm_k6",
-                                  "blast16ppmhllc_k6"])
+                                  "blast16ppmhllc_k6", "blasttiny_k5"])
 def test_hydro_bit_exact_vs_reference(name):
     case = Case(name)
     R = gpu_run(case)
@@ -161,7 +161,8 @@ def test_hydro_bit_exact_vs_reference(name):
         assert np.array_equal(out[v], case.U1[v]), f"{name}:{v} max abs diff {np.abs(out[v]-case.U1[v]).max()}"
 
 
-@pytest.mark.parametrize("name", ["ifront32_k1", "ifront32_k4", "ioniz24_k1", "ioniz24_k3", "ifront32hllc_k4", "ifront32ppm_k4"])
+@pytest.mark.parametrize("name", ["ifront32_k1", "ifront32_k4", "ioniz24_k1", "ioniz24_k3", "ifront32hllc_k4", "ifront32ppm_k4",
+                                  "ifronttiny_k3"])
 def test_ion_hydro_bit_exact_vs_reference(name):
     """stricter than north_star asks: with the host libm's exp/pow restated on the device (csrc/glibc_math.cuh) the
     hydro + ion-RT step reproduces the reference's dump to the last bit, EdgeFlux and sub-cycle counts included"""
