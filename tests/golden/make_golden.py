@@ -45,6 +45,9 @@ CASES = {
                   ["domain1/Nx1=8", "domain1/Nx2=4", "domain1/Nx3=6", "problem/radius=0.3"], [5]),
     "ifronttiny": ("ifront", "ifront.athinput",
                    ["domain1/Nx1=5", "domain1/Nx2=4", "domain1/Nx3=7"], [3]),
+    # static potential + Userwork reset on a Grid with three different, partly odd extents (the potential tables cannot all alias)
+    "ionizodd": ("ioniz_sphere", "ioniz_sphere.athinput",
+                 ["domain1/Nx1=21", "domain1/Nx2=18", "domain1/Nx3=15"], [1]),
     "ifront32": ("ifront", "ifront.athinput",
                  ["domain1/Nx1=32", "domain1/Nx2=16", "domain1/Nx3=16"], [1, 4]),
     "ioniz24": ("ioniz_sphere", "ioniz_sphere.athinput",

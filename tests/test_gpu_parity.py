@@ -162,7 +162,7 @@ def test_hydro_bit_exact_vs_reference(name):
 
 
 @pytest.mark.parametrize("name", ["ifront32_k1", "ifront32_k4", "ioniz24_k1", "ioniz24_k3", "ifront32hllc_k4", "ifront32ppm_k4",
-                                  "ifronttiny_k3"])
+                                  "ifronttiny_k3", "ionizodd_k1"])
 def test_ion_hydro_bit_exact_vs_reference(name):
     """stricter than north_star asks: with the host libm's exp/pow restated on the device (csrc/glibc_math.cuh) the
     hydro + ion-RT step reproduces the reference's dump to the last bit, EdgeFlux and sub-cycle counts included"""

@@ -121,7 +121,7 @@ def _oracle_run(case, log=None):
 @pytest.mark.parametrize("name", ["blast16_k1", "blast16_k6", "blastmix_k5", "ifront32_k1", "ifront32_k4",
                                   "ioniz24_k1", "ioniz24_k3", "blast16hllc_k6", "ifront32hllc_k4", "blast16noh_k6",
                                   "blast16ppm_k6", "ifront32ppm_k4", "blast16ppmhllc_k6",
-                                  "blasttiny_k5", "ifronttiny_k3"])
+                                  "blasttiny_k5", "ifronttiny_k3", "ionizodd_k1"])
 def test_run_matches_reference_dump(name):
     case = Case(name)
     log = {}
