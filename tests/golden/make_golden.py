@@ -73,6 +73,15 @@ CASES = {
                    ["domain1/Nx1=16", "domain1/Nx2=16", "domain1/Nx3=16", "problem/radius=0.25"], [6]),
     "ifront32hllc": ("ifront_hllc", "ifront.athinput",
                      ["domain1/Nx1=32", "domain1/Nx2=16", "domain1/Nx3=16"], [4]),
+    # a child Domain that touches root boundaries: its x1 faces get the root's physical BCs (reflect / outflow) instead of
+    # prolongation, the rays enter it through the root boundary itself, and two of its faces need no flux correction
+    "ifrontsmredge": ("ifront_smr", "ifront.athinput",
+                      ["job/num_domains=2", "domain1/Nx1=32", "domain1/Nx2=16", "domain1/Nx3=16", "problem/n_H=0.05",
+                       "domain2/Nx1=24", "domain2/Nx2=16", "domain2/Nx3=20", "domain2/iDisp=0", "domain2/jDisp=16", "domain2/kDisp=8"], [3]),
+    "blastsmredge": ("blast_smr", "blast.athinput",
+                     ["job/num_domains=2", "domain1/Nx1=16", "domain1/Nx2=16", "domain1/Nx3=16", "problem/radius=0.25",
+                      "domain1/bc_ix1=2", "domain1/bc_ox1=2", "domain1/bc_ix2=1", "domain1/bc_ox2=2", "domain1/bc_ix3=2", "domain1/bc_ox3=1",
+                      "domain2/Nx1=16", "domain2/Nx2=12", "domain2/Nx3=16", "domain2/iDisp=16", "domain2/jDisp=0", "domain2/kDisp=16"], [4]),
     # three nested levels.  The reference's serial build segfaults below level 1 with ion RT, so these
     # come from its MPI branch run as one rank against oracle/mpi_stub (builds *_smr_mpi).  n_H lowered so the box
     # is optically thin-ish (tau ~ 0.3 per root cell) and non-trivial fluxes are handed down to both fine levels.

@@ -68,7 +68,8 @@ def run_dropin_smr(case, build):
 
 
 @pytest.mark.parametrize("name,dropin", [("blastsmr_k4", "blast_smr"), ("blastsmr3_k4", "blast_smr"),
-                                         ("ifrontsmr_k3", "ifront_smr"), ("ifrontsmr3_k3", "ifront_smr")])
+                                         ("ifrontsmr_k3", "ifront_smr"), ("ifrontsmr3_k3", "ifront_smr"),
+                                         ("blastsmredge_k4", "blast_smr"), ("ifrontsmredge_k3", "ifront_smr")])
 def test_dropin_smr_bit_exact(name, dropin):
     """the unmodified SMR driver linked against the engine, two and three nested levels, against the reference's dumps
     (three levels: its MPI branch as one rank -- the reference's serial build segfaults there)"""

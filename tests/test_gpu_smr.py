@@ -18,7 +18,7 @@ def gpu_run_smr(case):
     return R
 
 
-@pytest.mark.parametrize("name", ["blastsmr_k1", "blastsmr_k4", "blastsmr3_k4"])
+@pytest.mark.parametrize("name", ["blastsmr_k1", "blastsmr_k4", "blastsmr3_k4", "blastsmredge_k4"])
 def test_smr_hydro_bit_exact(name):
     case = SmrCase(name)
     R = gpu_run_smr(case)
@@ -29,7 +29,7 @@ def test_smr_hydro_bit_exact(name):
             assert np.array_equal(a[v], lv["U1"][v]), f"level {n} {v}: max abs {np.abs(a[v]-lv['U1'][v]).max()}"
 
 
-@pytest.mark.parametrize("name", ["ifrontsmr_k1", "ifrontsmr_k3", "ifrontsmr3_k1", "ifrontsmr3_k3"])
+@pytest.mark.parametrize("name", ["ifrontsmr_k1", "ifrontsmr_k3", "ifrontsmr3_k1", "ifrontsmr3_k3", "ifrontsmredge_k3"])
 def test_smr_ion(name):
     case = SmrCase(name)
     R = gpu_run_smr(case)

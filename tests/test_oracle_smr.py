@@ -41,7 +41,7 @@ def oracle_run_smr(case, log=None):
 
 
 @pytest.mark.parametrize("name", ["blastsmr_k1", "blastsmr_k4", "ifrontsmr_k1", "ifrontsmr_k3",
-                                  "blastsmr3_k4", "ifrontsmr3_k1", "ifrontsmr3_k3"])
+                                  "blastsmr3_k4", "ifrontsmr3_k1", "ifrontsmr3_k3", "blastsmredge_k4", "ifrontsmredge_k3"])
 def test_smr_run_matches_reference_dump(name):
     case = SmrCase(name)
     log = {}
