@@ -300,6 +300,7 @@ template <bool UPDATE>
 __global__ void __launch_bounds__(128, AB2_LB_ION_RATES) k_ion_rates(GridDev g, IonParDev p, IonDev ion, double flux_in_root, int finegrid, double dt_upd,
                                                    const double* ef_in_base, double* ef_out_base, unsigned long long* scal)
 {
+  __shared__ double s_etau[128];
   const int lane = threadIdx.x & 31;
   const long ray = (long)blockIdx.x*(blockDim.x >> 5) + (threadIdx.x >> 5);
   const long nrays = (long)g.nx[1]*g.nx[2];
@@ -345,9 +346,13 @@ __global__ void __launch_bounds__(128, AB2_LB_ION_RATES) k_ion_rates(GridDev g, 
     // lockstep).  A log-step prefix scan would be 5 steps but reassociates the product, and a last-bit difference in a
     // flux is enough to flip a check_range / dt decision of the sub-cycle tens of steps later.
     double flux_before = carry;
+    __syncwarp();                       // the previous chunk's reads of s_etau are done
+    s_etau[threadIdx.x] = etau;         // broadcast through shared memory: one LDS per step instead of the two SHFL of a 64-bit shuffle
+    __syncwarp();
+    const double* se = s_etau + (threadIdx.x & ~31);
 #pragma unroll
     for (int l=0; l<31; l++) {
-      const double el = __shfl_sync(0xffffffffu, etau, l);
+      const double el = se[l];
       if (lane > l) flux_before *= el;
     }
     const double flux_after = flux_before*etau;
