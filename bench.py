@@ -334,7 +334,15 @@ def gpu_arm(args):
         prof_json = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(prof_json):
             try:
-                roof["traffic"] = json.load(open(prof_json)).get(dom, {}).get("dram_bytes_per_launch")
+                prof_all = json.load(open(prof_json))
+                ent = prof_all.get(dom, {})
+                roof["traffic"] = ent.get("dram_bytes_per_launch")
+                # which ceiling binds -- DRAM and FP64-pipe utilisation of the same kernel from the committed
+                # ncu --set full capture (profiles/<round>_ncu_full_table.md), next to the live algorithmic number above
+                roof["dram_util"] = round(ent["dram_pct"] / 100.0, 4) if "dram_pct" in ent else None
+                roof["fp64_util"] = round(ent["fp64_pipe_pct"] / 100.0, 4) if "fp64_pipe_pct" in ent else None
+                roof["per_kernel_ncu"] = {k: {"dram_util": round(v["dram_pct"] / 100.0, 3), "fp64_util": round(v["fp64_pipe_pct"] / 100.0, 3)}
+                                          for k, v in prof_all.items() if k.startswith("k_") and "dram_pct" in v}
             except Exception:
                 pass
 
