@@ -1,0 +1,47 @@
+#!/usr/bin/env python3
+"""SHA-256 fingerprints of the REFERENCE's dump at BASELINE.json's full sizes (the dumps are 0.9 GB each, so only their
+fingerprints are committed; same scheme as make_hires5_fingerprint.py):
+
+    ioniz256_k1  configs[2]: ioniz_sphere unigrid 256^3, 1 step   (oracle/_ref/ioniz_sphere, ~2 min of one core, 11 GB)
+    blast256_k2  configs[1]: blast 256^3 periodic, 2 steps        (oracle/_ref/blast)
+
+A bit-identical run reproduces every hash (tests/test_gpu_longrun.py).   python tests/golden/make_fullsize_fingerprint.py
+"""
+import json
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, HERE)
+from make_hires5_fingerprint import fingerprint, read_restart  # noqa: E402
+
+CASES = {
+    "ioniz256_k1": ("ioniz_sphere", "ioniz_sphere.athinput", 1),
+    "blast256_k2": ("blast", "blast.athinput", 2),
+}
+OVERRIDES = ["job/num_domains=1", "domain1/Nx1=256", "domain1/Nx2=256", "domain1/Nx3=256"]
+
+
+def main():
+    for name, (build, deck, nlim) in CASES.items():
+        if len(sys.argv) > 1 and name not in sys.argv[1:]:
+            continue
+        exe = os.path.join(ROOT, "oracle", "_ref", build, "athena")
+        with tempfile.TemporaryDirectory() as tmp:
+            r = subprocess.run([exe, "-i", os.path.join(ROOT, "tests", "decks", deck), f"time/nlim={nlim}"] + OVERRIDES,
+                               cwd=tmp, capture_output=True, text=True, check=True)
+            rst = sorted(f for f in os.listdir(tmp) if f.endswith(".rst"))
+            d = read_restart(os.path.join(tmp, rst[-1]))
+        rad = [int(a) for a in re.findall(r"Radiation done in (\d+) iterations", r.stderr)]
+        fp = fingerprint(d, rad, vars_=("d", "M1", "M2", "M3", "E") + (("s", "edgeflux") if build != "blast" else ()))
+        fp["deck"], fp["overrides"], fp["build"] = deck, OVERRIDES, build
+        json.dump(fp, open(os.path.join(HERE, name + ".json"), "w"), indent=1)
+        print(name, "rad", rad, "time", fp["time"])
+
+
+if __name__ == "__main__":
+    main()

@@ -29,11 +29,11 @@ from athena_b200.restart import read_restart  # noqa: E402
 VARS = ("d", "M1", "M2", "M3", "E", "s", "edgeflux")
 
 
-def fingerprint(d, rad):
+def fingerprint(d, rad, vars_=VARS):
     out = {"time": float(d["time"]).hex(), "dt": float(d["dt"]).hex(), "nstep": int(d["nstep"]), "rad": rad, "levels": []}
     for g in d["grids"]:
         lev = {}
-        for v in VARS:
+        for v in vars_:
             a = np.ascontiguousarray(g[v], dtype=np.float64) + 0.0      # -0.0 -> +0.0: equal values, equal bytes
             lev[v] = {"shape": list(a.shape), "sha256": hashlib.sha256(a.tobytes()).hexdigest(),
                       "sum": float(np.nansum(a)), "absmax": float(np.nanmax(np.abs(a))), "nan": int(np.isnan(a).sum())}

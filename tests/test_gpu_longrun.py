@@ -111,3 +111,34 @@ def test_full_size_determinism_and_bounds_ioniz_256():
         assert np.array_equal(a[v], b[v], equal_nan=True), v
     assert (a["s"] > 0).all() and (a["s"] <= a["d"]).all()
     assert np.isfinite(a["E"]).all()
+
+
+@pytest.mark.parametrize("name", ["ioniz256_k1", "blast256_k2"])
+def test_full_size_matches_reference_fingerprint(name):
+    """BASELINE configs[2] / configs[1] AT FULL SIZE (256^3) against the reference itself: SHA-256 of every conserved
+    variable (and EdgeFlux) of the reference's dump, generated by tests/golden/make_fullsize_fingerprint.py from the
+    reference binary on this container's CPU; the engine's dump must hash to the same bytes."""
+    import importlib.util
+    import json
+    from athena_b200.driver import Run
+    path = os.path.join(ROOT, "tests", "golden", name + ".json")
+    if not os.path.exists(path):
+        pytest.skip("fingerprint not generated")
+    gold = json.load(open(path))
+    spec = importlib.util.spec_from_file_location("fp5", os.path.join(ROOT, "tests", "golden", "make_hires5_fingerprint.py"))
+    fp5 = importlib.util.module_from_spec(spec); spec.loader.exec_module(fp5)
+    par = ParFile.par_open(os.path.join(DECKS, gold["deck"]))
+    par.par_cmdline(gold["overrides"])
+    R = Run(par, gold["build"], device=0)
+    R.run(gold["nstep"])
+    g = R.G.download_active()
+    ion = gold["build"] != "blast"
+    if ion:
+        g["edgeflux"] = R.G.download_edgeflux()
+    mine = fp5.fingerprint(dict(time=R.time, dt=R.dt, nstep=R.nstep, grids=[g]), [r[0] for r in R.rad_log], vars_=tuple(gold["levels"][0]))
+    assert mine["rad"] == gold["rad"]
+    assert mine["time"] == gold["time"] and mine["dt"] == gold["dt"]
+    for v, ref in gold["levels"][0].items():
+        got = mine["levels"][0][v]
+        assert got["shape"] == ref["shape"]
+        assert got["sha256"] == ref["sha256"], f"{v}: sum {got['sum']!r} vs {ref['sum']!r}, absmax {got['absmax']!r} vs {ref['absmax']!r}"
