@@ -4,6 +4,7 @@ fingerprints are committed; same scheme as make_hires5_fingerprint.py):
 
     ioniz256_k1  configs[2]: ioniz_sphere unigrid 256^3, 1 step   (oracle/_ref/ioniz_sphere, ~2 min of one core, 11 GB)
     blast256_k2  configs[1]: blast 256^3 periodic, 2 steps        (oracle/_ref/blast)
+    ifront64_k30 configs[0]: ifront 64^3 as shipped, 30 steps     (oracle/_ref/ifront)
 
 A bit-identical run reproduces every hash (tests/test_gpu_longrun.py).   python tests/golden/make_fullsize_fingerprint.py
 """
@@ -19,15 +20,16 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, HERE)
 from make_hires5_fingerprint import fingerprint, read_restart  # noqa: E402
 
+N256 = ["job/num_domains=1", "domain1/Nx1=256", "domain1/Nx2=256", "domain1/Nx3=256"]
 CASES = {
-    "ioniz256_k1": ("ioniz_sphere", "ioniz_sphere.athinput", 1),
-    "blast256_k2": ("blast", "blast.athinput", 2),
+    "ioniz256_k1": ("ioniz_sphere", "ioniz_sphere.athinput", 1, N256),
+    "blast256_k2": ("blast", "blast.athinput", 2, N256),
+    "ifront64_k30": ("ifront", "ifront.athinput", 30, ["job/num_domains=1"]),      # configs[0]: the deck as shipped, 64^3
 }
-OVERRIDES = ["job/num_domains=1", "domain1/Nx1=256", "domain1/Nx2=256", "domain1/Nx3=256"]
 
 
 def main():
-    for name, (build, deck, nlim) in CASES.items():
+    for name, (build, deck, nlim, OVERRIDES) in CASES.items():
         if len(sys.argv) > 1 and name not in sys.argv[1:]:
             continue
         exe = os.path.join(ROOT, "oracle", "_ref", build, "athena")

@@ -113,9 +113,9 @@ def test_full_size_determinism_and_bounds_ioniz_256():
     assert np.isfinite(a["E"]).all()
 
 
-@pytest.mark.parametrize("name", ["ioniz256_k1", "blast256_k2"])
+@pytest.mark.parametrize("name", ["ioniz256_k1", "blast256_k2", "ifront64_k30"])
 def test_full_size_matches_reference_fingerprint(name):
-    """BASELINE configs[2] / configs[1] AT FULL SIZE (256^3) against the reference itself: SHA-256 of every conserved
+    """BASELINE configs[2] / configs[1] / configs[0] AT FULL SIZE (256^3, 256^3, 64^3) against the reference itself: SHA-256 of every conserved
     variable (and EdgeFlux) of the reference's dump, generated by tests/golden/make_fullsize_fingerprint.py from the
     reference binary on this container's CPU; the engine's dump must hash to the same bytes."""
     import importlib.util
