@@ -17,10 +17,11 @@ def test_two_gpu_run_equals_one_gpu_run():
         pytest.skip("needs 2 GPUs")
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", str(port), os.path.join(ROOT, "tests", "multi_gpu_check.py"), "blast16_k6", "ifront32_k4", "ioniz24_k3"]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+           "--master-port", str(port), os.path.join(ROOT, "tests", "multi_gpu_check.py"), "blast16_k6", "ifront32_k4", "ioniz24_k3",
+           "ioniz256_k1", "blast256_k2"]        # the last two: BASELINE's full 256^3 over 2 slabs against the reference's fingerprint
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=1200)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert r.stdout.count("MULTI_GPU_OK") == 3, r.stdout
+    assert r.stdout.count("MULTI_GPU_OK") == 5, r.stdout
 
 
 def test_two_gpu_smr_equals_one_gpu_and_reference():
