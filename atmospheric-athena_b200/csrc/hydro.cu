@@ -1,7 +1,9 @@
 // hydro.cu -- FP64 CUDA kernels (sm_100a) for the hydro half of the hot path:
 //   bvals_mhd   (bvals_mhd.c:174-508, physical BCs :959-1949)
 //   new_dt      (new_dt.c:69-139)
-//   integrate_3d_ctu (integrators/integrate_3d_ctu.c:110-3368; PLM lr_states_plm.c, Roe roe.c/hlle.c)
+//   integrate_3d_ctu (integrators/integrate_3d_ctu.c:110-3368; lr_states: PLM lr_states_plm.c or PPM lr_states_ppm.c;
+//                     fluxes: Roe roe.c/hlle.c with or without H-correction, or HLLC hllc.c -- the reference's configure-time
+//                     choices, selected per Grid by ab2_set_reconstruction / ab2_set_riemann_solver)
 //
 // Layout: SoA, one double[n3][n2][n1] per variable, x1 fastest.  Face states and fluxes are kept in
 // PHYSICAL component order (d,M1,M2,M3,E,s) so the reference's (x,y,z)->(z,x,y) permutations between
@@ -10,9 +12,10 @@
 //
 // Pass structure of one step (HBM round trips):
 //   A  k_first_x1 / k_first_march<1|2> : U -> first-pass face states Ul,Ur + fluxes F     (steps 1-3)
+//      (PPM: k_ppm_slope / k_ppm_states / k_ppm_flux per direction instead)
 //   B  k_dhalf                         : d^{n+1/2} from first-pass fluxes (static potential only, step 8a)
 //   C  k_correct<0|1|2>                : transverse flux-gradient + gravity corrections of Ul,Ur, eta (steps 5-7, 9a)
-//   D  k_final<0|1|2>                  : etah = max of 9 etas, Roe flux from corrected states (step 9b-d)
+//   D  k_final<0|1|2>                  : etah = max of 9 etas, Riemann flux from corrected states (step 9b-d)
 //   E  k_update                        : gravity source (11a) + three ordered flux-difference updates (12a-c)
 #include "engine.cuh"
 #include "physics.cuh"

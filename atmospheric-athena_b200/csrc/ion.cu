@@ -7,9 +7,10 @@
 //
 // The reference makes nine full-grid sweeps per sub-cycle iteration; here an iteration is two kernels,
 // separated by the grid-wide min that chooses the sub-step:
-//   k_ion_rates  : one WARP per ray; 32 cells at a time, exp(-tau) in parallel, attenuation as a warp-level
-//                  prefix product with the reference's 1e-3 ray cut, then photo/chem/thermal rates and the
-//                  per-cell dt limits of those same cells while they are in registers.
+//   k_ion_rates  : one WARP per ray; 32 cells at a time, exp(-tau) in parallel, attenuation as the reference's
+//                  sequential product (every lane applies the factors of the lanes before it, in order) with its
+//                  1e-3 ray cut, then photo/chem/thermal rates and the per-cell dt limits of those same cells
+//                  while they are in registers.
 //   k_ion_update : E,s update, temperature and neutral floors, check_range count and the new hydro dt.
 // Arithmetic: every per-cell formula keeps the reference's operations and order; exp() and pow() are the host glibc's
 // own algorithms re-implemented operation for operation (glibc_math.cuh), and the attenuation along a ray is the
