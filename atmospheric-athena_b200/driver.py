@@ -148,7 +148,7 @@ class Run:
                 g = gat.cpu().view(world, 4)
                 return np.array([float(g[:, 0].sum()), float(g[:, 1].max()), float(g[:, 2].min()), float(g[:, 3].min())])
             dist.all_reduce(buf[:n], op=ops[op])
-            return buf[:n].cpu().numpy()
+            return buf[:n].cpu().numpy().copy()
         return reduce
 
     def bvals_mhd(self):
@@ -328,7 +328,7 @@ def make_group_reduce(dist, group=None):
             g = gat.cpu().view(n, 4)
             return np.array([float(g[:, 0].sum()), float(g[:, 1].max()), float(g[:, 2].min()), float(g[:, 3].min())])
         dist.all_reduce(buf[:k], op=ops[op], group=group)
-        return buf[:k].cpu().numpy()
+        return buf[:k].cpu().numpy().copy()        # a copy: on a CPU backend .cpu().numpy() aliases `buf`, which the next call overwrites
     return reduce
 
 
