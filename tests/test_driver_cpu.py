@@ -92,8 +92,19 @@ class OracleBackedGrid:
             self._U[n].reshape(-1)[cells] = vals[n]
 
     def new_dt(self, cour_no, dt_old, nstep, time, tlim, reduce=None):
-        assert reduce is None
-        return ol.lib().orc_new_dt(C.byref(self.g), cour_no, dt_old, nstep, time, tlim)
+        if reduce is None:
+            return ol.lib().orc_new_dt(C.byref(self.g), cour_no, dt_old, nstep, time, tlim)
+        v = self.max_wave_speeds()                              # as ab2_new_dt: local dt, MIN over ranks, then the tlim clip
+        max_dti = 0.0
+        for a in range(3):
+            if self.nx[a] > 1:
+                x = v[a] / self.dx[a]
+                max_dti = max_dti if max_dti > x else x
+        dt = cour_no / max_dti if nstep == 0 else min(2.0 * dt_old, cour_no / max_dti)
+        dt = float(reduce(np.array([dt]), 0)[0])
+        if time < tlim and (tlim - time) < dt:
+            dt = tlim - time
+        return dt
 
     # ---- ion RT (single rank: the oracle's sub-cycle is one C call) ----
     def ion_init(self, ip):
@@ -156,6 +167,42 @@ def _worker(rank, world, port, name, q):
         q.put((rank, ok and not bad, bad, held, R.cuts))
     finally:
         dist.destroy_process_group()
+
+
+def _worker_unigrid(rank, world, port, name, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import athena_b200.driver as drv
+        from cases import Case
+        drv.engine.Grid = OracleBackedGrid
+        case = Case(name)
+        R = drv.Run(case.par, case.problem, dist=dist, U0=case.U0)
+        ok = R.dt == float(case.gold["dt0"])
+        R.run(case.nsteps)
+        ok = ok and R.time == float(case.gold["time1"]) and R.dt == float(case.gold["dt1"])
+        a = R.G.download_active()
+        bad = [v for v in case.U1 if not np.array_equal(a[v], case.U1[v][R.k0:R.k1])]
+        q.put((rank, ok and not bad, bad, [True], [R.k0, R.k1]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name", ["blast16_k6", "blastmix_k5"])
+def test_unigrid_across_two_ranks_equals_reference_dump(name):
+    """driver.Run with the Grid cut into two x3 slabs (periodic ring for blast16, physical faces for blastmix)"""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_unigrid, args=(r, world, port, name, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, ok, bad, _, ks in res:
+        assert ok, f"rank {rank} (layers {ks}): differs from the reference dump in {bad}"
 
 
 @pytest.mark.parametrize("name", ["blastsmr_k4", "blastsmr3_k4"])
