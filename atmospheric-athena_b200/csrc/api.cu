@@ -119,6 +119,7 @@ ab2_grid* ab2_grid_create(const ab2_grid_desc* d)
   h->has_grav = false; h->has_ion = false; h->n_fixed = 0; h->d_fixed_cells = nullptr; h->d_fixed_vals = nullptr;
   h->bytes_allocated = 0; h->launches = 0; h->maxiter = 0; h->tcoarse = 0.0;
   h->prof_on = false;
+  h->comm = nullptr; h->lo_rank = h->hi_rank = -1; h->d_gather = nullptr; h->h_gather = nullptr;
   for (int n=0; n<KID_N; n++) { h->prof_ms[n] = 0.0; h->prof_cnt[n] = 0; }
   memset(&h->ion, 0, sizeof h->ion);
   if (d->use_external_stream) { h->stream = (cudaStream_t)d->stream; h->own_stream = false; }
@@ -171,6 +172,7 @@ void ab2_grid_destroy(ab2_grid* h)
   for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
   for (void* p : h->allocs) cudaFree(p);
   if (h->h_scal) cudaFreeHost(h->h_scal);
+  if (h->h_gather) cudaFreeHost(h->h_gather);
   if (h->own_stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -241,7 +243,11 @@ int ab2_download_edgeflux(ab2_grid* h, double* ef)
 }
 
 // ---- hydro -----------------------------------------------------------------------------------------------
-int ab2_bvals_mhd(ab2_grid* h, const int bc[6]) { return hydro_bvals(h, bc); }
+int ab2_bvals_mhd(ab2_grid* h, const int bc[6])
+{ // physical faces by kernels, faces shared with a neighbouring Grid by the NCCL exchange (bvals_mhd.c:423-446)
+  if (hydro_bvals(h, bc) != 0) return -1;
+  return comm_exchange_x3(h);
+}
 int ab2_max_wave_speeds(ab2_grid* h, double out[3]) { return hydro_max_speeds(h, out); }
 
 int ab2_new_dt(ab2_grid* h, double cour_no, double dt_old, int nstep, double time, double tlim,

@@ -56,6 +56,7 @@ enum {
   SC_ERR,                             // sticky error flags
   SC_N = 16
 };
+#define SC_NRED 8                     // SC_MAXV1 .. SC_ERR: the scalars one cross-rank exchange combines (comm.cu)
 
 struct IonParDev {
   double sigma_ph, m_H, mu, e_gamma, alpha_C, k_B, time_unit;
@@ -73,6 +74,7 @@ struct IonDev {
 };
 
 typedef void (*ab2_reduce_fn_t)(double* vals, int n, int op, void* ctx);
+struct ab2_comm;
 
 // per-kernel CUDA-event timing (bench.py's roofline): ids index KERNEL_NAMES in api.cu
 enum {
@@ -109,6 +111,10 @@ struct ab2_grid {
   std::vector<cudaEvent_t> prof_pool;
   double prof_ms[KID_N];
   long long prof_cnt[KID_N];
+  ab2_comm* comm;                  // NCCL communicator of the Grids that exchange / reduce with this one (comm.cu), or NULL
+  int lo_rank, hi_rank;            // x3 neighbours in that communicator, -1 = none (physical boundary or single Grid)
+  unsigned long long* d_gather;    // all-gathered loop scalars, nranks x SC_NRED
+  unsigned long long* h_gather;    // pinned host mirror
 };
 
 // launch bookkeeping: counts every kernel; with profiling on, brackets it with events on the launching stream
@@ -125,6 +131,9 @@ cudaEvent_t ab2_prof_event(ab2_grid* h);
 void ab2_set_error(const std::string& s);
 bool ab2_check(cudaError_t e, const char* what);
 
+// comm.cu
+int comm_exchange_x3(ab2_grid* h);
+int comm_read_scalars(ab2_grid* h);
 // hydro.cu
 int hydro_bvals(ab2_grid* h, const int bc[6]);
 int hydro_max_speeds(ab2_grid* h, double out[3]);

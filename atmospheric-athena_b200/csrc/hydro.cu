@@ -505,9 +505,13 @@ int hydro_max_speeds(ab2_grid* h, double out[3])
   const long nact = (long)g.nx[0]*g.nx[1]*g.nx[2];
   int blocks = (int)((nact + 255)/256); if (blocks > 148*8) blocks = 148*8;
   AB2_LAUNCH(h, KID_MAX_SPEEDS, (k_max_speeds<<<blocks, 256, 0, h->stream>>>(g, h->d_scal)));
-  if (!ab2_check(cudaMemcpyAsync(h->h_scal + SC_MAXV1, h->d_scal + SC_MAXV1, 3*sizeof(unsigned long long),
-                                 cudaMemcpyDeviceToHost, h->stream), "new_dt D2H")) return -1;
-  if (!ab2_check(cudaStreamSynchronize(h->stream), "new_dt sync")) return -1;
+  if (h->comm) {                               // new_dt.c:175-179: the maximum over the Grids of the Domain
+    if (comm_read_scalars(h) != 0) return -1;
+  } else {
+    if (!ab2_check(cudaMemcpyAsync(h->h_scal + SC_MAXV1, h->d_scal + SC_MAXV1, 3*sizeof(unsigned long long),
+                                   cudaMemcpyDeviceToHost, h->stream), "new_dt D2H")) return -1;
+    if (!ab2_check(cudaStreamSynchronize(h->stream), "new_dt sync")) return -1;
+  }
   for (int d=0; d<3; d++) {
     long long bits = (long long)h->h_scal[SC_MAXV1+d];
     double v; memcpy(&v, &bits, sizeof v);

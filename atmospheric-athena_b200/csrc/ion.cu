@@ -501,10 +501,9 @@ static int ion_radtransfer_impl(ab2_grid* h, int finegrid, double flux_in, doubl
     hs[SC_MAX_DTI] = double_to_bits(0.0); hs[SC_COUNT] = 0;
     return ab2_check(cudaMemcpyAsync(h->d_scal + SC_MAXV1, hs + SC_MAXV1, 7*sizeof(unsigned long long), cudaMemcpyHostToDevice, st), "ion scalars H2D");
   };
-  auto read_scalars = [&]() -> bool {
-    return ab2_check(cudaMemcpyAsync(hs + SC_MAXV1, h->d_scal + SC_MAXV1, 8*sizeof(unsigned long long), cudaMemcpyDeviceToHost, st), "ion scalars D2H")
-        && ab2_check(cudaStreamSynchronize(st), "ion sync");
-  };
+  // one copy + one synchronisation; with a communicator attached the scalars of all ranks are all-gathered first and
+  // combined (the MPI_Allreduce sites of ionrad_3d.c:275,399,554,672 in ONE exchange, comm.cu)
+  auto read_scalars = [&]() -> bool { return comm_read_scalars(h) == 0; };
 
   AB2_LAUNCH(h, KID_ION_PREP, (k_ion_prep<<<cgrid, 128, 0, st>>>(g, p, h->ion)));
 

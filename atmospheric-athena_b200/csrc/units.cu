@@ -3,6 +3,7 @@
 // objects (tests/golden/units_*.npz).  Rows of 6 doubles: (d,Mx,My,Mz,E,s) or (d,Vx,Vy,Vz,P,r).
 #include <vector>
 #include "../../include/athena_b200.h"
+#include "../../include/athena_b200_units.h"
 #include "engine.cuh"
 #include "physics.cuh"
 #include "glibc_math.cuh"

@@ -73,8 +73,11 @@ class Run:
         self.rank = dist.get_rank() if dist is not None else 0
         self.world = dist.get_world_size() if dist is not None else 1
         p = par
-        self.ion = problem in ("ifront", "ioniz_sphere")
-        self.nscal = 1 if self.ion else 0
+        if p.par_geti_def("job", "num_domains", 1) != 1:
+            raise ValueError("driver.Run drives one root Domain; use SmrRun / SmrRunSlabs for job/num_domains > 1")
+        self.nscal = 1 if problem in ("ifront", "ioniz_sphere") else 0      # an ion BUILD carries the scalar either way
+        # main.c:546 runs the radiation step only when a plane exists; both problem files add theirs iff problem/nradplanes > 0
+        self.ion = self.nscal == 1 and p.par_geti("problem", "nradplanes") > 0
         self.root_nx = tuple(p.par_geti("domain1", f"Nx{a}") for a in (1, 2, 3))
         xmin = [p.par_getd("domain1", f"x{a}min") for a in (1, 2, 3)]
         xmax = [p.par_getd("domain1", f"x{a}max") for a in (1, 2, 3)]
@@ -95,8 +98,19 @@ class Run:
                 self.bc_local[4] = 0
             if self.rank < self.world - 1 or self.bc[5] == 4:
                 self.bc_local[5] = 0
+        # More than one GPU: NCCL lives INSIDE the library (csrc/comm.cu) -- ab2_bvals_mhd exchanges the x3 ghost slabs and
+        # the dt / sub-cycle reductions span the communicator; torch.distributed only carries the unique id.  With a CPU
+        # backend (gloo: the host-logic tests, where a CPU stand-in sits behind engine.Grid) the same exchange and reductions
+        # go through torch.distributed below.
+        use_comm = self.world > 1 and dist.get_backend() == "nccl"
         self.G = engine.Grid(self.nx, self.dx, self.xmin, self.gamma, self.nscal, device=device,
-                             torch_memory=(self.world > 1) if torch_memory is None else torch_memory)
+                             torch_memory=(self.world > 1 and not use_comm) if torch_memory is None else torch_memory)
+        self.comm = None
+        if use_comm:
+            lo = self.rank - 1 if self.rank > 0 else (self.world - 1 if self.bc[4] == 4 else None)
+            hi = self.rank + 1 if self.rank < self.world - 1 else (0 if self.bc[5] == 4 else None)
+            self.comm = engine.Comm(dist, device)
+            self.G.set_comm(self.comm, lo, hi)
         if riemann:
             self.G.set_riemann_solver(riemann)       # the reference's --with-flux=hllc build
         if order != 2:
@@ -104,7 +118,7 @@ class Run:
         self.time, self.dt, self.nstep = 0.0, 0.0, 0
         self.flux_i = p.par_getd("problem", "flux") if self.ion else 0.0
         self.rad_log = []
-        self._reduce = self._make_reduce() if self.world > 1 else None
+        self._reduce = self._make_reduce() if (self.world > 1 and self.comm is None) else None
 
         # --- problem() (main.c:391-395)
         if U0 is None:
@@ -120,7 +134,7 @@ class Run:
             self.userwork = self.G.apply_fixed_cells
         else:
             self.userwork = None
-        if self.ion:
+        if self.nscal:
             self.G.ion_init(engine.ion_par_from(p, self.dx))                  # main.c:473
         # --- main.c:430-451
         self.bvals_mhd()
@@ -152,8 +166,8 @@ class Run:
         return reduce
 
     def bvals_mhd(self):
-        self.G.bvals_mhd(self.bc_local)
-        if self.world > 1:
+        self.G.bvals_mhd(self.bc_local)          # with a communicator attached this includes the NCCL ghost exchange
+        if self.world > 1 and self.comm is None:
             exchange_x3_ghosts(self.G.U_torch, self.rank, self.world, self.bc[4], self.bc[5], self.dist)
 
     def new_dt(self):
@@ -207,8 +221,8 @@ class SmrRun:
 
     def __init__(self, par, problem: str, U0: dict | None = None, *U0_fine: dict, device: int = 0):
         p = par
-        self.ion = problem in ("ifront", "ioniz_sphere")
-        self.nscal = 1 if self.ion else 0
+        self.nscal = 1 if problem in ("ifront", "ioniz_sphere") else 0
+        self.ion = self.nscal == 1 and p.par_geti("problem", "nradplanes") > 0       # main.c:546
         nlev = (1 + len(U0_fine)) if U0 is not None else p.par_geti("job", "num_domains")     # U0 None: problem() data
         nx0 = tuple(p.par_geti("domain1", f"Nx{a}") for a in (1, 2, 3))
         xmin = [p.par_getd("domain1", f"x{a}min") for a in (1, 2, 3)]
@@ -235,7 +249,7 @@ class SmrRun:
             G = engine.Grid(nx, dx, xm, self.gamma, self.nscal, device=device)
             self.userwork.append(_setup_problem_hooks(G, problem, p, nx, xm, dx, None if U0 is None else (U0 if n == 0 else U0_fine[n - 1])))
             self.grids.append(G); self.bcs.append(bc); disps.append(disp)
-        if self.ion:
+        if self.nscal:
             ip = engine.ion_par_from(p, dx0)                    # min_area, d_nlo from the ROOT spacing (ionrad.c:115-131)
             for G in self.grids:
                 G.ion_init(ip)
@@ -495,8 +509,8 @@ class SmrRunSlabs:
         p = par
         self.dist = dist
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
-        self.ion = problem in ("ifront", "ioniz_sphere")
-        self.nscal = 1 if self.ion else 0
+        self.nscal = 1 if problem in ("ifront", "ioniz_sphere") else 0
+        self.ion = self.nscal == 1 and p.par_geti("problem", "nradplanes") > 0       # main.c:546
         nlev = len(U0_levels) if U0_levels is not None else p.par_geti("job", "num_domains")   # None: problem() data
         self.gamma = p.par_getd("problem", "gamma")
         self.cour_no = p.par_getd("time", "cour_no")
@@ -505,6 +519,8 @@ class SmrRunSlabs:
         if cuts == "balanced":
             cuts = balanced_cuts(p, nlev, self.world)
         lay = smr_slab_layout(p, nlev, self.world, cuts)
+        use_comm = dist.get_backend() == "nccl"      # as in Run: NCCL inside the library on GPUs, torch.distributed under gloo
+        self.use_comm = use_comm
         self.cuts = lay["cuts"]
         dx0 = lay["dx0"]
         self.dom_nx = [L["nx"] for L in lay["levels"]]
@@ -527,19 +543,25 @@ class SmrRunSlabs:
             if S is None:
                 self.levels.append(None)
                 continue
-            G = engine.Grid(S["nx"], LV["dx"], S["xmin"], self.gamma, self.nscal, device=device, torch_memory=True)
+            G = engine.Grid(S["nx"], LV["dx"], S["xmin"], self.gamma, self.nscal, device=device, torch_memory=not use_comm)
+            if use_comm and len(holders) > 1:        # this level's communicator inside the library (csrc/comm.cu)
+                G.set_comm(engine.Comm(dist, device, ranks=holders, group=group), S["lo"], S["hi"])
             k0 = S["ka"] - S["dom"][0]
             U0 = None if U0_levels is None else {v: np.ascontiguousarray(U0_levels[n][v][k0:k0 + S["nx"][2]]) for v in VARS[:5 + self.nscal]}
             userwork = _setup_problem_hooks(G, problem, p, S["nx"], S["xmin"], LV["dx"], U0)
             self.levels.append(dict(G=G, bc=S["bc"], lo=S["lo"], hi=S["hi"], ka=S["ka"], kb=S["kb"], disp=S["disp"], nx=S["nx"],
                                     dom=S["dom"], userwork=userwork,
-                                    reduce=make_group_reduce(dist, group) if len(holders) > 1 else None))
-        if self.ion:
+                                    reduce=make_group_reduce(dist, group) if (len(holders) > 1 and not use_comm) else None))
+        if self.nscal:
             ip = engine.ion_par_from(p, dx0)
             for L in self.levels:
                 if L is not None:
                     L["G"].ion_init(ip)
-        self.all_reduce = make_group_reduce(dist, None)
+        if use_comm:
+            self.wcomm = engine.Comm(dist, device)
+            self.all_reduce = lambda vals, op: self.wcomm.allreduce(vals, op)
+        else:
+            self.all_reduce = make_group_reduce(dist, None)
         self.time, self.dt, self.nstep = 0.0, 0.0, 0
         self.gdt = [0.0] * nlev
         self.rad_log = []
@@ -558,7 +580,8 @@ class SmrRunSlabs:
         L = self.levels[n]
         if L is not None:
             L["G"].bvals_mhd(L["bc"])
-            exchange_x3_with(L["G"].U_torch, L["lo"], L["hi"], self.dist)
+            if not self.use_comm:
+                exchange_x3_with(L["G"].U_torch, L["lo"], L["hi"], self.dist)
 
     def _bvals_all(self):
         for n in range(len(self.levels)):
@@ -629,7 +652,10 @@ class SmrRunSlabs:
             # (exchange only: physical-boundary ghosts stay as the reference leaves them, set before the restriction).
             for n in range(nlev - 1):
                 if lv[n] is not None:
-                    exchange_x3_with(lv[n]["G"].U_torch, lv[n]["lo"], lv[n]["hi"], self.dist)
+                    if self.use_comm:
+                        lv[n]["G"].exchange_x3()
+                    else:
+                        exchange_x3_with(lv[n]["G"].U_torch, lv[n]["lo"], lv[n]["hi"], self.dist)
         for n in range(nlev):
             if lv[n] is not None:
                 lv[n]["G"].integrate_3d_ctu(self.gdt[n])

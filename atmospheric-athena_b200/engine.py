@@ -66,12 +66,17 @@ EXPORTS = ["ab2_last_error", "ab2_version", "ab2_device_count", "ab2_grid_create
            "ab2_download_edgeflux", "ab2_device_ptr", "ab2_bvals_mhd", "ab2_max_wave_speeds", "ab2_new_dt",
            "ab2_set_static_grav_pot", "ab2_integrate_3d_ctu", "ab2_set_fixed_cells", "ab2_apply_fixed_cells",
            "ab2_ion_init", "ab2_ion_derived", "ab2_bvals_ionrad", "ab2_ion_entering_flux", "ab2_ion_radtransfer_3d",
-           "ab2_unit_roe_flux", "ab2_unit_convert", "ab2_unit_lr_states", "ab2_unit_ieee", "ab2_unit_libm",
            "ab2_profile_enable", "ab2_profile_kernels", "ab2_profile_kernel_name", "ab2_profile_read",
            "ab2_smr_restrict_correct", "ab2_smr_ion_restrict", "ab2_smr_prolongate", "ab2_smr_ion_prolong",
            "ab2_ion_radtransfer_3d_fine", "ab2_ion_coarse_time",
-           "ab2_set_riemann_solver", "ab2_unit_hllc_flux", "ab2_unit_lr_states_hll",
-           "ab2_set_reconstruction", "ab2_unit_lr_states_ppm"]
+           "ab2_set_riemann_solver", "ab2_set_reconstruction",
+           "ab2_comm_get_unique_id", "ab2_comm_init_rank", "ab2_comm_destroy", "ab2_comm_rank", "ab2_comm_size",
+           "ab2_comm_exchanges", "ab2_comm_reductions", "ab2_comm_allreduce", "ab2_comm_bcast", "ab2_grid_set_comm",
+           "ab2_exchange_x3"]
+# libathena_b200_units.so (include/athena_b200_units.h): function-level test hooks, not part of the bound interface
+UNITS_LIB_PATH = os.path.join(_HERE, "csrc", "libathena_b200_units.so")
+UNIT_EXPORTS = ["ab2_unit_roe_flux", "ab2_unit_convert", "ab2_unit_lr_states", "ab2_unit_ieee", "ab2_unit_libm",
+                "ab2_unit_hllc_flux", "ab2_unit_lr_states_hll", "ab2_unit_lr_states_ppm"]
 
 
 def build(verbose=False):
@@ -141,6 +146,36 @@ def lib():
     L.ab2_profile_kernel_name.argtypes = [C.c_int]
     L.ab2_profile_kernel_name.restype = C.c_char_p
     L.ab2_profile_read.argtypes = [vp, dp, C.POINTER(C.c_longlong), C.c_int]
+    L.ab2_comm_get_unique_id.argtypes = [C.c_char_p]
+    L.ab2_comm_init_rank.argtypes = [C.c_int, C.c_int, C.c_char_p, C.c_int]
+    L.ab2_comm_init_rank.restype = vp
+    L.ab2_comm_destroy.argtypes = [vp]
+    L.ab2_comm_destroy.restype = None
+    for f in (L.ab2_comm_rank, L.ab2_comm_size):
+        f.argtypes = [vp]
+    for f in (L.ab2_comm_exchanges, L.ab2_comm_reductions):
+        f.argtypes = [vp]
+        f.restype = C.c_longlong
+    L.ab2_comm_allreduce.argtypes = [vp, dp, C.c_int, C.c_int]
+    L.ab2_comm_bcast.argtypes = [vp, vp, C.c_int, C.c_int]
+    L.ab2_grid_set_comm.argtypes = [vp, vp, C.c_int, C.c_int]
+    L.ab2_exchange_x3.argtypes = [vp]
+    _lib = L
+    return L
+
+
+_units = None
+
+
+def units():
+    """libathena_b200_units.so: single routines of the kernels on host arrays (tests only)."""
+    global _units
+    if _units is not None:
+        return _units
+    lib()                     # the units library links against the product library
+    if not os.path.exists(UNITS_LIB_PATH):
+        raise EngineError(f"{UNITS_LIB_PATH} is missing: run __graft_entry__.build()")
+    L = C.CDLL(UNITS_LIB_PATH)
     L.ab2_unit_ieee.argtypes = [C.c_int, dp, dp, dp, dp, dp, dp, C.POINTER(C.c_int)]
     L.ab2_unit_libm.argtypes = [C.c_int, dp, dp, dp, dp]
     L.ab2_unit_roe_flux.argtypes = [C.c_int, dp, dp, dp, dp, C.c_int, C.c_double, dp, dp]
@@ -151,8 +186,50 @@ def lib():
     L.ab2_set_riemann_solver.argtypes = [vp, C.c_int]
     L.ab2_set_reconstruction.argtypes = [vp, C.c_int]
     L.ab2_unit_lr_states_ppm.argtypes = [C.c_int, C.c_int, dp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, dp, dp]
-    _lib = L
+    _units = L
     return L
+
+
+class Comm:
+    """ab2_comm: one NCCL communicator inside the library (csrc/comm.cu).  `dist` (torch.distributed, any backend) only
+    carries the 128-byte unique id from the group's first rank to the others -- the job MPI_Bcast does in the C driver."""
+
+    def __init__(self, dist, device, ranks=None, group=None):
+        L = lib()
+        world_rank = dist.get_rank()
+        self.ranks = list(range(dist.get_world_size())) if ranks is None else list(ranks)
+        assert world_rank in self.ranks
+        self.rank, self.size = self.ranks.index(world_rank), len(self.ranks)
+        box = [None]
+        if self.rank == 0:
+            buf = C.create_string_buffer(128)
+            if L.ab2_comm_get_unique_id(buf) != 0:
+                raise EngineError(L.ab2_last_error().decode())
+            box[0] = buf.raw
+        dist.broadcast_object_list(box, src=self.ranks[0], group=group)
+        self.h = L.ab2_comm_init_rank(self.size, self.rank, box[0], device)
+        if not self.h:
+            raise EngineError(L.ab2_last_error().decode())
+
+    def local(self, world_rank):
+        """rank of a world rank inside this communicator; None stays None (no neighbour) and maps to -1"""
+        return -1 if world_rank is None else self.ranks.index(world_rank)
+
+    def allreduce(self, vals, op):
+        """op 0 MIN, 1 MAX, 2 SUM over the communicator; vals: up to 64 doubles.  Returns a new array."""
+        a = np.ascontiguousarray(vals, dtype=np.float64).copy()
+        if lib().ab2_comm_allreduce(self.h, a.ctypes.data_as(dp), len(a), op) != 0:
+            raise EngineError(lib().ab2_last_error().decode())
+        return a
+
+    @property
+    def counters(self):
+        return {"exchanges": lib().ab2_comm_exchanges(self.h), "reductions": lib().ab2_comm_reductions(self.h)}
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().ab2_comm_destroy(self.h)
+            self.h = None
 
 
 def ion_par_from(par, root_dx) -> IonPar:
@@ -195,6 +272,10 @@ class Grid:
 
     # -- helpers ---------------------------------------------------------------------------------
     def _ck(self, rc):
+        err = getattr(self, "_cb_error", None)
+        if err is not None:
+            self._cb_error = None
+            raise EngineError(f"reduction callback failed: {err!r}") from err
         if rc != 0:
             raise EngineError(lib().ab2_last_error().decode())
 
@@ -342,6 +423,16 @@ class Grid:
     def ion_coarse_time(self):
         return lib().ab2_ion_coarse_time(self.h)
 
+    # -- more than one GPU ------------------------------------------------------------------------
+    def set_comm(self, comm, lo=None, hi=None):
+        """Attach to an engine.Comm with the x3 neighbours' WORLD ranks (None = physical or fine/coarse boundary):
+        bvals_mhd then exchanges ghost slabs and the dt / sub-cycle reductions span the communicator, all inside the library."""
+        self.comm = comm
+        self._ck(lib().ab2_grid_set_comm(self.h, comm.h if comm else None, comm.local(lo) if comm else -1, comm.local(hi) if comm else -1))
+
+    def exchange_x3(self):
+        self._ck(lib().ab2_exchange_x3(self.h))
+
     # -- SMR: this Grid as the parent of `child` ---------------------------------------------------
     def smr_restrict_correct(self, child, o, dt_parent):
         self._ck(lib().ab2_smr_restrict_correct(self.h, child.h, C.byref(o), dt_parent))
@@ -363,7 +454,11 @@ class Grid:
 
         def _cb(vals, n, op, ctx):
             arr = np.ctypeslib.as_array(vals, shape=(n,))
-            arr[:] = reduce(arr.copy(), op)
+            try:
+                arr[:] = reduce(arr.copy(), op)
+            except BaseException as e:          # ctypes would print and swallow it: poison the values so the C loop stops,
+                self._cb_error = e              # and re-raise from _ck() once the C call has returned
+                arr[:] = np.nan
         cb = REDUCE_FN(_cb)
         self._keep.append(cb)
         self._reduce_src, self._reduce_ptr = reduce, C.cast(cb, C.c_void_p)

@@ -61,3 +61,19 @@ def read_restart(path: str, level_shapes=None) -> dict:
             pos += 8 * ncell
         grids.append(g)
     return dict(par=par, nstep=nstep, time=time, dt=dt, grids=grids)
+
+
+def fingerprint(d: dict, rad, vars_=("d", "M1", "M2", "M3", "E", "s", "edgeflux")) -> dict:
+    """SHA-256 of the raw FP64 bytes of every variable of every Grid of a dump `d` (read_restart's layout), plus time, dt
+    and the radiation iteration counts `rad`: what tests/golden/*.json commit of the REFERENCE's dumps that are too large
+    to commit themselves.  A bit-identical run reproduces every hash (-0.0 is folded onto +0.0: equal values, equal bytes)."""
+    import hashlib
+    out = {"time": float(d["time"]).hex(), "dt": float(d["dt"]).hex(), "nstep": int(d["nstep"]), "rad": rad, "levels": []}
+    for g in d["grids"]:
+        lev = {}
+        for v in vars_:
+            a = np.ascontiguousarray(g[v], dtype=np.float64) + 0.0
+            lev[v] = {"shape": list(a.shape), "sha256": hashlib.sha256(a.tobytes()).hexdigest(),
+                      "sum": float(np.nansum(a)), "absmax": float(np.nanmax(np.abs(a))), "nan": int(np.isnan(a).sum())}
+        out["levels"].append(lev)
+    return out

@@ -237,6 +237,62 @@ def reference_arm(args):
 
 
 # ---------------------------------------------------------------------------------------------------------
+# parity gate: before anything is timed, the very path that is about to be timed (same library, same driver, same number
+# of GPUs, NCCL exchange and reductions included) must reproduce the REFERENCE's dump of small cases bit for bit
+# ---------------------------------------------------------------------------------------------------------
+GATE_CASES = {"ioniz_sphere": ["ioniz64s_k2", "blast64s_k4"], "blast": ["blast64s_k4"], "ifront": ["ifront64s_k3"],
+              "ioniz_smr": ["ioniz64s_k2"]}
+
+
+def parity_gate(workload, rank, world, local, dist, riemann=0, order=2):
+    """Runs tests/golden/<case>.json (SHA-256 fingerprints of the reference binary's own dump: 32x32x64 zones, so each of up
+    to 8 x3 slabs keeps 8 layers) through driver.Run on `world` GPUs, gathers the slabs and compares every variable,
+    EdgeFlux, time, dt and the sub-cycle counts.  Returns the dict that goes into the JSON line; the caller exits non-zero
+    unless bit_equal."""
+    import numpy as np
+    import torch
+    from athena_b200.driver import Run
+    from athena_b200.restart import fingerprint
+    out = {"cases": [], "bit_equal": True, "against": "SHA-256 fingerprints of the reference binary's dump (tests/golden/*.json)", "n_gpus": world}
+    if riemann != 0 or order != 2:
+        return {"cases": [], "bit_equal": None, "note": "gate fixtures exist for the shipped configuration (PLM + Roe + H-correction) only"}
+    for name in GATE_CASES[workload]:
+        gold = json.load(open(os.path.join(ROOT, "tests", "golden", name + ".json")))
+        par = ParFile.par_open(os.path.join(DECKS, gold["deck"]))
+        par.par_cmdline(gold["overrides"])
+        R = Run(par, gold["build"], device=local, dist=dist)
+        R.run(gold["nstep"])
+        mine = R.G.download_active()
+        names = [v for v in gold["levels"][0] if v != "edgeflux"]
+        g = {v: mine[v] for v in names}
+        ef = R.G.download_edgeflux() if "edgeflux" in gold["levels"][0] else None
+        if world > 1:
+            loc = torch.from_numpy(np.stack([mine[v] for v in names])).cuda()
+            parts = [torch.empty_like(loc) for _ in range(world)]
+            dist.all_gather(parts, loc)
+            full = torch.cat(parts, dim=1).cpu().numpy()
+            g = {v: full[n] for n, v in enumerate(names)}
+            if ef is not None:      # ray rows of every slab, the last edge row from the top slab
+                e = torch.from_numpy(ef).cuda()
+                eparts = [torch.empty_like(e) for _ in range(world)]
+                dist.all_gather(eparts, e)
+                ef = torch.cat([x[:-1] for x in eparts[:-1]] + [eparts[-1]], dim=0).cpu().numpy()
+        if ef is not None:
+            g["edgeflux"] = ef
+        fp = fingerprint(dict(time=R.time, dt=R.dt, nstep=R.nstep, grids=[g]), [r[0] for r in R.rad_log], vars_=tuple(gold["levels"][0]))
+        bad = [v for v, ref in gold["levels"][0].items() if fp["levels"][0][v]["sha256"] != ref["sha256"]]
+        for k in ("rad", "time", "dt", "nstep"):
+            if fp[k] != gold[k]:
+                bad.append(k)
+        out["cases"].append({"case": name, "bit_equal": not bad, "differing": bad, "exchanges": R.comm.counters["exchanges"] if R.comm else 0})
+        out["bit_equal"] = out["bit_equal"] and not bad
+        R.G.close()
+        if R.comm:
+            R.comm.close()
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------------
 def gpu_arm(args):
@@ -258,6 +314,13 @@ def gpu_arm(args):
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
         d = dist
     assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+
+    parity = parity_gate(args.workload, rank, world, local, d, args.riemann, args.order) if not args.no_parity_gate else None
+    if parity is not None and parity["bit_equal"] is False:
+        if rank == 0:
+            print(json.dumps({"metric": "zone-updates/s per hydro+ion-RT step", "value": None, "n_gpus": world, "parity": parity,
+                              "error": "parity gate failed: nothing was timed"}))
+        raise SystemExit(3)
 
     n = args.n
     nx3_global = n if args.strong else n * world         # --strong: SURVEY 8d cfg 5, the n^3 box cut into `world` x3 slabs
@@ -391,12 +454,53 @@ def gpu_arm(args):
                        "variant": {"order": args.order, "riemann": args.riemann},
                        "ion_iterations_per_step": round(n_iter, 2), "l2": "working set >> L2 (state + scratch = "
                        f"{G.bytes_allocated / 2**30:.1f} GiB per GPU), no flush needed", "setup_s": round(t_setup, 1)},
+            "parity": parity,
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "dropin": dropin, "kernels": ktab,
         }
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def smr_parity_gate(rank, world, local, dist):
+    """The SMR path about to be timed (SmrRun on one GPU, SmrRunSlabs over x3 cut planes on several) on the reference's own
+    2-/3-level dumps (tests/golden/*smr*.npz, written by the reference's --enable-smr binary): every level, EdgeFlux, time,
+    dt and the sub-cycle counts bit for bit."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from smr_cases import SmrCase
+    from athena_b200.driver import SmrRun, SmrRunSlabs
+    out = {"cases": [], "bit_equal": True, "against": "restart dumps of the reference's --enable-smr binary (tests/golden/*.npz)", "n_gpus": world}
+    for name in ("blastsmr_k4", "ifrontsmr_k3", "ifrontsmr3_k3"):
+        case = SmrCase(name)
+        U0 = [lv["U0"] for lv in case.levels]
+        try:
+            R = SmrRunSlabs(case.par, case.build0, U0, dist, device=local) if world > 1 else SmrRun(case.par, case.build0, *U0, device=local)
+        except ValueError as e:          # the cut planes of this many ranks cannot serve this small nest (smr_slab_layout's rules)
+            out["cases"].append({"case": name, "bit_equal": None, "skipped": str(e)})
+            continue
+        R.run(case.nsteps)
+        bad = []
+        for n in range(case.nlevels):
+            if world > 1:
+                got = R.gather_level(n)
+                ef = R.gather_level(n, "edgeflux") if R.ion else None
+            else:
+                got = R.grids[n].download_active()
+                ef = R.grids[n].download_edgeflux() if R.ion else None
+            for v in got:
+                if not np.array_equal(got[v], case.levels[n]["U1"][v], equal_nan=True):
+                    bad.append(f"L{n}:{v}")
+            if ef is not None and not np.array_equal(ef[:-1], case.levels[n]["edgeflux1"][:-1]):
+                bad.append(f"L{n}:edgeflux")
+        if R.time != float(case.gold["time1"]) or R.dt != float(case.gold["dt1"]):
+            bad.append("time/dt")
+        if case.ion and [list(r[:3]) for r in R.rad_log] != [[int(x) for x in r[:3]] for r in case.gold["rad"]]:
+            bad.append("rad")
+        out["cases"].append({"case": name, "bit_equal": not bad, "differing": bad})
+        out["bit_equal"] = out["bit_equal"] and not bad
+    return out
 
 
 def smr_arm(args):
@@ -414,10 +518,17 @@ def smr_arm(args):
     nlev = par.par_geti("job", "num_domains")
     zones_total = sum(par.par_geti(f"domain{n + 1}", "Nx1") * par.par_geti(f"domain{n + 1}", "Nx2") * par.par_geti(f"domain{n + 1}", "Nx3")
                       for n in range(nlev))
-    t_setup = time.time()
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    parity = smr_parity_gate(rank, world, local, dist) if not args.no_parity_gate else None
+    if parity is not None and parity["bit_equal"] is False:
+        if rank == 0:
+            print(json.dumps({"metric": "zone-updates/s per hydro+ion-RT step", "value": None, "n_gpus": world, "parity": parity,
+                              "error": "parity gate failed: nothing was timed"}))
+        raise SystemExit(3)
+    t_setup = time.time()
+    if world > 1:
         R = SmrRunSlabs(par, "ioniz_sphere", None, dist, device=local, cuts="balanced")
         grids = [L["G"] for L in R.levels if L is not None]
         cuts = R.cuts
@@ -466,7 +577,7 @@ def smr_arm(args):
                 "config": {"workload": f"configs[3] ioniz_sphere SMR, shipped 5-level deck {zones_total} zones, steps {args.warmup}..{args.warmup + args.steps} from t=0",
                            "parallelism": f"x3 cut planes at root layers {cuts}", "ion_iterations_per_level_step": round(n_iter, 2),
                            "l2": "working set >> L2, no flush needed", "setup_s": round(t_setup, 1)},
-                "e2e": None, "gpu_launches": int(launches), "clocks": clocks,
+                "parity": parity, "e2e": None, "gpu_launches": int(launches), "clocks": clocks,
                 "roofline": {"bound": "hbm", "kernel": "whole step", "achieved": round(value / world * b_alg / 1e9, 1), "peak": peak, "unit": "GB/s",
                              "frac": round(value / world * b_alg / 1e9 / peak, 4), "traffic": None, "peak_source": peak_src,
                              "note": "whole step at SURVEY 8(d) compulsory bytes per GPU; per-kernel rooflines are those of the unigrid workload"},
@@ -492,6 +603,7 @@ def main():
     ap.add_argument("--cpu-n", type=int, default=64, help="grid of the bounded CPU sample")
     ap.add_argument("--cpu-steps", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-gate", action="store_true", help="skip the bit-exact check against the reference's fingerprints before the timed region")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         print("bench.py: note: fewer than 3 warm-up steps", file=sys.stderr)

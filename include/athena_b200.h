@@ -163,29 +163,34 @@ int ab2_profile_kernels(void);
 const char* ab2_profile_kernel_name(int id);
 int ab2_profile_read(ab2_grid* g, double* ms, long long* counts, int reset);
 
-/* ---- function-level entry points (parity tests): rows of 6 doubles, host arrays ------------------------- */
-/* fluxes() of rsolvers/roe.c:59-336 (+ hlle.c fallback) on n independent interfaces */
-int ab2_unit_roe_flux(int n, const double* Ul, const double* Ur, const double* Wl, const double* Wr,
-                      int nscal, double gamma, const double* etah, double* F);
-/* Cons1D_to_Prim1D / Prim1D_to_Cons1D / cfast (convert_var.c:389-499); cfast_out may be NULL */
-int ab2_unit_convert(int n, const double* in, int nscal, double gamma, int to_prim, double* out, double* cfast_out);
-/* a/b and sqrt(a) through the engine's branch-free IEEE refinement (csrc/physics.cuh Arith<true>, plain operators where
- * its range test rejects the operands) next to the plain operators; nrejected[2] = rejected divisions, square roots */
-int ab2_unit_ieee(int n, const double* a, const double* b, double* q_fast, double* q_exact, double* s_fast, double* s_exact, int* nrejected);
-/* exp(x[i]) and pow(y[i], x[i]) as the ion kernels evaluate them (csrc/glibc_math.cuh: the host glibc's algorithms) */
-int ab2_unit_libm(int n, const double* x, const double* y, double* exp_x, double* pow_y_x);
-/* lr_states() of reconstruction/lr_states_plm.c:62-374 on npencil pencils of n cells */
-int ab2_unit_lr_states(int npencil, int n, const double* W, int nscal, double gamma, double dt, double dx,
-                       int il, int iu, double* Wl, double* Wr);
-/* the same with steps 8-9 in the form an HLLE/HLLC/HLLD build compiles (lr_states_plm.c:257-293) */
-int ab2_unit_lr_states_hll(int npencil, int n, const double* W, int nscal, double gamma, double dt, double dx,
-                           int il, int iu, double* Wl, double* Wr);
-/* lr_states() of reconstruction/lr_states_ppm.c:67-651; hll != 0: steps 18-19 in the form an HLL-family build compiles */
-int ab2_unit_lr_states_ppm(int npencil, int n, const double* W, int nscal, double gamma, double dt, double dx,
-                           int il, int iu, int hll, double* Wl, double* Wr);
-/* fluxes() of rsolvers/hllc.c:50-261 on n independent interfaces */
-int ab2_unit_hllc_flux(int n, const double* Ul, const double* Ur, const double* Wl, const double* Wr,
-                       int nscal, double gamma, double* F);
+/* ---- more than one GPU: NCCL inside the library ------------------------------------------------------------
+ * One process per GPU, one ab2_comm per set of Grids that exchange ghost zones and reduce together (the Grids of a
+ * Domain cut into x3 slabs: NGrid_x1 = NGrid_x2 = 1, NGrid_x3 = ranks, rays run along x1 and are never cut).  The
+ * driver creates the 128-byte id on one rank, distributes it the way it distributes everything else (MPI_Bcast in
+ * main.c's MPI build; torch.distributed in the Python host) and every rank calls ab2_comm_init_rank.  libnccl is
+ * dlopen'ed at the first of these calls. */
+typedef struct ab2_comm ab2_comm;
+#define AB2_UNIQUE_ID_BYTES 128
+int ab2_comm_get_unique_id(char id[AB2_UNIQUE_ID_BYTES]);                       /* ncclGetUniqueId                      */
+ab2_comm* ab2_comm_init_rank(int nranks, int rank, const char id[AB2_UNIQUE_ID_BYTES], int device);   /* MPI_Comm_create */
+void ab2_comm_destroy(ab2_comm* c);
+int ab2_comm_rank(const ab2_comm* c);
+int ab2_comm_size(const ab2_comm* c);
+long long ab2_comm_exchanges(const ab2_comm* c);
+long long ab2_comm_reductions(const ab2_comm* c);
+/* MPI_Allreduce of n <= 64 host doubles, op 0 MIN / 1 MAX / 2 SUM (new_dt.c:175-179 for meshes whose dt the driver
+ * combines itself; main.c:725-734 zone-cycle totals) and MPI_Bcast of <= 512 raw bytes */
+int ab2_comm_allreduce(ab2_comm* c, double* vals, int n, int op);
+int ab2_comm_bcast(ab2_comm* c, void* data, int nbytes, int root);
+/* Attach a Grid to its communicator with its x3 neighbours (GridS.lx3_id / rx3_id, init_grid.c:253-283; -1 where the
+ * face is a physical boundary or a fine/coarse boundary).  From then on ab2_bvals_mhd also exchanges the 4 ghost layers
+ * at those faces (bvals_mhd.c:423-446: ncclSend/ncclRecv of the contiguous SoA slabs, in place, one NCCL group),
+ * ab2_max_wave_speeds / ab2_new_dt return the maximum over all ranks (new_dt.c:175-179) and the ion sub-cycle combines
+ * its scalars over all ranks with one all-gather per iteration (ionrad_3d.c:275,399,554,672); the `reduce` callbacks
+ * of those entry points are then passed NULL.  c = NULL detaches. */
+int ab2_grid_set_comm(ab2_grid* g, ab2_comm* c, int lo_rank, int hi_rank);
+/* the exchange alone (SMR across GPUs: parent cells rewritten by ionradRestrictCorrect after that level's bvals_mhd) */
+int ab2_exchange_x3(ab2_grid* g);
 
 #ifdef __cplusplus
 }

@@ -5,6 +5,7 @@ fingerprints are committed; same scheme as make_hires5_fingerprint.py):
     ioniz256_k1  configs[2]: ioniz_sphere unigrid 256^3, 1 step   (oracle/_ref/ioniz_sphere, ~2 min of one core, 11 GB)
     blast256_k2  configs[1]: blast 256^3 periodic, 2 steps        (oracle/_ref/blast)
     ifront64_k30 configs[0]: ifront 64^3 as shipped, 30 steps     (oracle/_ref/ifront)
+    ioniz64s_k2 / blast64s_k4 / ifront64s_k3: 32x32x64 grids for the multi-GPU parity gate inside bench.py
 
 A bit-identical run reproduces every hash (tests/test_gpu_longrun.py).   python tests/golden/make_fullsize_fingerprint.py
 """
@@ -25,6 +26,11 @@ CASES = {
     "ioniz256_k1": ("ioniz_sphere", "ioniz_sphere.athinput", 1, N256),
     "blast256_k2": ("blast", "blast.athinput", 2, N256),
     "ifront64_k30": ("ifront", "ifront.athinput", 30, ["job/num_domains=1"]),      # configs[0]: the deck as shipped, 64^3
+    # the parity gate bench.py runs before every timed region, on 1/2/4/8 GPUs: Nx3 = 64 gives every one of 8 x3 slabs
+    # 8 layers (two ghost widths); seconds of one core
+    "ioniz64s_k2": ("ioniz_sphere", "ioniz_sphere.athinput", 2, ["job/num_domains=1", "domain1/Nx1=32", "domain1/Nx2=32", "domain1/Nx3=64"]),
+    "blast64s_k4": ("blast", "blast.athinput", 4, ["job/num_domains=1", "domain1/Nx1=32", "domain1/Nx2=32", "domain1/Nx3=64", "problem/radius=0.25"]),
+    "ifront64s_k3": ("ifront", "ifront.athinput", 3, ["job/num_domains=1", "domain1/Nx1=32", "domain1/Nx2=32", "domain1/Nx3=64"]),
 }
 
 

@@ -8,7 +8,6 @@ conserved variable and of EdgeFlux on every level, plus time, dt, the radiation 
 
     python tests/golden/make_hires5_fingerprint.py [K=1] [existing_dump.rst]
 """
-import hashlib
 import json
 import os
 import re
@@ -30,15 +29,8 @@ VARS = ("d", "M1", "M2", "M3", "E", "s", "edgeflux")
 
 
 def fingerprint(d, rad, vars_=VARS):
-    out = {"time": float(d["time"]).hex(), "dt": float(d["dt"]).hex(), "nstep": int(d["nstep"]), "rad": rad, "levels": []}
-    for g in d["grids"]:
-        lev = {}
-        for v in vars_:
-            a = np.ascontiguousarray(g[v], dtype=np.float64) + 0.0      # -0.0 -> +0.0: equal values, equal bytes
-            lev[v] = {"shape": list(a.shape), "sha256": hashlib.sha256(a.tobytes()).hexdigest(),
-                      "sum": float(np.nansum(a)), "absmax": float(np.nanmax(np.abs(a))), "nan": int(np.isnan(a).sum())}
-        out["levels"].append(lev)
-    return out
+    from athena_b200.restart import fingerprint as fp
+    return fp(d, rad, vars_=vars_)
 
 
 def main():

@@ -23,6 +23,14 @@ def test_library_exports_every_declared_symbol():
     L = C.CDLL(engine.LIB_PATH)
     for s in sorted(declared):
         assert hasattr(L, s), s
+    assert not any(s.startswith("ab2_unit_") for s in declared), "test hooks do not belong in the bound interface"
+    # the function-level test hooks live in their own header and library
+    uhdr = open(os.path.join(ROOT, "include", "athena_b200_units.h")).read()
+    udecl = set(re.findall(r"\b(ab2_unit_[a-z0-9_]+)\s*\(", uhdr))
+    assert set(engine.UNIT_EXPORTS) == udecl
+    U = C.CDLL(engine.UNITS_LIB_PATH)
+    for s in sorted(udecl):
+        assert hasattr(U, s), s
     L.ab2_version.restype = C.c_char_p
     assert b"sm_100a" in L.ab2_version()
 

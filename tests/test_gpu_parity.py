@@ -28,7 +28,7 @@ def P(a):
 @pytest.mark.parametrize("nscal", [0, 1])
 def test_units_bit_exact(nscal):
     """fluxes(), lr_states(), Cons1D_to_Prim1D, Prim1D_to_Cons1D, cfast vs the reference's own objects."""
-    L = engine().lib()
+    L = engine().units()
     g = load_golden(f"units_nscal{nscal}")
     gam = float(g["gamma"])
     c = lambda k: np.ascontiguousarray(g[k])
@@ -55,7 +55,7 @@ def test_fast_ieee_division_and_sqrt_are_correctly_rounded():
     """Arith<true> (branch-free MUFU + FMA refinement) must return the bits of a/b and sqrt(a) for every operand its
     range test accepts; rejected operands go through the plain operators.  4e6 operand pairs over 600 binades plus
     the special values."""
-    L = engine().lib()
+    L = engine().units()
     rng = np.random.default_rng(7)
     n = 1 << 22
     a = rng.uniform(1, 2, n) * 2.0 ** rng.integers(-300, 300, n) * rng.choice([-1.0, 1.0], n)
@@ -80,7 +80,7 @@ def test_glibc_math_matches_host_libm_bit_for_bit():
     the path produces: exp(-tau), exp(-118348/T), pow(T/1e4,-0.7), pow(T,-0.89), plus wide random ranges."""
     import ctypes.util
     import math
-    L = engine().lib()
+    L = engine().units()
     rng = np.random.default_rng(11)
     n = 1 << 21
     x = np.concatenate([-10.0 ** rng.uniform(-12, 3.2, n // 4), rng.uniform(-745, 709, n // 4),
@@ -118,7 +118,7 @@ def rel_err(a, b):
 def test_hllc_units_bit_exact(nscal):
     """rsolvers/hllc.c fluxes() and the HLL-family form of PLM steps 8-9, against the reference's own objects"""
     g = load_units("hllc_", nscal)
-    L = engine().lib()
+    L = engine().units()
     gam = float(g["gamma"])
     n = len(g["Wl"])
     c = lambda k: np.ascontiguousarray(g[k])
@@ -139,7 +139,7 @@ def test_ppm_units_bit_exact(tag, nscal, hll):
     """reconstruction/lr_states_ppm.c (the reference's object built with THIRD_ORDER_CHAR) on the seeded pencils, incl. the
     passive scalar as the reference's aliased work arrays treat it, and the HLL-family form of the tracing"""
     g = load_units(tag, nscal)
-    L = engine().lib()
+    L = engine().units()
     il, iu = int(g["pencil_il"]), int(g["pencil_iu"])
     Wp = np.ascontiguousarray(g["pencil_W"])
     npen, m = Wp.shape[:2]
