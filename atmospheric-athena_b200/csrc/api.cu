@@ -33,24 +33,33 @@ static double* dev_alloc(ab2_grid* h, size_t ndouble, bool zero = true)
 // ---------------------------------------------------------------------------------------------------
 // AoS (ConsS) <-> SoA transposition on the device
 // ---------------------------------------------------------------------------------------------------
-__global__ void k_aos_to_soa(GridDev g, int nvar, long ncell, const double* aos)
+// `aos` holds cells [c0, c0+ncell) of the Grid.  Each block moves 256 cells through shared memory so that both the AoS side
+// (256*nvar consecutive doubles) and the SoA side (256 consecutive doubles per variable) are written and read unit-stride;
+// the plain per-thread form strides the AoS side by 48 B and reaches 46 % of the DRAM throughput.
+__global__ void __launch_bounds__(256) k_aos_to_soa(GridDev g, int nvar, long c0, long ncell, const double* aos)
 {
-  const long t = (long)blockIdx.x*blockDim.x + threadIdx.x;
-  if (t >= ncell) return;
-  for (int v=0; v<nvar; v++) g.U[v][t] = aos[t*nvar + v];
+  __shared__ double tile[256*AB2_NVAR];
+  const long b0 = (long)blockIdx.x*256;
+  const long nc = (ncell - b0 < 256) ? ncell - b0 : 256;
+  for (long t = threadIdx.x; t < nc*nvar; t += 256) tile[t] = aos[b0*nvar + t];
+  __syncthreads();
+  if (threadIdx.x < nc) for (int v=0; v<nvar; v++) g.U[v][c0 + b0 + threadIdx.x] = tile[threadIdx.x*nvar + v];
 }
-__global__ void k_soa_to_aos(GridDev g, int nvar, long ncell, double* aos)
+__global__ void __launch_bounds__(256) k_soa_to_aos(GridDev g, int nvar, long c0, long ncell, double* aos)
 {
-  const long t = (long)blockIdx.x*blockDim.x + threadIdx.x;
-  if (t >= ncell) return;
-  for (int v=0; v<nvar; v++) aos[t*nvar + v] = g.U[v][t];
+  __shared__ double tile[256*AB2_NVAR];
+  const long b0 = (long)blockIdx.x*256;
+  const long nc = (ncell - b0 < 256) ? ncell - b0 : 256;
+  if (threadIdx.x < nc) for (int v=0; v<nvar; v++) tile[threadIdx.x*nvar + v] = g.U[v][c0 + b0 + threadIdx.x];
+  __syncthreads();
+  for (long t = threadIdx.x; t < nc*nvar; t += 256) aos[b0*nvar + t] = tile[t];
 }
 
 static const char* KERNEL_NAMES[KID_N] = {
   "k_bvals", "k_max_speeds", "k_first_x1", "k_first_march<1>", "k_first_march<2>", "k_dhalf",
   "k_correct<0>", "k_correct<1>", "k_correct<2>", "k_final<0>", "k_final<1>", "k_final<2>", "k_update",
   "k_apply_fixed", "k_ion_prep", "k_ion_rates", "k_ion_update", "k_bvals_ionrad", "k_transpose",
-  "k_smr_restrict", "k_smr_flux_correct", "k_smr_prolongate", "k_ion_rates<fused update>" };
+  "k_smr_restrict", "k_smr_flux_correct", "k_smr_prolongate", "k_ion_rates<fused update>", "k_cfinal" };
 
 cudaEvent_t ab2_prof_event(ab2_grid* h)
 {
@@ -71,7 +80,40 @@ static void prof_drain(ab2_grid* h)
   h->prof_pending.clear();
 }
 
+int ab2_alloc_scratch(ab2_grid* h, int planes)
+{
+  GridDev& g = h->g;
+  const int nvar = 5 + h->nscal;
+  if (planes < 0 || (planes > 0 && planes < 4)) { ab2_set_error("[ab2_set_scratch_planes]: 0 (whole Grid) or at least 4 planes per chunk"); return -1; }
+  if (planes >= g.nx[2]) planes = 0;
+  if (planes > 0 && !h->own_U) { ab2_set_error("[ab2_set_scratch_planes]: chunked scratch needs library-owned U"); return -1; }
+  const size_t P = (size_t)g.n[0]*g.n[1];
+  const size_t depth = planes ? (size_t)(planes + 2*AB2_NG) : (size_t)g.n[2];
+  size_t nd = (size_t)(12*nvar + 3)*depth*P;
+  if (planes) nd += (size_t)nvar*depth*P + (size_t)nvar*AB2_NG*P;      // staged copy of the chunk's U^n, carry planes
+  if (h->scratch) { cudaStreamSynchronize(h->stream); cudaFree(h->scratch); h->bytes_allocated -= h->scratch_doubles*sizeof(double); h->scratch = nullptr; }
+  void* p = nullptr;
+  if (!ab2_check(cudaMalloc(&p, nd*sizeof(double)), "cudaMalloc CTU scratch")) return -1;
+  if (!ab2_check(cudaMemsetAsync(p, 0, nd*sizeof(double), h->stream), "cudaMemset CTU scratch")) return -1;
+  h->scratch = (double*)p; h->scratch_doubles = nd; h->chunk_planes = planes;
+  h->bytes_allocated += nd*sizeof(double);
+  const size_t na = depth*P;
+  size_t off = 0;
+  for (int dir=0; dir<3; dir++) for (int v=0; v<nvar; v++) { g.Ul[dir][v] = h->scratch + off; off += na; }
+  for (int dir=0; dir<3; dir++) for (int v=0; v<nvar; v++) { g.Ur[dir][v] = h->scratch + off; off += na; }
+  for (int dir=0; dir<3; dir++) for (int v=0; v<nvar; v++) { g.F[dir][v] = h->scratch + off; off += na; }
+  for (int dir=0; dir<3; dir++) for (int v=0; v<nvar; v++) { g.Ff[dir][v] = h->scratch + off; off += na; }
+  for (int dir=0; dir<3; dir++) { g.eta[dir] = h->scratch + off; off += na; }
+  for (int v=0; v<nvar; v++) g.Uin[v] = g.U[v];
+  return 0;
+}
+
 extern "C" {
+
+/* x3-chunked CTU scratch (the reference sizes its scratch to the whole Grid, integrate_3d_ctu.c:3374-3472): planes = active
+ * x3 planes per chunk, 0 = whole Grid.  Results do not depend on it. */
+int ab2_set_scratch_planes(ab2_grid* h, int planes) { return ab2_alloc_scratch(h, planes); }
+int ab2_scratch_planes(const ab2_grid* h) { return h->chunk_planes; }
 
 int ab2_profile_enable(ab2_grid* h, int on)
 {
@@ -144,14 +186,30 @@ ab2_grid* ab2_grid_create(const ab2_grid_desc* d)
     g.U[v] = h->own_U ? dev_alloc(h, ncell) : d->external_U[v];
     if (!g.U[v]) { ab2_set_error(h->own_U ? g_err : std::string("[ab2_grid_create]: external_U incomplete")); ab2_grid_destroy(h); return nullptr; }
   }
-  // CTU scratch: 9 state arrays of nvar components in one slab (also the staging area of the AoS transposes)
-  double* slab = dev_alloc(h, (size_t)9*nvar*ncell);
-  if (!slab) { ab2_grid_destroy(h); return nullptr; }
-  size_t off = 0;
-  for (int dir=0; dir<3; dir++) for (int v=0; v<nvar; v++) { g.Ul[dir][v] = slab + off; off += ncell; }
-  for (int dir=0; dir<3; dir++) for (int v=0; v<nvar; v++) { g.Ur[dir][v] = slab + off; off += ncell; }
-  for (int dir=0; dir<3; dir++) for (int v=0; v<nvar; v++) { g.F[dir][v] = slab + off; off += ncell; }
-  for (int dir=0; dir<3; dir++) { g.eta[dir] = dev_alloc(h, ncell); if (!g.eta[dir]) { ab2_grid_destroy(h); return nullptr; } }
+  // CTU scratch (also the staging area of the AoS transposes).  AB2_CHUNK_PLANES=n forces x3 chunks of n active planes;
+  // by default the scratch spans the whole Grid when that leaves room for the rest of the Grid's arrays, else it is chunked.
+  h->scratch = nullptr; h->scratch_doubles = 0; h->chunk_planes = 0;
+  h->fuse = 1;
+  if (const char* env = getenv("AB2_HYDRO_FUSE")) h->fuse = (atoi(env) != 0);
+  {
+    int planes = 0;
+    if (const char* env = getenv("AB2_CHUNK_PLANES")) planes = atoi(env);
+    else {
+      size_t free_b = 0, total_b = 0;
+      cudaMemGetInfo(&free_b, &total_b);
+      const size_t P = (size_t)g.n[0]*g.n[1]*sizeof(double);
+      const size_t rest = (size_t)34*ncell*sizeof(double);        // ion arrays, potential tables, dhalf still to come (upper estimate)
+      const size_t full = (size_t)(12*nvar + 3)*ncell*sizeof(double);
+      if (full + rest > (size_t)(0.92*(double)free_b)) {
+        const double avail = 0.92*(double)free_b - (double)rest;
+        long depth = (long)(avail/((double)(13*nvar + 3)*(double)P));       // 12 nvar + 3 scratch arrays + the staged copy of U
+        planes = (int)(depth - 2*AB2_NG);
+        planes -= planes % 8;
+        if (planes < 8) { ab2_set_error("[ab2_grid_create]: not enough device memory for even an 8-plane chunk of CTU scratch"); ab2_grid_destroy(h); return nullptr; }
+      }
+    }
+    if (ab2_alloc_scratch(h, planes) != 0) { ab2_grid_destroy(h); return nullptr; }
+  }
 
   void* p = nullptr;
   if (!ab2_check(cudaMalloc(&p, SC_N*sizeof(unsigned long long)), "cudaMalloc scalars")) { ab2_grid_destroy(h); return nullptr; }
@@ -169,6 +227,7 @@ void ab2_grid_destroy(ab2_grid* h)
   if (!h) return;
   cudaSetDevice(h->device);
   prof_drain(h);
+  if (h->scratch) cudaFree(h->scratch);
   for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
   for (void* p : h->allocs) cudaFree(p);
   if (h->h_scal) cudaFreeHost(h->h_scal);
@@ -183,14 +242,19 @@ int ab2_synchronize(ab2_grid* h) { CK(cudaStreamSynchronize(h->stream), "synchro
 double* ab2_device_ptr(ab2_grid* h, int var) { return (var >= 0 && var < 5+h->nscal) ? h->g.U[var] : nullptr; }
 
 // ---- coherence ----------------------------------------------------------------------------------------
+// The transposes stage through the CTU scratch (dead between steps), in x3 slabs sized to it.
 int ab2_upload_cons_aos(ab2_grid* h, const double* U_aos)
 {
   GridDev& g = h->g;
-  const long ncell = (long)g.n[0]*g.n[1]*g.n[2];
   const int nvar = 5 + h->nscal;
-  double* stage = g.Ul[0][0];      // scratch slab is dead between steps
-  CK(cudaMemcpyAsync(stage, U_aos, (size_t)ncell*nvar*sizeof(double), cudaMemcpyHostToDevice, h->stream), "upload aos");
-  AB2_LAUNCH(h, KID_TRANSPOSE, (k_aos_to_soa<<<(unsigned)((ncell+255)/256), 256, 0, h->stream>>>(g, nvar, ncell, stage)));
+  const long P = (long)g.n[0]*g.n[1];
+  long slab = (long)(h->scratch_doubles/((size_t)P*nvar)); if (slab > g.n[2]) slab = g.n[2];
+  for (long k0 = 0; k0 < g.n[2]; k0 += slab) {
+    const long nk = (k0 + slab <= g.n[2]) ? slab : g.n[2] - k0;
+    const long ncell = nk*P;
+    CK(cudaMemcpyAsync(h->scratch, U_aos + (size_t)k0*P*nvar, (size_t)ncell*nvar*sizeof(double), cudaMemcpyHostToDevice, h->stream), "upload aos");
+    AB2_LAUNCH(h, KID_TRANSPOSE, (k_aos_to_soa<<<(unsigned)((ncell+255)/256), 256, 0, h->stream>>>(g, nvar, k0*P, ncell, h->scratch)));
+  }
   CK(cudaStreamSynchronize(h->stream), "upload aos sync");
   return 0;
 }
@@ -198,11 +262,15 @@ int ab2_upload_cons_aos(ab2_grid* h, const double* U_aos)
 int ab2_download_cons_aos(ab2_grid* h, double* U_aos)
 {
   GridDev& g = h->g;
-  const long ncell = (long)g.n[0]*g.n[1]*g.n[2];
   const int nvar = 5 + h->nscal;
-  double* stage = g.Ul[0][0];
-  AB2_LAUNCH(h, KID_TRANSPOSE, (k_soa_to_aos<<<(unsigned)((ncell+255)/256), 256, 0, h->stream>>>(g, nvar, ncell, stage)));
-  CK(cudaMemcpyAsync(U_aos, stage, (size_t)ncell*nvar*sizeof(double), cudaMemcpyDeviceToHost, h->stream), "download aos");
+  const long P = (long)g.n[0]*g.n[1];
+  long slab = (long)(h->scratch_doubles/((size_t)P*nvar)); if (slab > g.n[2]) slab = g.n[2];
+  for (long k0 = 0; k0 < g.n[2]; k0 += slab) {
+    const long nk = (k0 + slab <= g.n[2]) ? slab : g.n[2] - k0;
+    const long ncell = nk*P;
+    AB2_LAUNCH(h, KID_TRANSPOSE, (k_soa_to_aos<<<(unsigned)((ncell+255)/256), 256, 0, h->stream>>>(g, nvar, k0*P, ncell, h->scratch)));
+    CK(cudaMemcpyAsync(U_aos + (size_t)k0*P*nvar, h->scratch, (size_t)ncell*nvar*sizeof(double), cudaMemcpyDeviceToHost, h->stream), "download aos");
+  }
   CK(cudaStreamSynchronize(h->stream), "download aos sync");
   return 0;
 }

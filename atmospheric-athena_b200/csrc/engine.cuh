@@ -39,10 +39,14 @@ struct GridDev {
   int order;                 // lr_states(): 2 = PLM (lr_states_plm.c), 3 = PPM (lr_states_ppm.c), the reference's --with-order
   int riemann;               // fluxes() of the build being replaced: 0 Roe + H-correction (roe.c), 1 HLLC (hllc.c), 2 Roe without H-correction
   double* U[AB2_NVAR];       // conserved state, SoA [n3][n2][n1]
+  const double* Uin[AB2_NVAR]; // what the integrator READS: U itself, or (x3-chunked scratch) a copy of the chunk's planes of U^n
+  // CTU scratch.  Whole-grid arrays, or -- when the scratch is chunked along x3 -- arrays that hold only the planes of the
+  // current chunk (+4 either side) with their base pointers shifted so that the cell index c of U addresses them too.
   double* Ul[3][AB2_NVAR];   // face states, PHYSICAL component order (d,M1,M2,M3,E,s), one set per face direction
   double* Ur[3][AB2_NVAR];
-  double* F[3][AB2_NVAR];    // fluxes, physical component order
-  double* eta[3];
+  double* F[3][AB2_NVAR];    // first-pass fluxes, physical component order
+  double* Ff[3][AB2_NVAR];   // final fluxes (integrate_3d_ctu.c step 9; what step 11-12 and the SMR flux correction read)
+  double* eta[3];            // only the unfused correct/final pair goes through these
   double* dhalf;
   const double* phi[PHI_NTAB];
 };
@@ -81,7 +85,7 @@ enum {
   KID_BVALS = 0, KID_MAX_SPEEDS, KID_FIRST_X1, KID_FIRST_X2, KID_FIRST_X3, KID_DHALF,
   KID_CORRECT_X1, KID_CORRECT_X2, KID_CORRECT_X3, KID_FINAL_X1, KID_FINAL_X2, KID_FINAL_X3, KID_UPDATE,
   KID_APPLY_FIXED, KID_ION_PREP, KID_ION_RATES, KID_ION_UPDATE, KID_BVALS_IONRAD, KID_TRANSPOSE,
-  KID_SMR_RESTRICT, KID_SMR_FLUXCORR, KID_SMR_PROLONG, KID_ION_FUSED, KID_N
+  KID_SMR_RESTRICT, KID_SMR_FLUXCORR, KID_SMR_PROLONG, KID_ION_FUSED, KID_CFINAL, KID_N
 };
 struct ProfPending { int id; cudaEvent_t a, b; };
 
@@ -101,6 +105,10 @@ struct ab2_grid {
   IonDev ion;
   int maxiter;
   double tcoarse;                  // ionrad_3d.c:1028: dt_done of the last root-level radiation call
+  double* scratch;                 // one allocation behind Ul/Ur/F/Ff/eta (and Uin, carry when chunked)
+  size_t scratch_doubles;
+  int chunk_planes;                // 0: scratch spans the whole Grid; else active x3 planes per chunk (scratch depth = that + 8)
+  int fuse;                        // 1: k_cfinal (correct + eta + final fused), 0: k_correct / k_final pair
   long n_fixed;                    // Userwork_in_loop replay table
   long* d_fixed_cells;
   double* d_fixed_vals;
@@ -134,6 +142,8 @@ bool ab2_check(cudaError_t e, const char* what);
 // comm.cu
 int comm_exchange_x3(ab2_grid* h);
 int comm_read_scalars(ab2_grid* h);
+// api.cu: (re)allocate the CTU scratch for `planes` active x3 planes per chunk (0 = whole Grid)
+int ab2_alloc_scratch(ab2_grid* h, int planes);
 // hydro.cu
 int hydro_bvals(ab2_grid* h, const int bc[6]);
 int hydro_max_speeds(ab2_grid* h, double out[3]);

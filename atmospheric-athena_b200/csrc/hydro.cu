@@ -14,9 +14,15 @@
 //   A  k_first_x1 / k_first_march<1|2> : U -> first-pass face states Ul,Ur + fluxes F     (steps 1-3)
 //      (PPM: k_ppm_slope / k_ppm_states / k_ppm_flux per direction instead)
 //   B  k_dhalf                         : d^{n+1/2} from first-pass fluxes (static potential only, step 8a)
-//   C  k_correct<0|1|2>                : transverse flux-gradient + gravity corrections of Ul,Ur, eta (steps 5-7, 9a)
-//   D  k_final<0|1|2>                  : etah = max of 9 etas, Riemann flux from corrected states (step 9b-d)
+//   CD k_cfinal                        : ONE kernel for steps 5-7 and 9: a (32 x 8) tile of cells marches along x3; per plane
+//                                        the transverse flux-gradient + gravity corrections of the L/R states of all three
+//                                        face directions and their eta go to a shared-memory tile (1-cell halo recomputed),
+//                                        etah = max of 9 etas comes from that tile, then the Riemann flux.  Corrected states
+//                                        and eta never touch HBM.  (AB2_HYDRO_FUSE=0: the unfused pair k_correct / k_final,
+//                                        which writes corrected states and eta to HBM and reads them back.)
 //   E  k_update                        : gravity source (11a) + three ordered flux-difference updates (12a-c)
+// The scratch (Ul,Ur,F,Ff) may be chunked along x3 (ab2_alloc_scratch): passes A-E then run chunk by chunk on scratch that
+// holds only the chunk's planes, reading U^n from a staged copy so that a chunk's update cannot disturb its neighbour's input.
 #include "engine.cuh"
 #include "physics.cuh"
 
@@ -30,7 +36,7 @@
 // ---------------------------------------------------------------------------------------------------
 // sweep-order <-> physical-order register shuffles
 // ---------------------------------------------------------------------------------------------------
-template <int DIR, int NS> __device__ __forceinline__ S6 load_sweep(double* const* A, long c)
+template <int DIR, int NS> __device__ __forceinline__ S6 load_sweep(const double* const* A, long c)
 {
   S6 r;
   r.d = A[0][c];
@@ -80,7 +86,7 @@ template <int DIR, int NS> __device__ __forceinline__ S6 sweep_from_phys(const d
 #define AB2_LB_UPDATE 5
 #endif
 template <int NS, bool GRAV, int A1_T>
-__global__ void __launch_bounds__(A1_T, (AB2_LB_FIRST_X1*128)/A1_T) k_first_x1(GridDev g, double dt)
+__global__ void __launch_bounds__(A1_T, (AB2_LB_FIRST_X1*128)/A1_T) k_first_x1(GridDev g, double dt, int klo)
 {
   constexpr int A1_F = A1_T-3;
   __shared__ double sW[6][A1_T];
@@ -89,13 +95,13 @@ __global__ void __launch_bounds__(A1_T, (AB2_LB_FIRST_X1*128)/A1_T) k_first_x1(G
   const int il = NG-2, iu = g.nx[0]+NG+1;
   const int f0 = il+1 + blockIdx.x*A1_F;
   const int c = f0 - 2 + t;
-  const int j = NG-2 + blockIdx.y, k = NG-2 + blockIdx.z;
+  const int j = NG-2 + blockIdx.y, k = klo + blockIdx.z;
   const long row = (long)k*g.st[2] + (long)j*g.st[1];
   const double dtodx = dt/g.dx[0];
 
   S6 W0;
   if (c <= iu+1) {
-    S6 U = load_sweep<0,NS>(g.U, row+c);
+    S6 U = load_sweep<0,NS>(g.Uin, row+c);
     AB2_GUARDED(W0 = cons_to_prim<NS>(U, g.Gamma_1, ar));
     sW[0][t] = W0.d; sW[1][t] = W0.x; sW[2][t] = W0.y; sW[3][t] = W0.z; sW[4][t] = W0.e; sW[5][t] = W0.s;
   }
@@ -132,16 +138,16 @@ __global__ void __launch_bounds__(A1_T, (AB2_LB_FIRST_X1*128)/A1_T) k_first_x1(G
 // 3-cell sliding window of primitives in registers; the left state of the next face is carried over.
 // ---------------------------------------------------------------------------------------------------
 template <int DIR, int NS, bool GRAV>
-__global__ void __launch_bounds__(128, AB2_LB_FIRST) k_first_march(GridDev g, double dt, int seg)
+__global__ void __launch_bounds__(128, AB2_LB_FIRST) k_first_march(GridDev g, double dt, int seg, int olo, int ocount, int fl, int fu)
 {
-  // threads enumerate the (x1, other transverse axis) pencils in one flat index, so every warp is full
+  // threads enumerate the (x1, other transverse axis) pencils in one flat index, so every warp is full;
+  // olo/ocount: range [l, u] of the other transverse axis, fl/fu: faces [l+1, u] along the sweep (of the Grid or of an x3 chunk)
   const int il = NG-2, ni = g.nx[0]+4;
   constexpr int OTH = (DIR == 1) ? 2 : 1;                 // the transverse axis that is not x1
   const long tp = (long)blockIdx.x*blockDim.x + threadIdx.x;
-  if (tp >= (long)ni*(g.nx[OTH]+4)) return;
-  const int o = NG-2 + (int)(tp / ni);                    // range [l, u] of that axis
-  const int i = il + (int)(tp - (long)(o-(NG-2))*ni);
-  const int fl = NG-2+1, fu = g.nx[DIR]+NG+1;             // faces [l+1, u] along the sweep
+  if (tp >= (long)ni*ocount) return;
+  const int o = olo + (int)(tp / ni);
+  const int i = il + (int)(tp - (long)(o-olo)*ni);
   const int fs = fl + blockIdx.y*seg;
   int fe = fs + seg; if (fe > fu+1) fe = fu+1;
   const long sd = g.st[DIR];
@@ -150,18 +156,18 @@ __global__ void __launch_bounds__(128, AB2_LB_FIRST) k_first_march(GridDev g, do
 
   S6 Wm, W0;
   {
-    const S6 Ua = load_sweep<DIR,NS>(g.U, base + (long)(fs-2)*sd), Ub = load_sweep<DIR,NS>(g.U, base + (long)(fs-1)*sd);
+    const S6 Ua = load_sweep<DIR,NS>(g.Uin, base + (long)(fs-2)*sd), Ub = load_sweep<DIR,NS>(g.Uin, base + (long)(fs-1)*sd);
     AB2_GUARDED(Wm = cons_to_prim<NS>(Ua, g.Gamma_1, ar); W0 = cons_to_prim<NS>(Ub, g.Gamma_1, ar));
   }
   S6 Wl_prev;
   // Register prefetch: the conserved state of cell c+2 and the potential values of this iteration are requested at the
   // top of iteration c and consumed ~one PLM+Roe evaluation later, so the HBM/L2 latency (the kernel's dominant stall
   // in the first ncu profile: long-scoreboard waits on the first use of each freshly loaded value) overlaps the FP64 work.
-  S6 Unext = load_sweep<DIR,NS>(g.U, base + (long)fs*sd);
+  S6 Unext = load_sweep<DIR,NS>(g.Uin, base + (long)fs*sd);
   for (int c = fs-1; c < fe; c++) {
     const long cc = base + (long)c*sd;
     const S6 Ucur = Unext;                                                   // cell c+1
-    if (c+1 < fe) Unext = load_sweep<DIR,NS>(g.U, cc + 2*sd);                // cell c+2 <= fu+1: always inside the array
+    if (c+1 < fe) Unext = load_sweep<DIR,NS>(g.Uin, cc + 2*sd);                // cell c+2 <= fu+1: always inside the array
     double phi_mh_p = 0.0, phi_m_p = 0.0, phi_c = 0.0, phi_mh = 0.0;
     if (GRAV) {
       phi_mh_p = g.phi[PHI_MH0+DIR][cc+sd]; phi_m_p = g.phi[PHI_M0+DIR][cc+sd];
@@ -213,7 +219,7 @@ __global__ void __launch_bounds__(128) k_ppm_slope(GridDev g, Box b)
   int i,j,k; if (!box_cell(b,i,j,k)) return;
   const long c = (long)k*g.st[2] + (long)j*g.st[1] + i;
   const long sd = g.st[DIR];
-  const S6 Um = load_sweep<DIR,NS>(g.U, c-sd), U0 = load_sweep<DIR,NS>(g.U, c), Up = load_sweep<DIR,NS>(g.U, c+sd);
+  const S6 Um = load_sweep<DIR,NS>(g.Uin, c-sd), U0 = load_sweep<DIR,NS>(g.Uin, c), Up = load_sweep<DIR,NS>(g.Uin, c+sd);
   double dWm[6];
   AB2_GUARDED(const S6 Wm = cons_to_prim<NS>(Um, g.Gamma_1, ar); const S6 W0 = cons_to_prim<NS>(U0, g.Gamma_1, ar);
               const S6 Wp = cons_to_prim<NS>(Up, g.Gamma_1, ar);
@@ -230,7 +236,7 @@ __global__ void __launch_bounds__(128) k_ppm_states(GridDev g, Box b, double dt)
   const long c = (long)k*g.st[2] + (long)j*g.st[1] + i;
   const long sd = g.st[DIR];
   const double dtodx = dt/g.dx[DIR];
-  const S6 Um = load_sweep<DIR,NS>(g.U, c-sd), U0 = load_sweep<DIR,NS>(g.U, c), Up = load_sweep<DIR,NS>(g.U, c+sd);
+  const S6 Um = load_sweep<DIR,NS>(g.Uin, c-sd), U0 = load_sweep<DIR,NS>(g.Uin, c), Up = load_sweep<DIR,NS>(g.Uin, c+sd);
   const S6 dm = load_sweep<DIR,NS>(g.F[DIR], c-sd), d0 = load_sweep<DIR,NS>(g.F[DIR], c), dp = load_sweep<DIR,NS>(g.F[DIR], c+sd);
   S6 Wl_next, Wr_this;
   AB2_GUARDED(
@@ -275,28 +281,24 @@ __global__ void k_dhalf(GridDev g, Box b, double dt)
   int i,j,k; if (!box_cell(b,i,j,k)) return;
   const long c = (long)k*g.st[2] + (long)j*g.st[1] + i;
   const double q1 = 0.5*(dt/g.dx[0]), q2 = 0.5*(dt/g.dx[1]), q3 = 0.5*(dt/g.dx[2]);
-  g.dhalf[c] = g.U[0][c]
+  g.dhalf[c] = g.Uin[0][c]
     - q1*(g.F[0][0][c+1]       - g.F[0][0][c])
     - q2*(g.F[1][0][c+g.st[1]] - g.F[1][0][c])
     - q3*(g.F[2][0][c+g.st[2]] - g.F[2][0][c]);
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Pass C: correct the L/R states of DIR-faces with the transverse flux gradients (steps 5a-b/6a-b/7a-b),
-// add the static-potential source terms (5d/6d/7d), and evaluate eta (9a).  One thread per face.
+// Steps 5a-b/6a-b/7a-b + 5d/6d/7d for ONE face: the L/R states of the DIR-face of cell cR corrected with the transverse
+// flux gradients (in ascending direction order, as the reference applies them) and the static-potential source terms.
 // ---------------------------------------------------------------------------------------------------
 template <int DIR, int NS, bool GRAV>
-__global__ void __launch_bounds__(128, AB2_LB_CORRECT) k_correct(GridDev g, Box b, double dt)
+__device__ __forceinline__ void corrected_states(const GridDev& g, long cR, double dt, double UL[6], double UR[6])
 {
-  int i,j,k; if (!box_cell(b,i,j,k)) return;
-  const long cR = (long)k*g.st[2] + (long)j*g.st[1] + i;
   const long cL = cR - g.st[DIR];
   constexpr int T1 = (DIR == 0) ? 1 : 0;           // transverse directions in ascending order:
   constexpr int T2 = (DIR == 2) ? 1 : 2;           // the order the reference applies them in
   const double qT1 = 0.5*(dt/g.dx[T1]), qT2 = 0.5*(dt/g.dx[T2]);
   const long s1 = g.st[T1], s2 = g.st[T2];
-
-  double UL[6], UR[6];
 #pragma unroll
   for (int v=0; v<5+NS; v++) { UL[v] = g.Ul[DIR][v][cR]; UR[v] = g.Ur[DIR][v][cR]; }
 #pragma unroll
@@ -313,20 +315,32 @@ __global__ void __launch_bounds__(128, AB2_LB_CORRECT) k_correct(GridDev g, Box 
     // right state: cell cR (integrate_3d_ctu.c:1171-1192 and cyclic)
     double phic = g.phi[PHI_C][cR];
     double phir = g.phi[PHI_PH0+T1][cR], phil = g.phi[PHI_MH0+T1][cR];
-    UR[1+T1] -= qT1*(phir-phil)*g.U[0][cR];
+    UR[1+T1] -= qT1*(phir-phil)*g.Uin[0][cR];
     UR[4] -= qT1*(g.F[T1][0][cR]*(phic - phil) + g.F[T1][0][cR+s1]*(phir - phic));
     phir = g.phi[PHI_PH0+T2][cR]; phil = g.phi[PHI_MH0+T2][cR];
-    UR[1+T2] -= qT2*(phir-phil)*g.U[0][cR];
+    UR[1+T2] -= qT2*(phir-phil)*g.Uin[0][cR];
     UR[4] -= qT2*(g.F[T2][0][cR]*(phic - phil) + g.F[T2][0][cR+s2]*(phir - phic));
     // left state: cell cL, potentials as seen from cell cR shifted by -dx_DIR (:1196-1215)
     phic = g.phi[PHI_M0+DIR][cR];
     phir = g.phi[phi_mix(DIR,T1,1)][cR]; phil = g.phi[phi_mix(DIR,T1,0)][cR];
-    UL[1+T1] -= qT1*(phir-phil)*g.U[0][cL];
+    UL[1+T1] -= qT1*(phir-phil)*g.Uin[0][cL];
     UL[4] -= qT1*(g.F[T1][0][cL]*(phic - phil) + g.F[T1][0][cL+s1]*(phir - phic));
     phir = g.phi[phi_mix(DIR,T2,1)][cR]; phil = g.phi[phi_mix(DIR,T2,0)][cR];
-    UL[1+T2] -= qT2*(phir-phil)*g.U[0][cL];
+    UL[1+T2] -= qT2*(phir-phil)*g.Uin[0][cL];
     UL[4] -= qT2*(g.F[T2][0][cL]*(phic - phil) + g.F[T2][0][cL+s2]*(phir - phic));
   }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Pass C (unfused pair): corrected L/R states back to HBM, and eta (9a).  One thread per face.
+// ---------------------------------------------------------------------------------------------------
+template <int DIR, int NS, bool GRAV>
+__global__ void __launch_bounds__(128, AB2_LB_CORRECT) k_correct(GridDev g, Box b, double dt)
+{
+  int i,j,k; if (!box_cell(b,i,j,k)) return;
+  const long cR = (long)k*g.st[2] + (long)j*g.st[1] + i;
+  double UL[6], UR[6];
+  corrected_states<DIR,NS,GRAV>(g, cR, dt, UL, UR);
 #pragma unroll
   for (int v=0; v<5+NS; v++) { g.Ul[DIR][v][cR] = UL[v]; g.Ur[DIR][v][cR] = UR[v]; }
   {
@@ -338,7 +352,7 @@ __global__ void __launch_bounds__(128, AB2_LB_CORRECT) k_correct(GridDev g, Box 
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Pass D: final fluxes with the H-correction (integrate_3d_ctu.c:2350-2437)
+// Pass D (unfused pair): final fluxes with the H-correction (integrate_3d_ctu.c:2350-2437)
 // ---------------------------------------------------------------------------------------------------
 template <int DIR, int NS>
 __global__ void __launch_bounds__(128, AB2_LB_FINAL) k_final(GridDev g, Box b)
@@ -364,7 +378,137 @@ __global__ void __launch_bounds__(128, AB2_LB_FINAL) k_final(GridDev g, Box b)
   S6 F;
   AB2_GUARDED(const S6 Wl = cons_to_prim<NS>(Ul, g.Gamma_1, ar); const S6 Wr = cons_to_prim<NS>(Ur, g.Gamma_1, ar);
               riemann_flux<NS>(RIEMANN_OF(g), Ul, Ur, Wl, Wr, etah, g.Gamma, g.Gamma_1, F, ar));
-  store_sweep<DIR,NS>(g.F[DIR], c, F);
+  store_sweep<DIR,NS>(g.Ff[DIR], c, F);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Passes C+D fused (steps 5-7 and 9, integrate_3d_ctu.c:978-1065, 1282-1366, 1691-1776, 2300-2437).
+//
+// A block owns a (CF_TX x CF_TY) tile of (x1,x2) columns, its outer ring being a halo, and marches along x3.  What makes
+// the unfused pair expensive is that etah of a face is the maximum over eta of NINE faces of all three directions, so
+// eta has to exist on the neighbours before any final flux can be solved; the pair therefore parks the corrected states
+// (2 x nvar doubles per face and direction) and eta in HBM.  Here eta lives in a two-plane shared-memory tile instead:
+//   per plane k:  eta1(k), eta2(k) of every tile cell (halo included: recomputed, not exchanged)        -> smem
+//                 __syncthreads
+//                 x3 flux of plane k from the x3 states kept from the previous iteration (etah needs eta1,2 of k-1 and k)
+//                 corrected x3 states of plane k+1 (kept, thread-private in smem) and eta3(k+1)         -> smem
+//                 __syncthreads
+//                 x1 and x2 fluxes of plane k (etah needs eta3 of k and k+1); their corrected states are recomputed from
+//                 the very same operands (same bits) rather than held in registers across two Riemann solves.
+// HBM traffic per zone: first-pass Ul,Ur,F read once (plus halo re-reads served by L2), final fluxes written once;
+// the corrected states and eta of the unfused pair (3 x (2 nvar + 1) doubles written and read back) are gone.
+// Every per-face operation is the unfused pair's, in the same order, so results are bit-identical to it.
+// ---------------------------------------------------------------------------------------------------
+#define CF_TX 32
+#define CF_TY 8
+#ifndef AB2_LB_CFINAL
+#define AB2_LB_CFINAL 2
+#endif
+
+template <int DIR> __device__ __forceinline__ double etah_tile(const double (*se)[2][CF_TY][CF_TX], int tx, int ty, int k)
+{ // the nine faces of integrate_3d_ctu.c:2354-2363 / 2385-2394 / 2416-2425, in k_final's order (ternary MAX: order matters for NaN)
+  constexpr int A = (DIR == 0) ? 1 : 0;
+  constexpr int B = (DIR == 2) ? 1 : 2;
+  // offset of "-1 along DIR" and "+1 along A / B" in (tx, ty, plane)
+  constexpr int dxd = (DIR == 0) ? -1 : 0, dyd = (DIR == 1) ? -1 : 0, dkd = (DIR == 2) ? -1 : 0;
+  constexpr int dxa = (A == 0) ? 1 : 0, dya = (A == 1) ? 1 : 0;                 // A is never 2
+  constexpr int dyb = (B == 1) ? 1 : 0, dkb = (B == 2) ? 1 : 0;                 // B is never 0
+#define ETA(dir, ddx, ddy, ddk) se[dir][(k+(ddk)) & 1][ty+(ddy)][tx+(ddx)]
+  double etah = AB2_MAX(ETA(A, dxd, dyd, dkd), ETA(A, 0, 0, 0));
+  etah = AB2_MAX(etah, ETA(A, dxd+dxa, dyd+dya, dkd));
+  etah = AB2_MAX(etah, ETA(A, dxa, dya, 0));
+  etah = AB2_MAX(etah, ETA(B, dxd, dyd, dkd));
+  etah = AB2_MAX(etah, ETA(B, 0, 0, 0));
+  etah = AB2_MAX(etah, ETA(B, dxd, dyd+dyb, dkd+dkb));
+  etah = AB2_MAX(etah, ETA(B, 0, dyb, dkb));
+  etah = AB2_MAX(etah, ETA(DIR, 0, 0, 0));
+#undef ETA
+  return etah;
+}
+
+template <int DIR, int NS> __device__ __forceinline__ void solve_store(const GridDev& g, long c, const double UL[6], const double UR[6], double etah)
+{
+  const S6 Ul = sweep_from_phys<DIR,NS>(UL), Ur = sweep_from_phys<DIR,NS>(UR);
+  S6 F;
+  AB2_GUARDED(const S6 Wl = cons_to_prim<NS>(Ul, g.Gamma_1, ar); const S6 Wr = cons_to_prim<NS>(Ur, g.Gamma_1, ar);
+              riemann_flux<NS>(RIEMANN_OF(g), Ul, Ur, Wl, Wr, etah, g.Gamma, g.Gamma_1, F, ar));
+  store_sweep<DIR,NS>(g.Ff[DIR], c, F);
+}
+
+template <int DIR, int NS> __device__ __forceinline__ double eta_of(const GridDev& g, const double UL[6], const double UR[6])
+{
+  const S6 sl = sweep_from_phys<DIR,NS>(UL), sr = sweep_from_phys<DIR,NS>(UR);
+  double eta;
+  AB2_GUARDED(eta = eta_face(sl, sr, g.Gamma, g.Gamma_1, ar));
+  return eta;
+}
+
+// ks..ke: the x3 planes whose final fluxes this launch produces (x1/x2 faces for planes <= e3, x3 faces for all of them);
+// blockIdx.z picks a segment of `kseg` planes.
+template <int NS, bool GRAV>
+__global__ void __launch_bounds__(CF_TX*CF_TY, AB2_LB_CFINAL) k_cfinal(GridDev g, double dt, int ks, int ke, int e3, int kseg)
+{
+  constexpr int NV = 5+NS;
+  __shared__ double s_eta[3][2][CF_TY][CF_TX];
+  __shared__ double s_st3[2*NV][CF_TX*CF_TY];
+  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty*CF_TX + tx;
+  const int e1 = g.nx[0]+NG-1, e2 = g.nx[1]+NG-1;
+  const int i = NG-1 + (int)blockIdx.x*(CF_TX-2) + tx;
+  const int j = NG-1 + (int)blockIdx.y*(CF_TY-2) + ty;
+  const int kA = ks + (int)blockIdx.z*kseg;
+  int kB = kA + kseg; if (kB > ke+1) kB = ke+1;
+  const bool hcorr = (RIEMANN_OF(g) == AB2_RIEMANN_ROE);
+  const bool inC = (i <= e1+1) && (j <= e2+1);                   // the box [s-1, e+1] on which eta is needed
+  const bool inner = inC && tx >= 1 && tx <= CF_TX-2 && ty >= 1 && ty <= CF_TY-2;
+  const bool d1 = inner && (j <= e2);                            // x1 faces [s, e1+1], active transversally
+  const bool d2 = inner && (i <= e1);
+  const bool d3 = inner && (i <= e1) && (j <= e2);
+  const long col = (long)j*g.st[1] + i;
+  double UL[6], UR[6];
+
+  // prologue: eta1, eta2 of plane kA-1; corrected x3 states and eta3 of plane kA
+  if (inC) {
+    const long c = col + (long)(kA-1)*g.st[2];
+    if (hcorr) {
+      corrected_states<0,NS,GRAV>(g, c, dt, UL, UR); s_eta[0][(kA-1)&1][ty][tx] = eta_of<0,NS>(g, UL, UR);
+      corrected_states<1,NS,GRAV>(g, c, dt, UL, UR); s_eta[1][(kA-1)&1][ty][tx] = eta_of<1,NS>(g, UL, UR);
+    }
+    corrected_states<2,NS,GRAV>(g, c + g.st[2], dt, UL, UR);
+    if (hcorr) s_eta[2][kA&1][ty][tx] = eta_of<2,NS>(g, UL, UR);
+#pragma unroll
+    for (int v=0; v<NV; v++) { s_st3[v][tid] = UL[v]; s_st3[NV+v][tid] = UR[v]; }
+  }
+  for (int k = kA; k < kB; k++) {
+    const long c = col + (long)k*g.st[2];
+    if (inC && hcorr && k <= e3+1) {
+      corrected_states<0,NS,GRAV>(g, c, dt, UL, UR); s_eta[0][k&1][ty][tx] = eta_of<0,NS>(g, UL, UR);
+      corrected_states<1,NS,GRAV>(g, c, dt, UL, UR); s_eta[1][k&1][ty][tx] = eta_of<1,NS>(g, UL, UR);
+    }
+    __syncthreads();
+    if (d3) {                                                     // x3 face of plane k
+#pragma unroll
+      for (int v=0; v<NV; v++) { UL[v] = s_st3[v][tid]; UR[v] = s_st3[NV+v][tid]; }
+      const double etah = hcorr ? etah_tile<2>(s_eta, tx, ty, k) : 0.0;
+      solve_store<2,NS>(g, c, UL, UR, etah);
+    }
+    if (inC && k+1 <= e3+1) {                                     // states and eta3 of plane k+1
+      corrected_states<2,NS,GRAV>(g, c + g.st[2], dt, UL, UR);
+      if (hcorr) s_eta[2][(k+1)&1][ty][tx] = eta_of<2,NS>(g, UL, UR);
+#pragma unroll
+      for (int v=0; v<NV; v++) { s_st3[v][tid] = UL[v]; s_st3[NV+v][tid] = UR[v]; }
+    }
+    __syncthreads();
+    if (k <= e3) {                                                // x1 and x2 faces of plane k
+      if (d1) {
+        corrected_states<0,NS,GRAV>(g, c, dt, UL, UR);
+        solve_store<0,NS>(g, c, UL, UR, hcorr ? etah_tile<0>(s_eta, tx, ty, k) : 0.0);
+      }
+      if (d2) {
+        corrected_states<1,NS,GRAV>(g, c, dt, UL, UR);
+        solve_store<1,NS>(g, c, UL, UR, hcorr ? etah_tile<1>(s_eta, tx, ty, k) : 0.0);
+      }
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -379,7 +523,7 @@ __global__ void __launch_bounds__(128, AB2_LB_UPDATE) k_update(GridDev g, Box b,
   const double dtodx[3] = { dt/g.dx[0], dt/g.dx[1], dt/g.dx[2] };
   double U[6];
 #pragma unroll
-  for (int v=0; v<5+NS; v++) U[v] = g.U[v][c];
+  for (int v=0; v<5+NS; v++) U[v] = g.Uin[v][c];
   if (GRAV) {
     const double phic = g.phi[PHI_C][c];
     const double dh = g.dhalf[c];
@@ -387,13 +531,13 @@ __global__ void __launch_bounds__(128, AB2_LB_UPDATE) k_update(GridDev g, Box b,
     for (int d=0; d<3; d++) {
       const double phir = g.phi[PHI_PH0+d][c], phil = g.phi[PHI_MH0+d][c];
       U[1+d] -= dtodx[d]*(phir-phil)*dh;
-      U[4] -= dtodx[d]*(g.F[d][0][c]*(phic - phil) + g.F[d][0][c+g.st[d]]*(phir - phic));
+      U[4] -= dtodx[d]*(g.Ff[d][0][c]*(phic - phil) + g.Ff[d][0][c+g.st[d]]*(phir - phic));
     }
   }
 #pragma unroll
   for (int d=0; d<3; d++) {
 #pragma unroll
-    for (int v=0; v<5+NS; v++) U[v] -= dtodx[d]*(g.F[d][v][c+g.st[d]] - g.F[d][v][c]);
+    for (int v=0; v<5+NS; v++) U[v] -= dtodx[d]*(g.Ff[d][v][c+g.st[d]] - g.Ff[d][v][c]);
   }
 #pragma unroll
   for (int v=0; v<5+NS; v++) g.U[v][c] = U[v];
@@ -547,12 +691,13 @@ static inline dim3 box_grid(const Box& b, int threads)
   return dim3((unsigned)((nij + threads-1)/threads), (unsigned)(b.hi[2]-b.lo[2]+1), 1);
 }
 
+// One pass of steps 1-12 over the active x3 planes [ka, kb] of the Grid, on scratch arrays addressed through `g`
+// (the whole Grid: g = h->g; an x3 chunk: base pointers shifted so U's cell index addresses the chunk's scratch).
 template <int NS, bool GRAV>
-static int integrate_impl(ab2_grid* h, double dt)
+static int integrate_range(ab2_grid* h, const GridDev& g, double dt, int ka, int kb)
 {
-  GridDev& g = h->g;
   cudaStream_t st = h->stream;
-  const int s[3] = {NG,NG,NG}, e[3] = {g.nx[0]+NG-1, g.nx[1]+NG-1, g.nx[2]+NG-1};
+  const int s[3] = {NG,NG,ka}, e[3] = {g.nx[0]+NG-1, g.nx[1]+NG-1, kb};
   int l[3], u[3];
   for (int a=0; a<3; a++) { l[a] = s[a]-2; u[a] = e[a]+2; }
   // faces per marching segment: ~32, balanced so the last segment of a pencil is not a stub
@@ -591,40 +736,86 @@ static int integrate_impl(ab2_grid* h, double dt)
     }
     const dim3 grid((nf + bestT-4)/(bestT-3), u[1]-l[1]+1, u[2]-l[2]+1);
     switch (bestT) {
-      case 64:  AB2_LAUNCH(h, KID_FIRST_X1, (k_first_x1<NS,GRAV,64><<<grid, 64, 0, st>>>(g, dt))); break;
-      case 96:  AB2_LAUNCH(h, KID_FIRST_X1, (k_first_x1<NS,GRAV,96><<<grid, 96, 0, st>>>(g, dt))); break;
-      case 160: AB2_LAUNCH(h, KID_FIRST_X1, (k_first_x1<NS,GRAV,160><<<grid, 160, 0, st>>>(g, dt))); break;
-      case 192: AB2_LAUNCH(h, KID_FIRST_X1, (k_first_x1<NS,GRAV,192><<<grid, 192, 0, st>>>(g, dt))); break;
-      case 256: AB2_LAUNCH(h, KID_FIRST_X1, (k_first_x1<NS,GRAV,256><<<grid, 256, 0, st>>>(g, dt))); break;
-      default:  AB2_LAUNCH(h, KID_FIRST_X1, (k_first_x1<NS,GRAV,128><<<grid, 128, 0, st>>>(g, dt))); break;
+      case 64:  AB2_LAUNCH(h, KID_FIRST_X1, (k_first_x1<NS,GRAV,64><<<grid, 64, 0, st>>>(g, dt, l[2]))); break;
+      case 96:  AB2_LAUNCH(h, KID_FIRST_X1, (k_first_x1<NS,GRAV,96><<<grid, 96, 0, st>>>(g, dt, l[2]))); break;
+      case 160: AB2_LAUNCH(h, KID_FIRST_X1, (k_first_x1<NS,GRAV,160><<<grid, 160, 0, st>>>(g, dt, l[2]))); break;
+      case 192: AB2_LAUNCH(h, KID_FIRST_X1, (k_first_x1<NS,GRAV,192><<<grid, 192, 0, st>>>(g, dt, l[2]))); break;
+      case 256: AB2_LAUNCH(h, KID_FIRST_X1, (k_first_x1<NS,GRAV,256><<<grid, 256, 0, st>>>(g, dt, l[2]))); break;
+      default:  AB2_LAUNCH(h, KID_FIRST_X1, (k_first_x1<NS,GRAV,128><<<grid, 128, 0, st>>>(g, dt, l[2]))); break;
     }
     const long ni = u[0]-l[0]+1;
-    const int seg2 = seg_for(g.nx[1]+4), seg3 = seg_for(g.nx[2]+4);
-    dim3 g2((unsigned)((ni*(u[2]-l[2]+1)+127)/128), (g.nx[1]+4 + seg2-1)/seg2, 1);
-    AB2_LAUNCH(h, KID_FIRST_X2, (k_first_march<1,NS,GRAV><<<g2, 128, 0, st>>>(g, dt, seg2)));
-    dim3 g3((unsigned)((ni*(u[1]-l[1]+1)+127)/128), (g.nx[2]+4 + seg3-1)/seg3, 1);
-    AB2_LAUNCH(h, KID_FIRST_X3, (k_first_march<2,NS,GRAV><<<g3, 128, 0, st>>>(g, dt, seg3)));
+    const int nf2 = u[1]-l[1], nf3 = u[2]-l[2];             // faces [l+1, u] along the sweep
+    const int seg2 = seg_for(nf2), seg3 = seg_for(nf3);
+    dim3 g2((unsigned)((ni*(u[2]-l[2]+1)+127)/128), (nf2 + seg2-1)/seg2, 1);
+    AB2_LAUNCH(h, KID_FIRST_X2, (k_first_march<1,NS,GRAV><<<g2, 128, 0, st>>>(g, dt, seg2, l[2], u[2]-l[2]+1, l[1]+1, u[1])));
+    dim3 g3((unsigned)((ni*(u[1]-l[1]+1)+127)/128), (nf3 + seg3-1)/seg3, 1);
+    AB2_LAUNCH(h, KID_FIRST_X3, (k_first_march<2,NS,GRAV><<<g3, 128, 0, st>>>(g, dt, seg3, l[1], u[1]-l[1]+1, l[2]+1, u[2])));
   }
   Box act; for (int a=0; a<3; a++) { act.lo[a] = s[a]; act.hi[a] = e[a]; }
   // Pass B
   if (GRAV) AB2_LAUNCH(h, KID_DHALF, (k_dhalf<<<box_grid(act,128), 128, 0, st>>>(g, act, dt)));
-  // Pass C: faces of direction d over [l+1, u-1] transversally and [l+1, u] along d
-  for (int d=0; d<3; d++) {
-    Box b; for (int a=0; a<3; a++) { b.lo[a] = l[a]+1; b.hi[a] = (a == d) ? u[a] : u[a]-1; }
-    if (d == 0) AB2_LAUNCH(h, KID_CORRECT_X1+0, (k_correct<0,NS,GRAV><<<box_grid(b,128), 128, 0, st>>>(g, b, dt)));
-    if (d == 1) AB2_LAUNCH(h, KID_CORRECT_X1+1, (k_correct<1,NS,GRAV><<<box_grid(b,128), 128, 0, st>>>(g, b, dt)));
-    if (d == 2) AB2_LAUNCH(h, KID_CORRECT_X1+2, (k_correct<2,NS,GRAV><<<box_grid(b,128), 128, 0, st>>>(g, b, dt)));
-  }
-  // Pass D: faces [s, e+1] along d, active transversally (the +-1 transverse ring of the reference's loops feeds MHD only)
-  for (int d=0; d<3; d++) {
-    Box b; for (int a=0; a<3; a++) { b.lo[a] = s[a]; b.hi[a] = (a == d) ? e[a]+1 : e[a]; }
-    if (d == 0) AB2_LAUNCH(h, KID_FINAL_X1+0, (k_final<0,NS><<<box_grid(b,128), 128, 0, st>>>(g, b)));
-    if (d == 1) AB2_LAUNCH(h, KID_FINAL_X1+1, (k_final<1,NS><<<box_grid(b,128), 128, 0, st>>>(g, b)));
-    if (d == 2) AB2_LAUNCH(h, KID_FINAL_X1+2, (k_final<2,NS><<<box_grid(b,128), 128, 0, st>>>(g, b)));
+  if (h->fuse) {
+    // Passes C+D in one kernel: x3 planes [s, e+1]
+    const int npl = e[2]+1 - s[2] + 1;
+    const int nseg = (npl + 47)/48, kseg = (npl + nseg-1)/nseg;
+    const dim3 grid((g.nx[0]+1 + CF_TX-3)/(CF_TX-2), (g.nx[1]+1 + CF_TY-3)/(CF_TY-2), (npl + kseg-1)/kseg);
+    AB2_LAUNCH(h, KID_CFINAL, (k_cfinal<NS,GRAV><<<grid, dim3(CF_TX,CF_TY,1), 0, st>>>(g, dt, s[2], e[2]+1, e[2], kseg)));
+  } else {
+    // Pass C: faces of direction d over [l+1, u-1] transversally and [l+1, u] along d
+    for (int d=0; d<3; d++) {
+      Box b; for (int a=0; a<3; a++) { b.lo[a] = l[a]+1; b.hi[a] = (a == d) ? u[a] : u[a]-1; }
+      if (d == 0) AB2_LAUNCH(h, KID_CORRECT_X1+0, (k_correct<0,NS,GRAV><<<box_grid(b,128), 128, 0, st>>>(g, b, dt)));
+      if (d == 1) AB2_LAUNCH(h, KID_CORRECT_X1+1, (k_correct<1,NS,GRAV><<<box_grid(b,128), 128, 0, st>>>(g, b, dt)));
+      if (d == 2) AB2_LAUNCH(h, KID_CORRECT_X1+2, (k_correct<2,NS,GRAV><<<box_grid(b,128), 128, 0, st>>>(g, b, dt)));
+    }
+    // Pass D: faces [s, e+1] along d, active transversally (the +-1 transverse ring of the reference's loops feeds MHD only)
+    for (int d=0; d<3; d++) {
+      Box b; for (int a=0; a<3; a++) { b.lo[a] = s[a]; b.hi[a] = (a == d) ? e[a]+1 : e[a]; }
+      if (d == 0) AB2_LAUNCH(h, KID_FINAL_X1+0, (k_final<0,NS><<<box_grid(b,128), 128, 0, st>>>(g, b)));
+      if (d == 1) AB2_LAUNCH(h, KID_FINAL_X1+1, (k_final<1,NS><<<box_grid(b,128), 128, 0, st>>>(g, b)));
+      if (d == 2) AB2_LAUNCH(h, KID_FINAL_X1+2, (k_final<2,NS><<<box_grid(b,128), 128, 0, st>>>(g, b)));
+    }
   }
   // Pass E
   AB2_LAUNCH(h, KID_UPDATE, (k_update<NS,GRAV><<<box_grid(act,128), 128, 0, st>>>(g, act, dt)));
   return ab2_check(cudaGetLastError(), "integrate_3d_ctu") ? 0 : -1;
+}
+
+// The reference allocates its scratch for the whole Grid (integrate_3d_ctu.c:3374-3472).  Here the scratch may hold only
+// `chunk_planes` active x3 planes (+4 either side): the step then runs chunk by chunk.  A chunk reads U^n from a staged copy
+// of its planes (its lowest 4 planes come from a carry buffer saved before the chunk below was updated) and writes U^{n+1}
+// straight into U, so results are those of the unchunked step bit for bit.
+template <int NS, bool GRAV>
+static int integrate_impl(ab2_grid* h, double dt)
+{
+  const GridDev& g0 = h->g;
+  const int ks = NG, ke = g0.nx[2]+NG-1;
+  if (h->chunk_planes <= 0 || h->chunk_planes >= g0.nx[2]) return integrate_range<NS,GRAV>(h, g0, dt, ks, ke);
+  const int nvar = 5 + NS;
+  const size_t P = (size_t)g0.st[2];
+  const int depth = h->chunk_planes + 2*NG;
+  // scratch layout (ab2_alloc_scratch): 12 nvar + 3 arrays of depth*P, then Uin (nvar arrays of depth*P), then carry (nvar x NG planes)
+  double* uin = h->scratch + (size_t)(12*nvar + 3)*depth*P;
+  double* carry = uin + (size_t)nvar*depth*P;
+  cudaStream_t st = h->stream;
+  for (int ka = ks; ka <= ke; ka += h->chunk_planes) {
+    const int kb = (ka + h->chunk_planes - 1 < ke) ? ka + h->chunk_planes - 1 : ke;
+    const int base = ka - NG;                               // lowest plane the chunk touches
+    const size_t npl = (size_t)(kb + NG - base + 1);
+    GridDev g = g0;
+    const long shift = (long)base*(long)P;
+    for (int d=0; d<3; d++) for (int v=0; v<nvar; v++) { g.Ul[d][v] -= shift; g.Ur[d][v] -= shift; g.F[d][v] -= shift; g.Ff[d][v] -= shift; }
+    for (int d=0; d<3; d++) g.eta[d] -= shift;
+    for (int v=0; v<nvar; v++) {
+      double* dst = uin + (size_t)v*depth*P;
+      if (!ab2_check(cudaMemcpyAsync(dst, g0.U[v] + shift, npl*P*sizeof(double), cudaMemcpyDeviceToDevice, st), "chunk stage")) return -1;
+      if (ka > ks && !ab2_check(cudaMemcpyAsync(dst, carry + (size_t)v*NG*P, NG*P*sizeof(double), cudaMemcpyDeviceToDevice, st), "chunk carry in")) return -1;
+      if (kb < ke && !ab2_check(cudaMemcpyAsync(carry + (size_t)v*NG*P, g0.U[v] + (size_t)(kb-NG+1)*P, NG*P*sizeof(double), cudaMemcpyDeviceToDevice, st), "chunk carry out")) return -1;
+      g.Uin[v] = dst - shift;
+    }
+    if (integrate_range<NS,GRAV>(h, g, dt, ka, kb) != 0) return -1;
+  }
+  return 0;
 }
 
 int hydro_integrate(ab2_grid* h, double dt)

@@ -71,11 +71,11 @@ __global__ void k_smr_flux_correct(GridDev pa, GridDev ch, OvDev o, int nvar, in
   const long xc = cidx(pa, pc[2], pc[1], pc[0]), xf = cidx(pa, pf[2], pf[1], pf[0]);
   const long c00 = cidx(ch, cf[2], cf[1], cf[0]), e1 = ch.st[t1], e2 = ch.st[t2];
   for (int v=0; v<nvar; v++) {
-    const double* Fc = ch.F[d][v];
+    const double* Fc = ch.Ff[d][v];
     double r = Fc[c00] + Fc[c00+e1];                                       // smr.c:2046-2064 (and x2/x3 analogues)
     r += Fc[c00+e2] + Fc[c00+e2+e1];                                       // :2072-2090
     r *= 0.25;
-    pa.U[v][xc] -= q*(pa.F[d][v][xf] - r);                                 // :1503-1517
+    pa.U[v][xc] -= q*(pa.Ff[d][v][xf] - r);                                 // :1503-1517
   }
 }
 
@@ -182,6 +182,10 @@ extern "C" {
 int ab2_smr_restrict_correct(ab2_grid* pa, ab2_grid* ch, const ab2_overlap* o, double dt_parent)
 {
   if (check_pair(pa, ch, "RestrictCorrect")) return -1;
+  if (pa->chunk_planes || ch->chunk_planes) {
+    ab2_set_error("[RestrictCorrect]: the flux correction reads both Grids' final fluxes of the whole Grid: call ab2_set_scratch_planes(g, 0) on SMR Grids");
+    return -1;
+  }
   const OvDev od = ov_dev(o);
   const int nvar = 5 + pa->nscal;
   if (!stream_wait(pa->stream, ch->stream)) return -1;

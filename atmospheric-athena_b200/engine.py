@@ -72,7 +72,7 @@ EXPORTS = ["ab2_last_error", "ab2_version", "ab2_device_count", "ab2_grid_create
            "ab2_set_riemann_solver", "ab2_set_reconstruction",
            "ab2_comm_get_unique_id", "ab2_comm_init_rank", "ab2_comm_destroy", "ab2_comm_rank", "ab2_comm_size",
            "ab2_comm_exchanges", "ab2_comm_reductions", "ab2_comm_allreduce", "ab2_comm_bcast", "ab2_grid_set_comm",
-           "ab2_exchange_x3"]
+           "ab2_exchange_x3", "ab2_set_scratch_planes", "ab2_scratch_planes"]
 # libathena_b200_units.so (include/athena_b200_units.h): function-level test hooks, not part of the bound interface
 UNITS_LIB_PATH = os.path.join(_HERE, "csrc", "libathena_b200_units.so")
 UNIT_EXPORTS = ["ab2_unit_roe_flux", "ab2_unit_convert", "ab2_unit_lr_states", "ab2_unit_ieee", "ab2_unit_libm",
@@ -146,6 +146,8 @@ def lib():
     L.ab2_profile_kernel_name.argtypes = [C.c_int]
     L.ab2_profile_kernel_name.restype = C.c_char_p
     L.ab2_profile_read.argtypes = [vp, dp, C.POINTER(C.c_longlong), C.c_int]
+    L.ab2_set_riemann_solver.argtypes = [vp, C.c_int]
+    L.ab2_set_reconstruction.argtypes = [vp, C.c_int]
     L.ab2_comm_get_unique_id.argtypes = [C.c_char_p]
     L.ab2_comm_init_rank.argtypes = [C.c_int, C.c_int, C.c_char_p, C.c_int]
     L.ab2_comm_init_rank.restype = vp
@@ -160,6 +162,8 @@ def lib():
     L.ab2_comm_bcast.argtypes = [vp, vp, C.c_int, C.c_int]
     L.ab2_grid_set_comm.argtypes = [vp, vp, C.c_int, C.c_int]
     L.ab2_exchange_x3.argtypes = [vp]
+    L.ab2_set_scratch_planes.argtypes = [vp, C.c_int]
+    L.ab2_scratch_planes.argtypes = [vp]
     _lib = L
     return L
 
@@ -183,8 +187,6 @@ def units():
     L.ab2_unit_lr_states.argtypes = [C.c_int, C.c_int, dp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, dp, dp]
     L.ab2_unit_lr_states_hll.argtypes = L.ab2_unit_lr_states.argtypes
     L.ab2_unit_hllc_flux.argtypes = [C.c_int, dp, dp, dp, dp, C.c_int, C.c_double, dp]
-    L.ab2_set_riemann_solver.argtypes = [vp, C.c_int]
-    L.ab2_set_reconstruction.argtypes = [vp, C.c_int]
     L.ab2_unit_lr_states_ppm.argtypes = [C.c_int, C.c_int, dp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, dp, dp]
     _units = L
     return L
@@ -300,6 +302,14 @@ class Grid:
 
     def synchronize(self):
         self._ck(lib().ab2_synchronize(self.h))
+
+    def set_scratch_planes(self, planes):
+        """x3-chunked CTU scratch: `planes` active planes per chunk, 0 = whole Grid (results do not depend on it)"""
+        self._ck(lib().ab2_set_scratch_planes(self.h, int(planes)))
+
+    @property
+    def scratch_planes(self):
+        return lib().ab2_scratch_planes(self.h)
 
     def profile_enable(self, on=True):
         self._ck(lib().ab2_profile_enable(self.h, 1 if on else 0))

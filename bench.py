@@ -34,6 +34,7 @@ load_package()
 from athena_b200.athinput import ParFile  # noqa: E402
 
 DECKS = os.path.join(ROOT, "tests", "decks")
+OUT = sys.stdout
 WORKLOADS = {
     # name: (deck, problem/reference build, BASELINE.json config it corresponds to)
     "ioniz_sphere": ("ioniz_sphere.athinput", "ioniz_sphere", "configs[2] ioniz_sphere unigrid"),
@@ -232,7 +233,7 @@ def reference_arm(args):
         "e2e": {"value": value, "unit": "zone-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=OUT, flush=True)
     return 0
 
 
@@ -319,7 +320,7 @@ def gpu_arm(args):
     if parity is not None and parity["bit_equal"] is False:
         if rank == 0:
             print(json.dumps({"metric": "zone-updates/s per hydro+ion-RT step", "value": None, "n_gpus": world, "parity": parity,
-                              "error": "parity gate failed: nothing was timed"}))
+                              "error": "parity gate failed: nothing was timed"}), file=OUT, flush=True)
         raise SystemExit(3)
 
     n = args.n
@@ -457,7 +458,7 @@ def gpu_arm(args):
             "parity": parity,
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "dropin": dropin, "kernels": ktab,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), file=OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -525,7 +526,7 @@ def smr_arm(args):
     if parity is not None and parity["bit_equal"] is False:
         if rank == 0:
             print(json.dumps({"metric": "zone-updates/s per hydro+ion-RT step", "value": None, "n_gpus": world, "parity": parity,
-                              "error": "parity gate failed: nothing was timed"}))
+                              "error": "parity gate failed: nothing was timed"}), file=OUT, flush=True)
         raise SystemExit(3)
     t_setup = time.time()
     if world > 1:
@@ -582,13 +583,18 @@ def smr_arm(args):
                              "frac": round(value / world * b_alg / 1e9 / peak, 4), "traffic": None, "peak_source": peak_src,
                              "note": "whole step at SURVEY 8(d) compulsory bytes per GPU; per-kernel rooflines are those of the unigrid workload"},
                 "cpu_baseline": None}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
 def main():
+    # stdout carries exactly ONE line, the JSON record: whatever libraries print there (NCCL's version banner, torchrun
+    # notices) goes to stderr instead
+    global OUT
+    OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=40)

@@ -72,6 +72,12 @@ int  ab2_device_count(void);
 ab2_grid* ab2_grid_create(const ab2_grid_desc* desc);
 /* integrate_destruct (integrate_3d_ctu.c:3498-3550) */
 void ab2_grid_destroy(ab2_grid* g);
+/* The reference sizes its CTU scratch to the whole Grid (integrate_3d_ctu.c:3374-3472: ~0.6 kB per zone with a passive scalar).
+ * Here it may hold only `planes` active x3 planes (+4 either side): ab2_integrate_3d_ctu then sweeps the Grid chunk by
+ * chunk with identical results.  ab2_grid_create picks 0 (whole Grid) when that fits the device next to the Grid's other
+ * arrays and a chunk size otherwise (AB2_CHUNK_PLANES overrides); this call changes it.  SMR Grids must stay at 0. */
+int ab2_set_scratch_planes(ab2_grid* g, int planes);
+int ab2_scratch_planes(const ab2_grid* g);
 long long ab2_bytes_allocated(const ab2_grid* g);
 long long ab2_kernel_launches(const ab2_grid* g);
 int  ab2_synchronize(ab2_grid* g);

@@ -5,6 +5,8 @@ Bars (BASELINE.json north_star): hydro -- bit-exact (the library is built --fmad
 operation order); ion RT -- per-cell relative error <= 1e-10 after one step, identical sub-cycle iteration counts."""
 import ctypes as C
 
+import os
+
 import numpy as np
 import pytest
 
@@ -101,12 +103,38 @@ def test_glibc_math_matches_host_libm_bit_for_bit():
         assert not bad.any(), f"pow differs in {bad.sum()} of {len(sel)}: {y[sel][bad][:4]} ^ {x[sel][bad][:4]}"
 
 
-def gpu_run(case):
+def gpu_run(case, fuse=None, planes=None):
+    """fuse: 0 forces the unfused k_correct / k_final pair (AB2_HYDRO_FUSE, read at Grid creation); planes: x3-chunked scratch"""
     from athena_b200.driver import Run
-    R = Run(case.par, case.problem, device=0, U0=case.U0, riemann=case.riemann, order=case.order)
+    if fuse is not None:
+        os.environ["AB2_HYDRO_FUSE"] = str(fuse)
+    try:
+        R = Run(case.par, case.problem, device=0, U0=case.U0, riemann=case.riemann, order=case.order)
+    finally:
+        os.environ.pop("AB2_HYDRO_FUSE", None)
+    if planes is not None:
+        R.G.set_scratch_planes(planes)
+        assert R.G.scratch_planes == (planes if planes < case.nx[2] else 0)
     assert R.dt == float(case.gold["dt0"]), "first new_dt must be bit-identical (max is order independent)"
     R.run(case.nsteps)
     return R
+
+
+@pytest.mark.parametrize("name", ["blast16_k6", "blastmix_k5", "blasttiny_k5", "blast16hllc_k6", "blast16ppm_k6", "ifront32_k4",
+                                  "ioniz24_k3", "ionizodd_k1", "ifronttiny_k3"])
+@pytest.mark.parametrize("variant", ["unfused", "chunk4", "chunk8_unfused", "chunk5"])
+def test_hydro_pass_variants_bit_exact_vs_reference(name, variant):
+    """The step's pass structure does not show in the results: the unfused correct/final pair (corrected states and eta
+    through HBM) and the x3-chunked scratch (chunks of 4, 5 or 8 active planes, incl. a ragged last chunk) reproduce the
+    reference's dump bit for bit, exactly like the default fused, unchunked path of the tests below."""
+    case = Case(name)
+    fuse = 0 if "unfused" in variant else 1
+    planes = {"unfused": None, "chunk4": 4, "chunk8_unfused": 8, "chunk5": 5}[variant]
+    R = gpu_run(case, fuse=fuse, planes=planes)
+    out = R.G.download_active()
+    assert R.time == float(case.gold["time1"]) and R.dt == float(case.gold["dt1"])
+    for v in case.U1:
+        assert np.array_equal(out[v], case.U1[v], equal_nan=True), f"{name}/{variant}:{v} differs in {(out[v] != case.U1[v]).sum()} cells"
 
 
 def rel_err(a, b):
