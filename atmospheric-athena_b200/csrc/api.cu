@@ -161,6 +161,7 @@ ab2_grid* ab2_grid_create(const ab2_grid_desc* d)
   h->has_grav = false; h->has_ion = false; h->n_fixed = 0; h->d_fixed_cells = nullptr; h->d_fixed_vals = nullptr;
   h->bytes_allocated = 0; h->launches = 0; h->maxiter = 0; h->tcoarse = 0.0;
   h->prof_on = false;
+  for (int f=0; f<6; f++) { h->bc_n[f] = 0; h->bc_dst[f] = nullptr; h->bc_src[f] = nullptr; h->bc_coef[f] = nullptr; }
   h->comm = nullptr; h->lo_rank = h->hi_rank = -1; h->d_gather = nullptr; h->h_gather = nullptr;
   for (int n=0; n<KID_N; n++) { h->prof_ms[n] = 0.0; h->prof_cnt[n] = 0; }
   memset(&h->ion, 0, sizeof h->ion);
@@ -191,6 +192,8 @@ ab2_grid* ab2_grid_create(const ab2_grid_desc* d)
   h->scratch = nullptr; h->scratch_doubles = 0; h->chunk_planes = 0;
   h->fuse = 1;
   if (const char* env = getenv("AB2_HYDRO_FUSE")) h->fuse = (atoi(env) != 0);
+  h->correct3 = 1;
+  if (const char* env = getenv("AB2_CORRECT3")) h->correct3 = (atoi(env) != 0);
   {
     int planes = 0;
     if (const char* env = getenv("AB2_CHUNK_PLANES")) planes = atoi(env);
@@ -228,6 +231,9 @@ void ab2_grid_destroy(ab2_grid* h)
   cudaSetDevice(h->device);
   prof_drain(h);
   if (h->scratch) cudaFree(h->scratch);
+  if (h->d_fixed_cells) { cudaFree(h->d_fixed_cells); cudaFree(h->d_fixed_vals); }
+  for (void* p : h->phi_allocs) cudaFree(p);
+  for (int f=0; f<6; f++) if (h->bc_dst[f]) { cudaFree(h->bc_dst[f]); cudaFree(h->bc_src[f]); cudaFree(h->bc_coef[f]); }
   for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
   for (void* p : h->allocs) cudaFree(p);
   if (h->h_scal) cudaFreeHost(h->h_scal);
@@ -339,10 +345,12 @@ int ab2_integrate_3d_ctu(ab2_grid* h, double dt) { return hydro_integrate(h, dt)
 int ab2_set_fixed_cells(ab2_grid* h, long n, const long* cells, const double* vals)
 {
   h->n_fixed = 0;
+  CK(cudaStreamSynchronize(h->stream), "fixed cells sync");
+  if (h->d_fixed_cells) { cudaFree(h->d_fixed_cells); cudaFree(h->d_fixed_vals); h->d_fixed_cells = nullptr; h->d_fixed_vals = nullptr; }   // a re-set replaces the table
   if (n <= 0) return 0;
   void* p = nullptr;
-  CK(cudaMalloc(&p, n*sizeof(long)), "cudaMalloc fixed cells"); h->allocs.push_back(p); h->d_fixed_cells = (long*)p;
-  CK(cudaMalloc(&p, (size_t)6*n*sizeof(double)), "cudaMalloc fixed vals"); h->allocs.push_back(p); h->d_fixed_vals = (double*)p;
+  CK(cudaMalloc(&p, n*sizeof(long)), "cudaMalloc fixed cells"); h->d_fixed_cells = (long*)p;
+  CK(cudaMalloc(&p, (size_t)6*n*sizeof(double)), "cudaMalloc fixed vals"); h->d_fixed_vals = (double*)p;
   CK(cudaMemcpyAsync(h->d_fixed_cells, cells, n*sizeof(long), cudaMemcpyHostToDevice, h->stream), "fixed cells H2D");
   CK(cudaMemcpyAsync(h->d_fixed_vals, vals, (size_t)6*n*sizeof(double), cudaMemcpyHostToDevice, h->stream), "fixed vals H2D");
   CK(cudaStreamSynchronize(h->stream), "fixed sync");
@@ -351,6 +359,31 @@ int ab2_set_fixed_cells(ab2_grid* h, long n, const long* cells, const double* va
 }
 
 int ab2_apply_fixed_cells(ab2_grid* h) { return hydro_apply_fixed(h); }
+
+int ab2_set_bc_table(ab2_grid* h, int face, long n, const long* dst, const long* src, const double* coef)
+{
+  if (face < 0 || face > 5 || n < 0) { ab2_set_error("[ab2_set_bc_table]: face 0..5 (ix1, ox1, ix2, ox2, ix3, ox3)"); return -1; }
+  const int nvar = 5 + h->nscal;
+  const long ncell = (long)h->g.n[0]*h->g.n[1]*h->g.n[2];
+  for (long t=0; t<n; t++) {
+    if (dst[t] < 0 || dst[t] >= ncell) { ab2_set_error("[ab2_set_bc_table]: destination outside the Grid"); return -1; }
+    for (int v=0; v<nvar; v++) if (src[(long)v*n+t] >= ncell) { ab2_set_error("[ab2_set_bc_table]: source outside the Grid"); return -1; }
+  }
+  CK(cudaStreamSynchronize(h->stream), "bc table sync");
+  if (h->bc_dst[face]) { cudaFree(h->bc_dst[face]); cudaFree(h->bc_src[face]); cudaFree(h->bc_coef[face]); h->bc_dst[face] = nullptr; }
+  h->bc_n[face] = 0;
+  if (n == 0) return 0;
+  void* p = nullptr;
+  CK(cudaMalloc(&p, n*sizeof(long)), "cudaMalloc bc table"); h->bc_dst[face] = (long*)p;
+  CK(cudaMalloc(&p, (size_t)nvar*n*sizeof(long)), "cudaMalloc bc table"); h->bc_src[face] = (long*)p;
+  CK(cudaMalloc(&p, (size_t)nvar*n*sizeof(double)), "cudaMalloc bc table"); h->bc_coef[face] = (double*)p;
+  CK(cudaMemcpyAsync(h->bc_dst[face], dst, n*sizeof(long), cudaMemcpyHostToDevice, h->stream), "bc table H2D");
+  CK(cudaMemcpyAsync(h->bc_src[face], src, (size_t)nvar*n*sizeof(long), cudaMemcpyHostToDevice, h->stream), "bc table H2D");
+  CK(cudaMemcpyAsync(h->bc_coef[face], coef, (size_t)nvar*n*sizeof(double), cudaMemcpyHostToDevice, h->stream), "bc table H2D");
+  CK(cudaStreamSynchronize(h->stream), "bc table sync");
+  h->bc_n[face] = n;
+  return 0;
+}
 
 // ---- static potential -------------------------------------------------------------------------------------
 // 1-D coordinate kinds per direction: the four argument forms the reference uses
@@ -379,8 +412,11 @@ int ab2_set_reconstruction(ab2_grid* h, int order)
 int ab2_set_static_grav_pot(ab2_grid* h, ab2_grav_pot_fn phi)
 {
   GridDev& g = h->g;
-  if (!phi) { h->has_grav = false; return 0; }
   const size_t ncell = (size_t)g.n[0]*g.n[1]*g.n[2];
+  CK(cudaStreamSynchronize(h->stream), "grav sync");
+  for (void* p : h->phi_allocs) { cudaFree(p); h->bytes_allocated -= ncell*sizeof(double); }      // a re-set replaces the tables
+  h->phi_allocs.clear();
+  if (!phi) { h->has_grav = false; return 0; }
   // coordinates exactly as cc_pos() and the call sites form them
   std::vector<double> X[3][4];
   bool alias_m[3], alias_mh[3];
@@ -405,8 +441,10 @@ int ab2_set_static_grav_pot(ab2_grid* h, ab2_grav_pot_fn phi)
   auto build = [&](int k0, int k1, int k2) -> double* {
     const int kinds[3] = {k0,k1,k2};
     const int n1 = g.n[0], n2 = g.n[1], n3 = g.n[2];
-    unsigned nthr = std::thread::hardware_concurrency(); if (nthr < 1) nthr = 1; if (nthr > 32) nthr = 32;
-    const char* env = getenv("AB2_GRAV_THREADS"); if (env) { int v = atoi(env); if (v >= 1) nthr = (unsigned)v; }
+    // A problem file's potential is plain C written for a serial code and may touch statics: it is called from ONE thread
+    // unless the user vouches for re-entrancy with AB2_GRAV_THREADS=n (athena_b200.h).
+    unsigned nthr = 1;
+    const char* env = getenv("AB2_GRAV_THREADS"); if (env) { int v = atoi(env); if (v >= 1 && v <= 256) nthr = (unsigned)v; }
     std::vector<std::thread> pool;
     for (unsigned t=0; t<nthr; t++) pool.emplace_back([&, t]() {
       for (int k=(int)t; k<n3; k+=(int)nthr) for (int j=0; j<n2; j++) {
@@ -416,8 +454,11 @@ int ab2_set_static_grav_pot(ab2_grid* h, ab2_grav_pot_fn phi)
       }
     });
     for (auto& th : pool) th.join();
-    double* dptr = dev_alloc(h, ncell, false);
-    if (!dptr) return nullptr;
+    void* raw = nullptr;
+    if (!ab2_check(cudaMalloc(&raw, ncell*sizeof(double)), "cudaMalloc phi table")) return nullptr;
+    double* dptr = (double*)raw;
+    h->phi_allocs.push_back(raw);
+    h->bytes_allocated += ncell*sizeof(double);
     if (!ab2_check(cudaMemcpyAsync(dptr, host.data(), ncell*sizeof(double), cudaMemcpyHostToDevice, h->stream), "phi H2D")) return nullptr;
     if (!ab2_check(cudaStreamSynchronize(h->stream), "phi sync")) return nullptr;
     return dptr;
@@ -443,7 +484,6 @@ int ab2_set_static_grav_pot(ab2_grid* h, ab2_grav_pot_fn phi)
     }
   }
   for (int n=0; n<PHI_NTAB; n++) g.phi[n] = T[n];
-  if (!g.dhalf) { g.dhalf = dev_alloc(h, ncell); if (!g.dhalf) return -1; }
   CK(cudaStreamSynchronize(h->stream), "grav sync");
   h->has_grav = true;
   return 0;

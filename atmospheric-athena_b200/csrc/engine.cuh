@@ -47,7 +47,6 @@ struct GridDev {
   double* F[3][AB2_NVAR];    // first-pass fluxes, physical component order
   double* Ff[3][AB2_NVAR];   // final fluxes (integrate_3d_ctu.c step 9; what step 11-12 and the SMR flux correction read)
   double* eta[3];            // only the unfused correct/final pair goes through these
-  double* dhalf;
   const double* phi[PHI_NTAB];
 };
 
@@ -97,6 +96,7 @@ struct ab2_grid {
   cudaStream_t stream;
   bool own_stream, own_U;
   std::vector<void*> allocs;
+  std::vector<void*> phi_allocs;   // static-potential tables (replaced as a set by ab2_set_static_grav_pot)
   unsigned long long* d_scal;      // device scalars
   unsigned long long* h_scal;      // pinned host mirror
   bool has_grav;
@@ -109,6 +109,13 @@ struct ab2_grid {
   size_t scratch_doubles;
   int chunk_planes;                // 0: scratch spans the whole Grid; else active x3 planes per chunk (scratch depth = that + 8)
   int fuse;                        // 1: k_cfinal (correct + eta + final fused), 0: k_correct / k_final pair
+  int correct3;                    // unfused pair: 1 = the three directions of pass C in one launch (k_correct3)
+  // problem-file boundary functions (bvals_mhd_fun) in table form, one slot per face (ix1, ox1, ix2, ox2, ix3, ox3):
+  // entry t sets U[v][dst[t]] = (src[v][t] >= 0) ? coef[v][t]*U[v][src[v][t]] : coef[v][t]
+  long bc_n[6];
+  long* bc_dst[6];
+  long* bc_src[6];                 // [nvar][n]
+  double* bc_coef[6];              // [nvar][n]
   long n_fixed;                    // Userwork_in_loop replay table
   long* d_fixed_cells;
   double* d_fixed_vals;

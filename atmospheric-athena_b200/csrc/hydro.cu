@@ -13,7 +13,7 @@
 // Pass structure of one step (HBM round trips):
 //   A  k_first_x1 / k_first_march<1|2> : U -> first-pass face states Ul,Ur + fluxes F     (steps 1-3)
 //      (PPM: k_ppm_slope / k_ppm_states / k_ppm_flux per direction instead)
-//   B  k_dhalf                         : d^{n+1/2} from first-pass fluxes (static potential only, step 8a)
+//   B  (d^{n+1/2} from first-pass fluxes, static potential only, step 8a: evaluated inside pass E)
 //   CD k_cfinal                        : ONE kernel for steps 5-7 and 9: a (32 x 8) tile of cells marches along x3; per plane
 //                                        the transverse flux-gradient + gravity corrections of the L/R states of all three
 //                                        face directions and their eta go to a shared-memory tile (1-cell halo recomputed),
@@ -23,6 +23,7 @@
 //   E  k_update                        : gravity source (11a) + three ordered flux-difference updates (12a-c)
 // The scratch (Ul,Ur,F,Ff) may be chunked along x3 (ab2_alloc_scratch): passes A-E then run chunk by chunk on scratch that
 // holds only the chunk's planes, reading U^n from a staged copy so that a chunk's update cannot disturb its neighbour's input.
+#include <stdlib.h>
 #include "engine.cuh"
 #include "physics.cuh"
 
@@ -85,8 +86,11 @@ template <int DIR, int NS> __device__ __forceinline__ S6 sweep_from_phys(const d
 #ifndef AB2_LB_UPDATE
 #define AB2_LB_UPDATE 5
 #endif
+#ifndef AB2_X1_THREADS_PER_SM
+#define AB2_X1_THREADS_PER_SM (AB2_LB_FIRST_X1*128)
+#endif
 template <int NS, bool GRAV, int A1_T>
-__global__ void __launch_bounds__(A1_T, (AB2_LB_FIRST_X1*128)/A1_T) k_first_x1(GridDev g, double dt, int klo)
+__global__ void __launch_bounds__(A1_T, (AB2_X1_THREADS_PER_SM/A1_T) > 0 ? (AB2_X1_THREADS_PER_SM/A1_T) : 1) k_first_x1(GridDev g, double dt, int klo)
 {
   constexpr int A1_F = A1_T-3;
   __shared__ double sW[6][A1_T];
@@ -275,18 +279,6 @@ __global__ void __launch_bounds__(128, AB2_LB_FINAL) k_ppm_flux(GridDev g, Box b
   store_sweep<DIR,NS>(g.F[DIR], c, F);
 }
 
-// Pass B: integrate_3d_ctu.c:2104-2125 (active zones are all the update needs)
-__global__ void k_dhalf(GridDev g, Box b, double dt)
-{
-  int i,j,k; if (!box_cell(b,i,j,k)) return;
-  const long c = (long)k*g.st[2] + (long)j*g.st[1] + i;
-  const double q1 = 0.5*(dt/g.dx[0]), q2 = 0.5*(dt/g.dx[1]), q3 = 0.5*(dt/g.dx[2]);
-  g.dhalf[c] = g.Uin[0][c]
-    - q1*(g.F[0][0][c+1]       - g.F[0][0][c])
-    - q2*(g.F[1][0][c+g.st[1]] - g.F[1][0][c])
-    - q3*(g.F[2][0][c+g.st[2]] - g.F[2][0][c]);
-}
-
 // ---------------------------------------------------------------------------------------------------
 // Steps 5a-b/6a-b/7a-b + 5d/6d/7d for ONE face: the L/R states of the DIR-face of cell cR corrected with the transverse
 // flux gradients (in ascending direction order, as the reference applies them) and the static-potential source terms.
@@ -331,6 +323,14 @@ __device__ __forceinline__ void corrected_states(const GridDev& g, long cR, doub
   }
 }
 
+template <int DIR, int NS> __device__ __forceinline__ double eta_of(const GridDev& g, const double UL[6], const double UR[6])
+{
+  const S6 sl = sweep_from_phys<DIR,NS>(UL), sr = sweep_from_phys<DIR,NS>(UR);
+  double eta;
+  AB2_GUARDED(eta = eta_face(sl, sr, g.Gamma, g.Gamma_1, ar));
+  return eta;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Pass C (unfused pair): corrected L/R states back to HBM, and eta (9a).  One thread per face.
 // ---------------------------------------------------------------------------------------------------
@@ -348,6 +348,35 @@ __global__ void __launch_bounds__(128, AB2_LB_CORRECT) k_correct(GridDev g, Box 
     double eta;
     AB2_GUARDED(eta = eta_face(sl, sr, g.Gamma, g.Gamma_1, ar));
     g.eta[DIR][cR] = eta;
+  }
+}
+
+// Pass C for the three face directions of a cell in ONE launch: every first-pass flux array is needed by the corrections of
+// the two other directions and the potential tables by all three, so one thread doing its cell's three faces back to back
+// finds them in L1 instead of in HBM a second and third time (784 instead of 3 x 328 compulsory bytes per zone).
+template <int NS, bool GRAV>
+__global__ void __launch_bounds__(128, AB2_LB_CORRECT) k_correct3(GridDev g, Box b, double dt)
+{
+  int i,j,k; if (!box_cell(b,i,j,k)) return;          // b = [l+1, u] in every direction; face d needs the transverse indices <= u-1
+  const long cR = (long)k*g.st[2] + (long)j*g.st[1] + i;
+  double UL[6], UR[6];
+  if (j < b.hi[1] && k < b.hi[2]) {
+    corrected_states<0,NS,GRAV>(g, cR, dt, UL, UR);
+#pragma unroll
+    for (int v=0; v<5+NS; v++) { g.Ul[0][v][cR] = UL[v]; g.Ur[0][v][cR] = UR[v]; }
+    g.eta[0][cR] = eta_of<0,NS>(g, UL, UR);
+  }
+  if (i < b.hi[0] && k < b.hi[2]) {
+    corrected_states<1,NS,GRAV>(g, cR, dt, UL, UR);
+#pragma unroll
+    for (int v=0; v<5+NS; v++) { g.Ul[1][v][cR] = UL[v]; g.Ur[1][v][cR] = UR[v]; }
+    g.eta[1][cR] = eta_of<1,NS>(g, UL, UR);
+  }
+  if (i < b.hi[0] && j < b.hi[1]) {
+    corrected_states<2,NS,GRAV>(g, cR, dt, UL, UR);
+#pragma unroll
+    for (int v=0; v<5+NS; v++) { g.Ul[2][v][cR] = UL[v]; g.Ur[2][v][cR] = UR[v]; }
+    g.eta[2][cR] = eta_of<2,NS>(g, UL, UR);
   }
 }
 
@@ -435,14 +464,6 @@ template <int DIR, int NS> __device__ __forceinline__ void solve_store(const Gri
   store_sweep<DIR,NS>(g.Ff[DIR], c, F);
 }
 
-template <int DIR, int NS> __device__ __forceinline__ double eta_of(const GridDev& g, const double UL[6], const double UR[6])
-{
-  const S6 sl = sweep_from_phys<DIR,NS>(UL), sr = sweep_from_phys<DIR,NS>(UR);
-  double eta;
-  AB2_GUARDED(eta = eta_face(sl, sr, g.Gamma, g.Gamma_1, ar));
-  return eta;
-}
-
 // ks..ke: the x3 planes whose final fluxes this launch produces (x1/x2 faces for planes <= e3, x3 faces for all of them);
 // blockIdx.z picks a segment of `kseg` planes.
 template <int NS, bool GRAV>
@@ -526,7 +547,12 @@ __global__ void __launch_bounds__(128, AB2_LB_UPDATE) k_update(GridDev g, Box b,
   for (int v=0; v<5+NS; v++) U[v] = g.Uin[v][c];
   if (GRAV) {
     const double phic = g.phi[PHI_C][c];
-    const double dh = g.dhalf[c];
+    // d^{n+1/2} (step 8a, integrate_3d_ctu.c:2104-2125) from the FIRST-pass mass fluxes, which are still in F
+    const double q1 = 0.5*(dt/g.dx[0]), q2 = 0.5*(dt/g.dx[1]), q3 = 0.5*(dt/g.dx[2]);
+    const double dh = U[0]
+      - q1*(g.F[0][0][c+1]       - g.F[0][0][c])
+      - q2*(g.F[1][0][c+g.st[1]] - g.F[1][0][c])
+      - q3*(g.F[2][0][c+g.st[2]] - g.F[2][0][c]);
 #pragma unroll
     for (int d=0; d<3; d++) {
       const double phir = g.phi[PHI_PH0+d][c], phil = g.phi[PHI_MH0+d][c];
@@ -576,6 +602,19 @@ __global__ void k_bvals(GridDev g, int nvar, int dir, int side, int flag, Box tr
   }
 }
 
+// a problem file's boundary function in table form (api.cu ab2_set_bc_table): ghost cell <- constant, or +-(a cell of the same variable)
+__global__ void k_bvals_table(GridDev g, int nvar, long n, const long* dst, const long* src, const double* coef)
+{
+  const long t = (long)blockIdx.x*blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const long d = dst[t];
+  for (int v=0; v<nvar; v++) {
+    const long sidx = src[(long)v*n + t];
+    const double c = coef[(long)v*n + t];
+    g.U[v][d] = (sidx >= 0) ? c*g.U[v][sidx] : c;
+  }
+}
+
 int hydro_bvals(ab2_grid* h, const int bc[6])
 {
   GridDev& g = h->g;
@@ -594,6 +633,12 @@ int hydro_bvals(ab2_grid* h, const int bc[6])
     const long nt = (long)(tr.hi[A]-tr.lo[A]+1)*(tr.hi[B]-tr.lo[B]+1)*NG;
     for (int side=0; side<2; side++) {
       const int flag = bc[2*dir+side];
+      if (flag == -2) {                       // the problem file's own function for this face, in table form
+        const int f = 2*dir+side;
+        if (h->bc_n[f] > 0)
+          AB2_LAUNCH(h, KID_BVALS, (k_bvals_table<<<(unsigned)((h->bc_n[f]+255)/256), 256, 0, h->stream>>>(g, nvar, h->bc_n[f], h->bc_dst[f], h->bc_src[f], h->bc_coef[f])));
+        continue;
+      }
       if (flag != 1 && flag != 2 && flag != 4 && flag != 5) continue;   // <=0: neighbouring Grid / prolongated face
       AB2_LAUNCH(h, KID_BVALS, (k_bvals<<<(unsigned)((nt+255)/256), 256, 0, h->stream>>>(g, nvar, dir, side, flag, tr)));
     }
@@ -729,15 +774,17 @@ static int integrate_range(ab2_grid* h, const GridDev& g, double dt, int ka, int
   } else {
     const int nf = g.nx[0]+4;
     int bestT = 128; double bestw = 1e30;
-    for (int T : {64, 96, 128, 160, 192, 256}) {          // least padded tile width
+    for (int T : {64, 96, 128, 136, 160, 192, 256}) {     // least padded tile width (136: two tiles cover the 260 faces of a 256-zone row)
       const int nt = (nf + T-4)/(T-3);
       const double w = (double)nt*T/nf + 0.02*(256.0/T);  // padding, with a small bias against very narrow tiles
       if (w < bestw) { bestw = w; bestT = T; }
     }
+    if (const char* env = getenv("AB2_X1_TILE")) { const int T = atoi(env); if (T == 64 || T == 96 || T == 128 || T == 136 || T == 160 || T == 192 || T == 256) bestT = T; }
     const dim3 grid((nf + bestT-4)/(bestT-3), u[1]-l[1]+1, u[2]-l[2]+1);
     switch (bestT) {
       case 64:  AB2_LAUNCH(h, KID_FIRST_X1, (k_first_x1<NS,GRAV,64><<<grid, 64, 0, st>>>(g, dt, l[2]))); break;
       case 96:  AB2_LAUNCH(h, KID_FIRST_X1, (k_first_x1<NS,GRAV,96><<<grid, 96, 0, st>>>(g, dt, l[2]))); break;
+      case 136: AB2_LAUNCH(h, KID_FIRST_X1, (k_first_x1<NS,GRAV,136><<<grid, 136, 0, st>>>(g, dt, l[2]))); break;
       case 160: AB2_LAUNCH(h, KID_FIRST_X1, (k_first_x1<NS,GRAV,160><<<grid, 160, 0, st>>>(g, dt, l[2]))); break;
       case 192: AB2_LAUNCH(h, KID_FIRST_X1, (k_first_x1<NS,GRAV,192><<<grid, 192, 0, st>>>(g, dt, l[2]))); break;
       case 256: AB2_LAUNCH(h, KID_FIRST_X1, (k_first_x1<NS,GRAV,256><<<grid, 256, 0, st>>>(g, dt, l[2]))); break;
@@ -752,8 +799,7 @@ static int integrate_range(ab2_grid* h, const GridDev& g, double dt, int ka, int
     AB2_LAUNCH(h, KID_FIRST_X3, (k_first_march<2,NS,GRAV><<<g3, 128, 0, st>>>(g, dt, seg3, l[1], u[1]-l[1]+1, l[2]+1, u[2])));
   }
   Box act; for (int a=0; a<3; a++) { act.lo[a] = s[a]; act.hi[a] = e[a]; }
-  // Pass B
-  if (GRAV) AB2_LAUNCH(h, KID_DHALF, (k_dhalf<<<box_grid(act,128), 128, 0, st>>>(g, act, dt)));
+  // Pass B (d^{n+1/2}) is folded into pass E: the first-pass fluxes outlive pass D now that the final ones have their own arrays
   if (h->fuse) {
     // Passes C+D in one kernel: x3 planes [s, e+1]
     const int npl = e[2]+1 - s[2] + 1;
@@ -762,6 +808,10 @@ static int integrate_range(ab2_grid* h, const GridDev& g, double dt, int ka, int
     AB2_LAUNCH(h, KID_CFINAL, (k_cfinal<NS,GRAV><<<grid, dim3(CF_TX,CF_TY,1), 0, st>>>(g, dt, s[2], e[2]+1, e[2], kseg)));
   } else {
     // Pass C: faces of direction d over [l+1, u-1] transversally and [l+1, u] along d
+    if (h->correct3) {
+      Box b; for (int a=0; a<3; a++) { b.lo[a] = l[a]+1; b.hi[a] = u[a]; }
+      AB2_LAUNCH(h, KID_CORRECT_X1, (k_correct3<NS,GRAV><<<box_grid(b,128), 128, 0, st>>>(g, b, dt)));
+    } else
     for (int d=0; d<3; d++) {
       Box b; for (int a=0; a<3; a++) { b.lo[a] = l[a]+1; b.hi[a] = (a == d) ? u[a] : u[a]-1; }
       if (d == 0) AB2_LAUNCH(h, KID_CORRECT_X1+0, (k_correct<0,NS,GRAV><<<box_grid(b,128), 128, 0, st>>>(g, b, dt)));

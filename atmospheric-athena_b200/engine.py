@@ -72,7 +72,8 @@ EXPORTS = ["ab2_last_error", "ab2_version", "ab2_device_count", "ab2_grid_create
            "ab2_set_riemann_solver", "ab2_set_reconstruction",
            "ab2_comm_get_unique_id", "ab2_comm_init_rank", "ab2_comm_destroy", "ab2_comm_rank", "ab2_comm_size",
            "ab2_comm_exchanges", "ab2_comm_reductions", "ab2_comm_allreduce", "ab2_comm_bcast", "ab2_grid_set_comm",
-           "ab2_exchange_x3", "ab2_set_scratch_planes", "ab2_scratch_planes"]
+           "ab2_exchange_x3", "ab2_set_scratch_planes", "ab2_scratch_planes", "ab2_set_bc_table", "ab2_pin_host", "ab2_unpin_host",
+           "ab2_output_vtk_field", "ab2_output_active_var"]
 # libathena_b200_units.so (include/athena_b200_units.h): function-level test hooks, not part of the bound interface
 UNITS_LIB_PATH = os.path.join(_HERE, "csrc", "libathena_b200_units.so")
 UNIT_EXPORTS = ["ab2_unit_roe_flux", "ab2_unit_convert", "ab2_unit_lr_states", "ab2_unit_ieee", "ab2_unit_libm",
@@ -163,6 +164,11 @@ def lib():
     L.ab2_grid_set_comm.argtypes = [vp, vp, C.c_int, C.c_int]
     L.ab2_exchange_x3.argtypes = [vp]
     L.ab2_set_scratch_planes.argtypes = [vp, C.c_int]
+    L.ab2_set_bc_table.argtypes = [vp, C.c_int, C.c_long, C.POINTER(C.c_long), C.POINTER(C.c_long), dp]
+    L.ab2_pin_host.argtypes = [vp, C.c_longlong]
+    L.ab2_unpin_host.argtypes = [vp]
+    L.ab2_output_vtk_field.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_float)]
+    L.ab2_output_active_var.argtypes = [vp, C.c_int, dp]
     L.ab2_scratch_planes.argtypes = [vp]
     _lib = L
     return L
@@ -302,6 +308,27 @@ class Grid:
 
     def synchronize(self):
         self._ck(lib().ab2_synchronize(self.h))
+
+    def set_bc_table(self, face, dst, src, coef):
+        """A problem file's boundary function in table form (ab2_set_bc_table): dst [n], src [nvar][n] (-1: constant), coef [nvar][n]"""
+        dst = np.ascontiguousarray(dst, dtype=np.int64)
+        src = np.ascontiguousarray(src, dtype=np.int64)
+        coef = np.ascontiguousarray(coef, dtype=np.float64)
+        assert src.shape == (self.nvar, len(dst)) and coef.shape == src.shape
+        lp = C.POINTER(C.c_long)
+        self._ck(lib().ab2_set_bc_table(self.h, int(face), len(dst), dst.ctypes.data_as(lp), src.ctypes.data_as(lp), coef.ctypes.data_as(dp)))
+
+    def output_vtk_field(self, field, prim=False):
+        """dump_vtk's bytes for one CELL_DATA field of the active zones: float32 big-endian, as a uint8 array"""
+        n = self.nx[0] * self.nx[1] * self.nx[2] * (3 if field == 1 else 1)
+        out = np.empty(n, dtype=np.float32)
+        self._ck(lib().ab2_output_vtk_field(self.h, int(field), 1 if prim else 0, out.ctypes.data_as(C.POINTER(C.c_float))))
+        return out.view(np.uint8)
+
+    def output_active_var(self, var):
+        out = np.empty((self.nx[2], self.nx[1], self.nx[0]))
+        self._ck(lib().ab2_output_active_var(self.h, int(var), out.ctypes.data_as(dp)))
+        return out
 
     def set_scratch_planes(self, planes):
         """x3-chunked CTU scratch: `planes` active planes per chunk, 0 = whole Grid (results do not depend on it)"""

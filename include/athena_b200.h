@@ -102,7 +102,9 @@ int ab2_max_wave_speeds(ab2_grid* g, double out[3]);
 int ab2_new_dt(ab2_grid* g, double cour_no, double dt_old, int nstep, double time, double tlim,
                ab2_reduce_fn reduce, void* ctx, double* dt_out);
 /* StaticGravPot enrolment: tabulates the user's potential on the host at exactly the arguments the reference
- * passes (integrate_3d_ctu.c:334-336,1172-1215,1468-1522,1878-1933,2746-2777) and uploads the tables. NULL clears. */
+ * passes (integrate_3d_ctu.c:334-336,1172-1215,1468-1522,1878-1933,2746-2777) and uploads the tables. NULL clears;
+ * a second call replaces the tables.  The callback runs on ONE host thread (problem-file potentials are written for a
+ * serial code); AB2_GRAV_THREADS=n in the environment tabulates with n threads if the function is re-entrant. */
 int ab2_set_static_grav_pot(ab2_grid* g, ab2_grav_pot_fn phi);
 /* integrate_3d_ctu (integrators/integrate_3d_ctu.c:110-3368) with GridS.dt = dt. */
 int ab2_integrate_3d_ctu(ab2_grid* g, double dt);
@@ -120,6 +122,12 @@ int ab2_set_reconstruction(ab2_grid* g, int order);
  * vals[6][n] every step, e.g. prob/ioniz_sphere.c:255-306. */
 int ab2_set_fixed_cells(ab2_grid* g, long n, const long* cells, const double* vals);
 int ab2_apply_fixed_cells(ab2_grid* g);
+/* A problem file's boundary function (bvals_mhd_fun, bvals_mhd.c:917-947) in table form, so it need not run on the host:
+ * for face = 0..5 (ix1, ox1, ix2, ox2, ix3, ox3) entry t sets, for every variable v,
+ *   U[v][dst[t]] = src[v*n+t] >= 0 ? coef[v*n+t] * U[v][src[v*n+t]] : coef[v*n+t]
+ * (flat cell indices incl. ghosts) -- constants (inflow) and signed copies (reflection, outflow, periodic wrap).  A face
+ * whose table is set is applied by ab2_bvals_mhd when bc[face] == -2, in the reference's order (x1, x2, x3).  n = 0 clears. */
+int ab2_set_bc_table(ab2_grid* g, int face, long n, const long* dst, const long* src, const double* coef);
 
 /* ion_radtransfer_init (ionradiation/ionrad.c:64-149, ionrad_3d.c:739-814) */
 int ab2_ion_init(ab2_grid* g, const ab2_ion_par* par);
@@ -160,6 +168,18 @@ int ab2_ion_radtransfer_3d_fine(ab2_grid* g, double tcoarse, double* dt, int* ni
                                 ab2_reduce_fn reduce, void* ctx);
 /* the reference's file-static tcoarse (ionrad_3d.c:47,1028): dt_done of the last root-level ab2_ion_radtransfer_3d */
 double ab2_ion_coarse_time(const ab2_grid* g);
+
+/* ---- the device side of the driver's writers ---------------------------------------------------------- */
+/* Page-lock a host array the driver owns (GridS.U) so the coherence copies run at PCIe speed straight into it. */
+int ab2_pin_host(void* p, long long bytes);
+int ab2_unpin_host(void* p);
+/* One CELL_DATA field of dump_vtk (dump_vtk.c:164-312) for the active zones, the very bytes the reference writes: float32,
+ * big-endian, k-j-i order.  field 0 density, 1 momentum / velocity (3 interleaved components), 2 total energy / pressure,
+ * 3 scalar / specific scalar; prim != 0: primitive variables (Cons_to_Prim, convert_var.c:97-160).  dst: host floats. */
+int ab2_output_vtk_field(ab2_grid* g, int field, int prim, float* dst);
+/* Active zones of one conserved variable as FP64 in k-j-i order: a DENSITY / n-MOMENTUM / ENERGY / SCALAR block of
+ * dump_restart (restart.c:548-760) without the ghost zones and the AoS transposition of the full mirror. */
+int ab2_output_active_var(ab2_grid* g, int var, double* dst);
 
 /* ---- per-kernel device timing (bench.py's roofline) ------------------------------------------------------ */
 /* When enabled every kernel launch is bracketed by CUDA events on the launching stream; ab2_profile_read drains

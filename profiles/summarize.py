@@ -20,7 +20,7 @@ def short(name):
     if not m:
         return name[:40]
     base, targs = m.group(1), m.group(2) or ""
-    if base in ("k_first_march", "k_correct", "k_final"):
+    if base in ("k_first_march", "k_correct", "k_final", "k_ppm_slope", "k_ppm_states", "k_ppm_flux"):
         return f"{base}<{targs[1:].split(',')[0].strip()}>"
     if base == "k_ion_rates":
         return "k_ion_rates<fused update>" if targs.startswith("<1") or "true" in targs else "k_ion_rates"
@@ -111,7 +111,79 @@ def full(tag):
     json.dump(traffic, open(os.path.join(HERE, "ncu_traffic.json"), "w"), indent=1)
 
 
+def full_multi(tag, names):
+    """Round-2 captures (profiles/capture2.sh): one --set full csv per workload, gpurun_out/<tag>_<name>_ncu_full_raw.csv ->
+    profiles/<tag>_ncu_full_table.md (a section per workload) + profiles/<tag>_<name>_ncu_full_raw.csv.gz + ncu_traffic.json
+    (first capture that has a kernel wins: `default` is the bench workload)."""
+    import gzip
+    titles = {"default": "bench.py default workload (256^3 ioniz_sphere), unfused correct/final pair, separate ion kernels",
+              "fused": "the same with AB2_HYDRO_FUSE=1 (k_cfinal) and AB2_ION_FUSE=1 (k_ion_rates<fused update>)",
+              "ppm": "--workload blast --order 3 (PPM pass A)", "smr": "--workload ioniz_smr (shipped 5-level deck)"}
+    traffic = {}
+    with open(os.path.join(HERE, f"{tag}_ncu_full_table.md"), "w") as f:
+        f.write(f"# ncu --set full, {tag}\n\n`profiles/capture2.sh {tag}` on one B200: every command first ran plain (exit 0), then its launch list, "
+                "then ONE `ncu --set full --clock-control none --import-source on -k regex:^k_` capture.  Averages over the captured launches of "
+                "each kernel; times are cold-cache and serialised (compare shares, not absolutes, with bench.py's CUDA-event times).\n")
+        for name in names:
+            src = os.path.join(OUT, f"{tag}_{name}_ncu_full_raw.csv")
+            if not os.path.exists(src) or os.path.getsize(src) < 1000:
+                f.write(f"\n## {name}: capture missing\n")
+                continue
+            rows = list(csv.reader(open(src)))
+            hdr, units = rows[0], rows[1]
+            ni = hdr.index("Kernel Name")
+            col = {h: i for i, h in enumerate(hdr)}
+            for h, i in list(col.items()):
+                col.setdefault(h.split(".TriageCompute.")[-1], i)
+
+            def val(r, nm, scale_bytes=False):
+                if nm not in col:
+                    return float("nan")
+                i = col[nm]
+                x = fnum(r[i])
+                if scale_bytes:
+                    x *= {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(units[i], 1)
+                return x
+
+            def ms(r):
+                i = col["gpu__time_duration.sum"]
+                return fnum(r[i]) * {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(units[i], 1e-6)
+
+            agg = collections.OrderedDict()
+            for r in rows[2:]:
+                agg.setdefault(short(r[ni]), []).append(r)
+            with gzip.open(os.path.join(HERE, f"{tag}_{name}_ncu_full_raw.csv.gz"), "wt") as gz:
+                gz.write(open(src).read())
+            f.write(f"\n## {name}: {titles.get(name, name)}\n\n"
+                    "| kernel | launches | time/launch (ms) | DRAM read (GB) | DRAM write (GB) | DRAM % | FP64 pipe % | issue % | LSU pipe % | L1 hit % | L2 hit % | warps active % | regs | smem/block (KB) | warp-inst (M) |\n"
+                    "|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|\n")
+            for k, rs in agg.items():
+                n = len(rs)
+                avg = lambda nm, **kw: sum(val(r, nm, **kw) for r in rs) / n
+                t = sum(ms(r) for r in rs) / n
+                rd, wr = avg("dram__bytes_read.sum", scale_bytes=True), avg("dram__bytes_write.sum", scale_bytes=True)
+                dpct = avg("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed")
+                fp64 = avg("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active")
+                issue = avg("smsp__issue_active.avg.pct_of_peak_sustained_active")
+                lsu = avg("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active")
+                l1 = avg("l1tex__t_sector_hit_rate.pct")
+                l2 = avg("lts__t_sector_hit_rate.pct")
+                wa = avg("sm__warps_active.avg.pct_of_peak_sustained_active")
+                regs = avg("launch__registers_per_thread")
+                smem = (avg("launch__shared_mem_per_block_static", scale_bytes=True) + avg("launch__shared_mem_per_block_dynamic", scale_bytes=True)) / 1e3
+                inst = avg("smsp__inst_executed.sum") / 1e6
+                f.write(f"| {k} | {n} | {t:.3f} | {rd / 1e9:.3f} | {wr / 1e9:.3f} | {dpct:.1f} | {fp64:.1f} | {issue:.1f} | {lsu:.1f} | {l1:.1f} | {l2:.1f} | {wa:.1f} | {regs:.0f} | {smem:.1f} | {inst:.0f} |\n")
+                if k not in traffic and t > 0.02:
+                    traffic[k] = {"dram_bytes_per_launch": rd + wr, "time_ms": t, "dram_pct": dpct, "fp64_pipe_pct": fp64, "issue_pct": issue,
+                                  "warps_active_pct": wa, "regs": regs, "capture": f"{tag}_{name}"}
+    json.dump(traffic, open(os.path.join(HERE, "ncu_traffic.json"), "w"), indent=1)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 2 and sys.argv[2] == "multi":
+        full_multi(sys.argv[1], sys.argv[3:] or ["default", "fused", "ppm", "smr"])
+        print("wrote profiles/%s_ncu_full_table.md" % sys.argv[1])
+        sys.exit(0)
     tag = sys.argv[1]
     bench = sys.argv[2] if len(sys.argv) > 2 else None
     launches(tag, bench)

@@ -48,6 +48,8 @@ CASES = {
     # static potential + Userwork reset on a Grid with three different, partly odd extents (the potential tables cannot all alias)
     "ionizodd": ("ioniz_sphere", "ioniz_sphere.athinput",
                  ["domain1/Nx1=21", "domain1/Nx2=18", "domain1/Nx3=15"], [1]),
+    # a problem-file boundary function (prob/jet.c jet_iib on ix1: inflow constants inside the jet radius, reflection outside)
+    "jet24": ("jet", "jet.athinput", [], [6]),
     "ifront32": ("ifront", "ifront.athinput",
                  ["domain1/Nx1=32", "domain1/Nx2=16", "domain1/Nx3=16"], [1, 4]),
     "ioniz24": ("ioniz_sphere", "ioniz_sphere.athinput",

@@ -203,3 +203,47 @@ def test_dropin_linear_wave_convergence_known_answer(build, ref):
         assert row == ref[n].split(), f"N={n}: {row}"       # the very digits the reference prints
         rms[n] = float(row[3])
     assert rms[16] / rms[32] > 3.3, "second-order convergence of the sound wave (the reference reaches 3.4-3.5 on these grids)"
+
+
+def test_dropin_user_boundary_function_as_device_table():
+    """prob/jet.c enrols jet_iib on the ix1 face with bvals_mhd_fun (inflow constants inside the jet radius,
+    reflection outside).  The shim turns it into a device table (constants + signed copies) instead of a host round trip
+    per call; both paths must reproduce the reference's dump bit for bit."""
+    case = Case("jet24_k6")
+    for force_host in (False, True):
+        if force_host:
+            os.environ["AB2_USER_BC"] = "host"
+        try:
+            d1, _, r = run_dropin(case)
+        finally:
+            os.environ.pop("AB2_USER_BC", None)
+        assert d1["nstep"] == case.nsteps and d1["time"] == float(case.gold["time1"]) and d1["dt"] == float(case.gold["dt1"])
+        for v in case.U1:
+            assert np.array_equal(d1["grids"][0][v], case.U1[v]), (force_host, v)
+        assert ("boundary function of face 0 runs on the device" in r.stdout) == (not force_host), r.stdout[-1500:]
+
+
+@pytest.mark.parametrize("out", ["cons", "prim"])
+@pytest.mark.parametrize("cfg,deck,nlim", [("ifront", "ifront.athinput", 3), ("blast", "blast.athinput", 4)])
+def test_dropin_vtk_dumps_are_the_reference_bytes(cfg, deck, nlim, out):
+    """dump_vtk's float32 big-endian fields are produced on the device (ab2_output_vtk_field) and written by the
+    shim; conserved and primitive dumps must be byte-identical to the files the reference binary writes."""
+    ref = os.path.join(ROOT, "oracle", "_ref", cfg, "athena")
+    exe = os.path.join(ROOT, "build", "dropin", cfg, "athena")
+    if not (os.path.exists(ref) and os.path.exists(exe)):
+        pytest.skip("needs oracle/_ref and build/dropin")
+    text = open(os.path.join(DECKS, deck)).read()
+    assert "maxout      = 1" in text
+    text = text.replace("maxout      = 1", "maxout      = 2")
+    text += f"\n<output2>\nout_fmt = vtk\nout     = {out}\ndt      = 1.0e30\n"
+    files = {}
+    for tag, binary in (("ref", ref), ("b200", exe)):
+        with tempfile.TemporaryDirectory() as tmp:
+            open(os.path.join(tmp, "deck"), "w").write(text)
+            cmd = [binary, "-i", "deck", f"time/nlim={nlim}", "domain1/Nx1=24", "domain1/Nx2=16", "domain1/Nx3=20"]
+            r = subprocess.run(cmd, cwd=tmp, capture_output=True, text=True)
+            assert r.returncode == 0, tag + r.stdout[-1500:] + r.stderr[-1500:]
+            files[tag] = {f: open(os.path.join(tmp, f), "rb").read() for f in sorted(os.listdir(tmp)) if f.endswith(".vtk")}
+    assert len(files["ref"]) == 2 and sorted(files["ref"]) == sorted(files["b200"]), (sorted(files["ref"]), sorted(files["b200"]))
+    for f in files["ref"]:
+        assert files["b200"][f] == files["ref"][f], f"{f}: {len(files['b200'][f])} vs {len(files['ref'][f])} bytes"

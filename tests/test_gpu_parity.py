@@ -283,3 +283,50 @@ def test_no_device_memory_growth_and_launch_count():
     R.run(case.nsteps + 3)
     assert R.G.bytes_allocated == b0
     assert R.G.kernel_launches > l0
+
+
+def test_device_side_writer_fields_and_bc_table():
+    """ab2_output_vtk_field / ab2_output_active_var against numpy on the downloaded state; ab2_set_bc_table against the built-in
+    reflecting boundary (the same ghost cells written as a signed-copy table)."""
+    from athena_b200 import engine as eng
+    rng = np.random.default_rng(11)
+    G = eng.Grid((12, 8, 6), (0.1, 0.1, 0.1), (0, 0, 0), 5 / 3, 1)
+    U = {v: rng.uniform(0.5, 2.0, size=G.shape) for v in VARS}
+    U["E"] += 5.0
+    G.upload(U)
+    act = {v: U[v][4:-4, 4:-4, 4:-4] for v in VARS}
+    be = lambda a: np.ascontiguousarray(a, dtype=np.float64).astype(np.float32).astype(">f4").view(np.uint8).ravel()
+    assert np.array_equal(G.output_vtk_field(0), be(act["d"]))
+    assert np.array_equal(G.output_vtk_field(1), be(np.stack([act["M1"], act["M2"], act["M3"]], axis=-1)))
+    assert np.array_equal(G.output_vtk_field(2), be(act["E"]))
+    assert np.array_equal(G.output_vtk_field(3), be(act["s"]))
+    di = 1.0 / act["d"]
+    assert np.array_equal(G.output_vtk_field(1, prim=True), be(np.stack([act["M1"] * di, act["M2"] * di, act["M3"] * di], axis=-1)))
+    P = (act["E"] - 0.5 * (act["M1"] ** 2 + act["M2"] ** 2 + act["M3"] ** 2) * di) * (5 / 3 - 1.0)
+    assert np.array_equal(G.output_vtk_field(2, prim=True), be(P))
+    for n, v in enumerate(VARS):
+        assert np.array_equal(G.output_active_var(n), act[v])
+    # reflecting ix1 as a table: ghost (k,j,4-l) <- active (k,j,4+l-1), M1 negated, j,k active (bvals_mhd.c:959-977)
+    n3, n2, n1 = G.shape
+    dst, src = [], []
+    for k in range(4, n3 - 4):
+        for j in range(4, n2 - 4):
+            for l in range(1, 5):
+                dst.append((k * n2 + j) * n1 + 4 - l); src.append((k * n2 + j) * n1 + 4 + l - 1)
+    nv = 6
+    S = np.tile(np.array(src), (nv, 1)); Cf = np.ones((nv, len(dst))); Cf[1] = -1.0
+    G.set_bc_table(0, dst, S, Cf)
+    G.bvals_mhd([-2, 0, 0, 0, 0, 0])
+    a = G.download()
+    G.upload(U)
+    G.bvals_mhd([1, 0, 0, 0, 0, 0])
+    b = G.download()
+    for v in VARS:
+        assert np.array_equal(a[v], b[v]), v
+    # constants
+    Cf2 = rng.normal(size=(nv, len(dst)))
+    G.set_bc_table(0, dst, -np.ones_like(S), Cf2)
+    G.bvals_mhd([-2, 0, 0, 0, 0, 0])
+    a = G.download()
+    for n, v in enumerate(VARS):
+        assert np.array_equal(a[v].ravel()[np.array(dst)], Cf2[n])
