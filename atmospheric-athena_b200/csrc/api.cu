@@ -190,7 +190,10 @@ ab2_grid* ab2_grid_create(const ab2_grid_desc* d)
   // CTU scratch (also the staging area of the AoS transposes).  AB2_CHUNK_PLANES=n forces x3 chunks of n active planes;
   // by default the scratch spans the whole Grid when that leaves room for the rest of the Grid's arrays, else it is chunked.
   h->scratch = nullptr; h->scratch_doubles = 0; h->chunk_planes = 0;
-  h->fuse = 1;
+  // Passes C+D: the pair k_correct3 / k_final is the default.  The fused k_cfinal halves their HBM traffic (ncu: 25.9 -> 11.7 GB
+  // per 256^3 step) but runs at 24 % occupancy with 30 % more instructions (halo + recomputed corrections) and measures
+  // SLOWER on B200 (6.3 vs 5.0 ms; profiles/r2a_ncu_full_table.md): opt-in with AB2_HYDRO_FUSE=1.
+  h->fuse = 0;
   if (const char* env = getenv("AB2_HYDRO_FUSE")) h->fuse = (atoi(env) != 0);
   h->correct3 = 1;
   if (const char* env = getenv("AB2_CORRECT3")) h->correct3 = (atoi(env) != 0);

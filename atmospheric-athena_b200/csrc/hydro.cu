@@ -774,7 +774,10 @@ static int integrate_range(ab2_grid* h, const GridDev& g, double dt, int ka, int
   } else {
     const int nf = g.nx[0]+4;
     int bestT = 128; double bestw = 1e30;
-    for (int T : {64, 96, 128, 136, 160, 192, 256}) {     // least padded tile width (136: two tiles cover the 260 faces of a 256-zone row)
+    // least padded tile width.  (136, two tiles for the 260 faces of a 256-zone row at 98 % busy lanes, was measured SLOWER
+    // than three tiles of 96 at 90 %: 1.87 vs 1.62 ms -- 5 resident blocks of 96 hide latency better than 3 of 136; it stays
+    // selectable through AB2_X1_TILE for experiments.)
+    for (int T : {64, 96, 128, 160, 192, 256}) {
       const int nt = (nf + T-4)/(T-3);
       const double w = (double)nt*T/nf + 0.02*(256.0/T);  // padding, with a small bias against very narrow tiles
       if (w < bestw) { bestw = w; bestT = T; }

@@ -369,6 +369,8 @@ def gpu_arm(args):
         d = dist
     assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
+    # the bench's own static potential (csrc/problems.c ab2_planet_pot) is re-entrant: tabulate it with several host threads
+    os.environ.setdefault("AB2_GRAV_THREADS", str(max(1, min(32, (os.cpu_count() or 1) // max(1, world)))))
     parity = parity_gate(args.workload, rank, world, local, d, args.riemann, args.order) if not args.no_parity_gate else None
     if parity is not None and parity["bit_equal"] is False:
         if rank == 0:
@@ -517,7 +519,10 @@ def gpu_arm(args):
                        "zones_per_gpu": zones_local, "parallelism": f"x3-slabs x{world}",
                        "variant": {"order": args.order, "riemann": args.riemann},
                        "ion_iterations_per_step": round(n_iter, 2), "l2": "working set >> L2 (state + scratch = "
-                       f"{G.bytes_allocated / 2**30:.1f} GiB per GPU), no flush needed", "setup_s": round(t_setup, 1)},
+                       f"{G.bytes_allocated / 2**30:.1f} GiB per GPU), no flush needed", "setup_s": round(t_setup, 1),
+                       "device_bytes_per_gpu": int(G.bytes_allocated), "scratch_planes": G.scratch_planes,
+                       "hydro_passes": "fused correct+final (k_cfinal)" if os.environ.get("AB2_HYDRO_FUSE", "0") == "1" else "k_correct3 + k_final pair",
+                       "comm": (dict(R.comm.counters, where="NCCL inside libathena_b200 (csrc/comm.cu)") if R.comm else None)},
             "parity": parity,
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "dropin": dropin, "kernels": ktab,
         }
@@ -578,6 +583,7 @@ def smr_arm(args):
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
+    os.environ.setdefault("AB2_GRAV_THREADS", str(max(1, min(32, (os.cpu_count() or 1) // max(1, world)))))
     par = ParFile.par_open(os.path.join(DECKS, "ioniz_sphere_hires.athinput"))
     nlev = par.par_geti("job", "num_domains")
     zones_total = sum(par.par_geti(f"domain{n + 1}", "Nx1") * par.par_geti(f"domain{n + 1}", "Nx2") * par.par_geti(f"domain{n + 1}", "Nx3")

@@ -122,15 +122,21 @@ def gpu_run(case, fuse=None, planes=None):
 
 @pytest.mark.parametrize("name", ["blast16_k6", "blastmix_k5", "blasttiny_k5", "blast16hllc_k6", "blast16ppm_k6", "ifront32_k4",
                                   "ioniz24_k3", "ionizodd_k1", "ifronttiny_k3"])
-@pytest.mark.parametrize("variant", ["unfused", "chunk4", "chunk8_unfused", "chunk5"])
+@pytest.mark.parametrize("variant", ["fused", "chunk4_fused", "chunk8", "chunk5", "pairwise_correct"])
 def test_hydro_pass_variants_bit_exact_vs_reference(name, variant):
-    """The step's pass structure does not show in the results: the unfused correct/final pair (corrected states and eta
-    through HBM) and the x3-chunked scratch (chunks of 4, 5 or 8 active planes, incl. a ragged last chunk) reproduce the
-    reference's dump bit for bit, exactly like the default fused, unchunked path of the tests below."""
+    """The step's pass structure does not show in the results: the fused correct+eta+final kernel (k_cfinal: corrected states
+    and eta in shared memory only), pass C as one or three launches, and the x3-chunked scratch (chunks of 4, 5 or 8 active
+    planes, incl. a ragged last chunk) reproduce the reference's dump bit for bit, exactly like the default path of the
+    tests below (k_correct3 / k_final pair, whole-Grid scratch)."""
     case = Case(name)
-    fuse = 0 if "unfused" in variant else 1
-    planes = {"unfused": None, "chunk4": 4, "chunk8_unfused": 8, "chunk5": 5}[variant]
-    R = gpu_run(case, fuse=fuse, planes=planes)
+    fuse = 1 if "fused" in variant else 0
+    planes = {"fused": None, "chunk4_fused": 4, "chunk8": 8, "chunk5": 5, "pairwise_correct": None}[variant]
+    if variant == "pairwise_correct":
+        os.environ["AB2_CORRECT3"] = "0"          # pass C as three launches, one per face direction
+    try:
+        R = gpu_run(case, fuse=fuse, planes=planes)
+    finally:
+        os.environ.pop("AB2_CORRECT3", None)
     out = R.G.download_active()
     assert R.time == float(case.gold["time1"]) and R.dt == float(case.gold["dt1"])
     for v in case.U1:
@@ -302,8 +308,10 @@ def test_device_side_writer_fields_and_bc_table():
     assert np.array_equal(G.output_vtk_field(3), be(act["s"]))
     di = 1.0 / act["d"]
     assert np.array_equal(G.output_vtk_field(1, prim=True), be(np.stack([act["M1"] * di, act["M2"] * di, act["M3"] * di], axis=-1)))
-    P = (act["E"] - 0.5 * (act["M1"] ** 2 + act["M2"] ** 2 + act["M3"] ** 2) * di) * (5 / 3 - 1.0)
-    assert np.array_equal(G.output_vtk_field(2, prim=True), be(P))
+    # x*x, not x**2: numpy's power loop may go through a vector libm that is not correctly rounded on every host
+    P = (act["E"] - 0.5 * (act["M1"] * act["M1"] + act["M2"] * act["M2"] + act["M3"] * act["M3"]) * di) * (5 / 3 - 1.0)
+    got = G.output_vtk_field(2, prim=True)
+    assert np.array_equal(got, be(P)), f"{(got != be(P)).sum()} differing bytes; floats {got.view('>f4')[:4]} vs {be(P).view('>f4')[:4]}"
     for n, v in enumerate(VARS):
         assert np.array_equal(G.output_active_var(n), act[v])
     # reflecting ix1 as a table: ghost (k,j,4-l) <- active (k,j,4+l-1), M1 negated, j,k active (bvals_mhd.c:959-977)
