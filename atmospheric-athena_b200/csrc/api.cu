@@ -204,7 +204,7 @@ ab2_grid* ab2_grid_create(const ab2_grid_desc* d)
       size_t free_b = 0, total_b = 0;
       cudaMemGetInfo(&free_b, &total_b);
       const size_t P = (size_t)g.n[0]*g.n[1]*sizeof(double);
-      const size_t rest = (size_t)34*ncell*sizeof(double);        // ion arrays, potential tables, dhalf still to come (upper estimate)
+      const size_t rest = (size_t)24*ncell*sizeof(double);        // still to come: ion arrays (8.5), EdgeFlux (2), potential tables (4 typical, up to 22)
       const size_t full = (size_t)(12*nvar + 3)*ncell*sizeof(double);
       if (full + rest > (size_t)(0.92*(double)free_b)) {
         const double avail = 0.92*(double)free_b - (double)rest;

@@ -385,6 +385,8 @@ def gpu_arm(args):
     par = make_par(args.workload, n, nx3_global)
     prob = WORKLOADS[args.workload][1]
     t_setup = time.time()
+    if args.chunk_planes is not None:
+        os.environ["AB2_CHUNK_PLANES"] = str(args.chunk_planes)
     R = Run(par, prob, device=local, dist=d, riemann=args.riemann, order=args.order)
     t_setup = time.time() - t_setup
     G = R.G
@@ -675,6 +677,7 @@ def main():
     ap.add_argument("--riemann", type=int, default=0, choices=[0, 1, 2], help="0 Roe + H-correction (shipped), 1 HLLC, 2 Roe without H-correction")
     ap.add_argument("--strong", action="store_true", help="--n is the GLOBAL cube size, cut into --gpus x3 slabs (strong scaling)")
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--chunk-planes", type=int, default=None, help="x3-chunked CTU scratch: active planes per chunk (default: whole Grid if it fits, else automatic)")
     ap.add_argument("--cpu-n", type=int, default=None, help="grid of the bounded CPU sample (default: 128 for --impl reference, 64 for the GPU arm's cpu_baseline)")
     ap.add_argument("--cpu-instances", type=int, default=0, help="--impl reference: concurrent serial instances (default: one per host core)")
     ap.add_argument("--cpu-steps", type=int, default=8)
