@@ -349,6 +349,27 @@ def parity_gate(workload, rank, world, local, dist, riemann=0, order=2):
 # ---------------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa(local):
+    """Run this rank on the CPUs nearest its GPU (NVML's affinity mask), so the pinned host buffers of the e2e leg are first
+    touched on that socket: with 8 ranks each moving 1.8 GB per step through host memory, cross-socket copies are what limits
+    the end-to-end scaling.  Best effort; returns the number of CPUs bound to, or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = ((os.cpu_count() or 64) + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [64 * i + b for i, w in enumerate(mask) for b in range(64) if (int(w) >> b) & 1]
+        allowed = set(os.sched_getaffinity(0))
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def gpu_arm(args):
     import numpy as np
     import torch
@@ -359,6 +380,7 @@ def gpu_arm(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    numa_cpus = bind_to_gpu_numa(local) if world > 1 else None
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- this engine has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
@@ -496,7 +518,8 @@ def gpu_arm(args):
         ms_e2e = float(t.item())
     e2e = {"value": zones_total * e2e_steps / (ms_e2e * 1e-3), "unit": "zone-updates/s",
            "h2d_bytes_per_step": int(host.nbytes), "d2h_bytes_per_step": int(host.nbytes), "steps": e2e_steps,
-           "path": "ab2_upload_cons_aos(pinned host ConsS) -> step -> ab2_download_cons_aos, per step"}
+           "path": "ab2_upload_cons_aos(pinned host ConsS) -> step -> ab2_download_cons_aos, per step",
+           "cpus_bound_near_gpu": numa_cpus}
 
     # ---- CPU baseline beside it (rank 0, N=1): the reference's own binary on a bounded sample ----
     cpu = None
