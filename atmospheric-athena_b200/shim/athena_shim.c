@@ -17,7 +17,7 @@
  *
  * Problem-file boundary functions (bvals_mhd_fun) are turned into device tables the same way when they are constants and
  * signed copies (inflow, reflection, outflow); dump_vtk gets its float32 big-endian fields straight from the device.
- * Both discoveries are re-validated against the real host function on a sparse schedule (steps 1, 2, 3, 4, 8, 16, ...)
+ * Both discoveries are re-validated against the real host function on a sparse schedule (steps 1, 2, 4, 8, 16, ...)
  * and fall back to the host round trip on any mismatch; AB2_USERWORK=host / AB2_USER_BC=host / AB2_HOST_WRITERS=1 force
  * the host paths.
  *
@@ -236,8 +236,8 @@ void new_dt(MeshS *pM)
 }
 
 /* ---- bvals_mhd.c ------------------------------------------------------------------------------------------- */
-/* steps at which a discovered device table is checked against the real host function again: 1, 2, 3, 4, 8, 16, 32, ... */
-static int revalidation_step(int nstep) { return nstep >= 1 && (nstep <= 3 || (nstep & (nstep-1)) == 0); }
+/* steps at which a discovered device table is checked against the real host function again: 1, 2, 4, 8, 16, 32, ... */
+static int revalidation_step(int nstep) { return nstep >= 1 && (nstep & (nstep-1)) == 0; }
 
 /* A problem-file boundary function in table form.  The function is run on two synthetic host states whose every value
  * encodes its own (cell, variable): a ghost value that decodes, in BOTH runs, to +-(another cell of the same variable)
@@ -662,25 +662,29 @@ void __wrap_Userwork_in_loop(MeshS *pM)
      * values; otherwise the replay is abandoned for the host round trip.  (This also lets a hook that only reads the
      * state -- diagnostics -- see fresh data on those steps.) */
     int g = 0, same = 1;
+    double *before[8];
     sync_all_to_host();
     FOR_ALL_GRIDS(pM, pD, pG) {
       const long ncell = (long)(pG->Nx[0]+2*nghost)*(pG->Nx[1]+2*nghost)*(pG->Nx[2]+2*nghost);
+      before[g] = (double*)malloc(sizeof(double)*ncell*nv);
+      if (!before[g]) ath_error("[Userwork_in_loop]: malloc failed\n");
+      memcpy(before[g], (double*)&(pG->U[0][0][0]), sizeof(double)*ncell*nv);
+      g++;
+    }
+    __real_Userwork_in_loop(pM);                              /* one call serves every Grid of the Mesh */
+    g = 0;
+    FOR_ALL_GRIDS(pM, pD, pG) {
+      const long ncell = (long)(pG->Nx[0]+2*nghost)*(pG->Nx[1]+2*nghost)*(pG->Nx[2]+2*nghost);
       double *U = (double*)&(pG->U[0][0][0]);
-      double *before = (double*)malloc(sizeof(double)*ncell*nv);
-      long c, n; int v;
-      if (!before) ath_error("[Userwork_in_loop]: malloc failed\n");
-      memcpy(before, U, sizeof(double)*ncell*nv);
-      if (g == 0) __real_Userwork_in_loop(pM);              /* one call serves every Grid of the Mesh */
-      /* every table cell must now hold the table's values ... */
-      for (n=0; n<uw_n[g] && same; n++) for (v=0; v<nv; v++) if (U[uw_cells[g][n]*nv+v] != uw_vals[g][(long)v*uw_n[g]+n]) { same = 0; break; }
-      /* ... and no other cell may have changed.  (Grids after the first were already modified by the one call: compare
-       * against the table instead of `before` for those -- cells outside the table must equal the device state.) */
-      if (g == 0 && same) {
-        long nchanged = 0;
-        for (c=0; c<ncell; c++) { int w = 0; for (v=0; v<nv; v++) if (U[c*nv+v] != before[c*nv+v]) w = 1; nchanged += w; }
-        if (nchanged > uw_n[g]) same = 0;
+      long n; int v;
+      /* every table cell must now hold the table's values; put those into `before` as well, so that ... */
+      for (n=0; n<uw_n[g] && same; n++) for (v=0; v<nv; v++) {
+        if (U[uw_cells[g][n]*nv+v] != uw_vals[g][(long)v*uw_n[g]+n]) { same = 0; break; }
+        before[g][uw_cells[g][n]*nv+v] = U[uw_cells[g][n]*nv+v];
       }
-      free(before);
+      /* ... one memcmp shows that no cell outside the table changed */
+      if (same && memcmp(U, before[g], sizeof(double)*ncell*nv) != 0) same = 0;
+      free(before[g]);
       g++;
     }
     if (!same) {

@@ -113,7 +113,7 @@ class ClockSampler:
         sm, mx, reasons = [], 0.0, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ts, line in self.lines:
-            if ts < t0 or ts > t1 + 0.3:
+            if ts < t0 - 0.15 or ts > t1 + 0.3:          # 100 ms sampling period: the sample that straddles the start counts
                 continue
             f = [x.strip() for x in line.split(",")]
             try:
@@ -172,7 +172,9 @@ def run_dropin(workload, n, nsteps):
     cmd = [exe, "-i", os.path.join(DECKS, WORKLOADS[workload][0]), "job/maxout=0", "job/num_domains=1",
            f"domain1/Nx1={n}", f"domain1/Nx2={n}", f"domain1/Nx3={n}", f"time/nlim={nsteps}"]
     t0 = time.time()
-    r = subprocess.run(cmd, cwd=tmp, capture_output=True, text=True)
+    env = dict(os.environ)
+    env.setdefault("AB2_GRAV_THREADS", str(max(1, min(32, os.cpu_count() or 1))))    # prob/ioniz_sphere.c PlanetPot only reads file statics: re-entrant
+    r = subprocess.run(cmd, cwd=tmp, capture_output=True, text=True, env=env)
     wall = time.time() - t0
     subprocess.run(["rm", "-rf", tmp])
     m = re.search(r"zone-cycles/wall-second = (\S+)", r.stdout)
@@ -381,6 +383,7 @@ def gpu_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     numa_cpus = bind_to_gpu_numa(local) if world > 1 else None
+    sampler = ClockSampler(local) if rank == 0 else None     # started first thing: nvidia-smi takes ~1 s to emit its first sample
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- this engine has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
@@ -421,10 +424,13 @@ def gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local) if rank == 0 else None     # started early: nvidia-smi takes ~1 s to emit its first sample
     for _ in range(args.warmup):
         R.step()
     barrier()
+    if sampler is not None:      # nvidia-smi needs ~1 s for its first sample: make sure it is emitting before the timed region
+        t_wait = time.time()
+        while not sampler.lines and time.time() - t_wait < 3.0:
+            time.sleep(0.05)
 
     # ---- timed region: K steps, state resident in HBM ----
     G.profile_enable(True)
@@ -533,7 +539,8 @@ def gpu_arm(args):
         torch.cuda.synchronize()
         dropin = run_dropin(args.workload, n, max(200, args.warmup + args.steps))     # long enough to amortise its one-time set-up
         if dropin and "value" in dropin:
-            dropin["what"] += "; includes the first step's one-time work (potential tables from the host callback, Userwork discovery, first upload)"
+            dropin["what"] += ("; includes the first step's one-time work (potential tables from the host callback, Userwork discovery, first upload) "
+                               "and the re-validations of the Userwork replay against the real host function at steps 1, 2, 4, 8, ... (each a full download)")
 
     if rank == 0:
         line = {
@@ -641,6 +648,10 @@ def smr_arm(args):
     for _ in range(args.warmup):
         R.step()
     barrier()
+    if sampler is not None:
+        t_wait = time.time()
+        while not sampler.lines and time.time() - t_wait < 3.0:
+            time.sleep(0.05)
     l0 = sum(G.kernel_launches for G in grids)
     it0 = len(R.rad_log)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -308,14 +308,9 @@ def test_device_side_writer_fields_and_bc_table():
     assert np.array_equal(G.output_vtk_field(3), be(act["s"]))
     di = 1.0 / act["d"]
     assert np.array_equal(G.output_vtk_field(1, prim=True), be(np.stack([act["M1"] * di, act["M2"] * di, act["M3"] * di], axis=-1)))
-    # x*x, not x**2: numpy's power loop may go through a vector libm that is not correctly rounded on every host
     P = (act["E"] - 0.5 * (act["M1"] * act["M1"] + act["M2"] * act["M2"] + act["M3"] * act["M3"]) * di) * (5 / 3 - 1.0)
-    # pressure: byte-exactness of the primitive dump is pinned on the reference's own files (test_dropin_vtk_dumps_are_the_
-    # reference_bytes); against this numpy restatement (whose elementwise loops are not the C expression's on every host)
-    # the float32 values must agree to the last place
-    got = G.output_vtk_field(2, prim=True).view(">f4").astype(np.float64)
-    want = be(P).view(">f4").astype(np.float64)
-    assert np.abs(got - want).max() <= 2.4e-7 * np.abs(want).max(), f"max rel diff {np.abs(got / want - 1).max():.3e}"
+    P = np.maximum(P, 1.0e-20)            # convert_var.c:409 MAX(P, TINY_NUMBER): some of the random cells have KE > E
+    assert np.array_equal(G.output_vtk_field(2, prim=True), be(P))
     for n, v in enumerate(VARS):
         assert np.array_equal(G.output_active_var(n), act[v])
     # reflecting ix1 as a table: ghost (k,j,4-l) <- active (k,j,4+l-1), M1 negated, j,k active (bvals_mhd.c:959-977)
