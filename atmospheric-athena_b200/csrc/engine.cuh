@@ -84,7 +84,7 @@ enum {
   KID_BVALS = 0, KID_MAX_SPEEDS, KID_FIRST_X1, KID_FIRST_X2, KID_FIRST_X3, KID_DHALF,
   KID_CORRECT_X1, KID_CORRECT_X2, KID_CORRECT_X3, KID_FINAL_X1, KID_FINAL_X2, KID_FINAL_X3, KID_UPDATE,
   KID_APPLY_FIXED, KID_ION_PREP, KID_ION_RATES, KID_ION_UPDATE, KID_BVALS_IONRAD, KID_TRANSPOSE,
-  KID_SMR_RESTRICT, KID_SMR_FLUXCORR, KID_SMR_PROLONG, KID_ION_FUSED, KID_CFINAL, KID_N
+  KID_SMR_RESTRICT, KID_SMR_FLUXCORR, KID_SMR_PROLONG, KID_ION_FUSED, KID_CFINAL, KID_CORRECT3, KID_N
 };
 struct ProfPending { int id; cudaEvent_t a, b; };
 

@@ -813,7 +813,7 @@ static int integrate_range(ab2_grid* h, const GridDev& g, double dt, int ka, int
     // Pass C: faces of direction d over [l+1, u-1] transversally and [l+1, u] along d
     if (h->correct3) {
       Box b; for (int a=0; a<3; a++) { b.lo[a] = l[a]+1; b.hi[a] = u[a]; }
-      AB2_LAUNCH(h, KID_CORRECT_X1, (k_correct3<NS,GRAV><<<box_grid(b,128), 128, 0, st>>>(g, b, dt)));
+      AB2_LAUNCH(h, KID_CORRECT3, (k_correct3<NS,GRAV><<<box_grid(b,128), 128, 0, st>>>(g, b, dt)));
     } else
     for (int d=0; d<3; d++) {
       Box b; for (int a=0; a<3; a++) { b.lo[a] = l[a]+1; b.hi[a] = (a == d) ? u[a] : u[a]-1; }

@@ -49,7 +49,8 @@ KERNEL_BYTES = {
     "k_dhalf": (0, 5, 0),
     "k_correct<0>": (6, 1, 4), "k_correct<1>": (6, 1, 4), "k_correct<2>": (6, 1, 4),
     "k_final<0>": (3, 3, 0), "k_final<1>": (3, 3, 0), "k_final<2>": (3, 3, 0),
-    "k_update": (5, 0, 5),
+    "k_correct3": (15, 3, 5),    # Ul,Ur of three directions read and written, F of three directions read once, 3 eta written; U0 + 4 potential tables
+    "k_update": (5, 0, 7),       # U read and written, final fluxes of three directions; 4 potential tables + 3 first-pass mass fluxes (d^{n+1/2})
     "k_ion_prep": (0, 11.5, 0), "k_ion_rates": (0, 11, 0), "k_ion_update": (0, 14, 0), "k_ion_rates<fused update>": (0, 19, 0),
     "k_max_speeds": (0, 5, 0),
     "k_cfinal": (12, 0, 6),      # first-pass Ul,Ur,F of three directions read once, final fluxes written once

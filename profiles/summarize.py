@@ -116,7 +116,9 @@ def full_multi(tag, names):
     profiles/<tag>_ncu_full_table.md (a section per workload) + profiles/<tag>_<name>_ncu_full_raw.csv.gz + ncu_traffic.json
     (first capture that has a kernel wins: `default` is the bench workload)."""
     import gzip
-    titles = {"default": "bench.py default workload (256^3 ioniz_sphere), unfused correct/final pair, separate ion kernels",
+    titles = {"smr_ops": "--workload ioniz_smr: the SMR operators, k_correct3 and k_update on the five levels of the shipped deck",
+              "pair": "bench.py default workload: k_correct3 / k_final / k_update (the default passes C, D, E since r2)",
+              "default": "bench.py default workload (256^3 ioniz_sphere), unfused correct/final pair, separate ion kernels",
               "fused": "the same with AB2_HYDRO_FUSE=1 (k_cfinal) and AB2_ION_FUSE=1 (k_ion_rates<fused update>)",
               "ppm": "--workload blast --order 3 (PPM pass A)", "smr": "--workload ioniz_smr (shipped 5-level deck)"}
     traffic = {}
@@ -176,7 +178,12 @@ def full_multi(tag, names):
                 if k not in traffic and t > 0.02:
                     traffic[k] = {"dram_bytes_per_launch": rd + wr, "time_ms": t, "dram_pct": dpct, "fp64_pipe_pct": fp64, "issue_pct": issue,
                                   "warps_active_pct": wa, "regs": regs, "capture": f"{tag}_{name}"}
-    json.dump(traffic, open(os.path.join(HERE, "ncu_traffic.json"), "w"), indent=1)
+    path = os.path.join(HERE, "ncu_traffic.json")
+    if os.environ.get("NCU_TRAFFIC_MERGE") and os.path.exists(path):      # a supplementary capture adds kernels, keeps the rest
+        old = json.load(open(path))
+        old.update({k: v for k, v in traffic.items() if k not in old or os.environ["NCU_TRAFFIC_MERGE"] == "override"})
+        traffic = old
+    json.dump(traffic, open(path, "w"), indent=1)
 
 
 if __name__ == "__main__":
