@@ -195,6 +195,8 @@ ab2_grid* ab2_grid_create(const ab2_grid_desc* d)
   // SLOWER on B200 (6.3 vs 5.0 ms; profiles/r2a_ncu_full_table.md): opt-in with AB2_HYDRO_FUSE=1.
   h->fuse = 0;
   if (const char* env = getenv("AB2_HYDRO_FUSE")) h->fuse = (atoi(env) != 0);
+  h->first_split = 0;
+  if (const char* env = getenv("AB2_FIRST_SPLIT")) h->first_split = atoi(env) & 7;
   h->correct3 = 1;
   if (const char* env = getenv("AB2_CORRECT3")) h->correct3 = (atoi(env) != 0);
   {

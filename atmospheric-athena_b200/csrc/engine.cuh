@@ -109,6 +109,7 @@ struct ab2_grid {
   size_t scratch_doubles;
   int chunk_planes;                // 0: scratch spans the whole Grid; else active x3 planes per chunk (scratch depth = that + 8)
   int fuse;                        // 1: k_cfinal (correct + eta + final fused), 0: k_correct / k_final pair
+  int first_split;                 // pass A, PLM: bit d set = direction d as two kernels (k_plm_states + k_ppm_flux) instead of the fused one
   int correct3;                    // unfused pair: 1 = the three directions of pass C in one launch (k_correct3)
   // problem-file boundary functions (bvals_mhd_fun) in table form, one slot per face (ix1, ox1, ix2, ox2, ix3, ox3):
   // entry t sets U[v][dst[t]] = (src[v][t] >= 0) ? coef[v][t]*U[v][src[v][t]] : coef[v][t]

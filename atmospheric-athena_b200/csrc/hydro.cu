@@ -265,6 +265,34 @@ __global__ void __launch_bounds__(128) k_ppm_states(GridDev g, Box b, double dt)
   store_sweep<DIR,NS>(g.Ur[DIR], c, Wr_this);
 }
 
+// Pass A with PLM as TWO kernels per direction (AB2_FIRST_SPLIT, bit d = direction d): the same per-cell PLM and per-face
+// Riemann evaluations as k_first_x1 / k_first_march, but the L/R primitive states take a round trip through HBM (the Ul/Ur
+// arrays, converted in place by k_ppm_flux) so that neither kernel carries the other's live registers: more resident
+// warps for +192 B per zone and direction.
+#ifndef AB2_LB_PLM
+#define AB2_LB_PLM 4
+#endif
+template <int DIR, int NS, bool GRAV>
+__global__ void __launch_bounds__(128, AB2_LB_PLM) k_plm_states(GridDev g, Box b, double dt)
+{
+  int i,j,k; if (!box_cell(b,i,j,k)) return;
+  const long c = (long)k*g.st[2] + (long)j*g.st[1] + i;
+  const long sd = g.st[DIR];
+  const double dtodx = dt/g.dx[DIR];
+  const S6 Um = load_sweep<DIR,NS>(g.Uin, c-sd), U0 = load_sweep<DIR,NS>(g.Uin, c), Up = load_sweep<DIR,NS>(g.Uin, c+sd);
+  S6 Wl_next, Wr_this;
+  AB2_GUARDED(
+    const S6 Wm = cons_to_prim<NS>(Um, g.Gamma_1, ar); const S6 W0 = cons_to_prim<NS>(U0, g.Gamma_1, ar);
+    const S6 Wp = cons_to_prim<NS>(Up, g.Gamma_1, ar);
+    plm_cell<NS>(Wm, W0, Wp, dtodx, g.Gamma, Wl_next, Wr_this, ar, RIEMANN_OF(g) == AB2_RIEMANN_HLLC));
+  if (GRAV) {   // integrate_3d_ctu.c:318-342, 635-645, 819-829
+    Wl_next.x -= dtodx*(g.phi[PHI_MH0+DIR][c+sd] - g.phi[PHI_M0+DIR][c+sd]);
+    Wr_this.x -= dtodx*(g.phi[PHI_C][c] - g.phi[PHI_MH0+DIR][c]);
+  }
+  store_sweep<DIR,NS>(g.Ul[DIR], c+sd, Wl_next);      // primitive for now; k_ppm_flux converts in place
+  store_sweep<DIR,NS>(g.Ur[DIR], c, Wr_this);
+}
+
 template <int DIR, int NS>
 __global__ void __launch_bounds__(128, AB2_LB_FINAL) k_ppm_flux(GridDev g, Box b)
 {
@@ -783,7 +811,20 @@ static int integrate_range(ab2_grid* h, const GridDev& g, double dt, int ka, int
       if (w < bestw) { bestw = w; bestT = T; }
     }
     if (const char* env = getenv("AB2_X1_TILE")) { const int T = atoi(env); if (T == 64 || T == 96 || T == 128 || T == 136 || T == 160 || T == 192 || T == 256) bestT = T; }
+    // per direction: fused PLM+Riemann kernel (default) or the two-kernel split (h->first_split bit d)
+    auto split_dir = [&](int d) {
+      Box bc, bf;      // states from cells [l,u] (all directions), faces [l+1,u] along d
+      for (int a=0; a<3; a++) { bc.lo[a] = l[a]; bc.hi[a] = u[a]; bf.lo[a] = (a == d) ? l[a]+1 : l[a]; bf.hi[a] = u[a]; }
+      if (d == 0) { AB2_LAUNCH(h, KID_FIRST_X1, (k_plm_states<0,NS,GRAV><<<box_grid(bc,128), 128, 0, st>>>(g, bc, dt)));
+                    AB2_LAUNCH(h, KID_FIRST_X1, (k_ppm_flux<0,NS><<<box_grid(bf,128), 128, 0, st>>>(g, bf))); }
+      if (d == 1) { AB2_LAUNCH(h, KID_FIRST_X2, (k_plm_states<1,NS,GRAV><<<box_grid(bc,128), 128, 0, st>>>(g, bc, dt)));
+                    AB2_LAUNCH(h, KID_FIRST_X2, (k_ppm_flux<1,NS><<<box_grid(bf,128), 128, 0, st>>>(g, bf))); }
+      if (d == 2) { AB2_LAUNCH(h, KID_FIRST_X3, (k_plm_states<2,NS,GRAV><<<box_grid(bc,128), 128, 0, st>>>(g, bc, dt)));
+                    AB2_LAUNCH(h, KID_FIRST_X3, (k_ppm_flux<2,NS><<<box_grid(bf,128), 128, 0, st>>>(g, bf))); }
+    };
     const dim3 grid((nf + bestT-4)/(bestT-3), u[1]-l[1]+1, u[2]-l[2]+1);
+    if (h->first_split & 1) split_dir(0);
+    else
     switch (bestT) {
       case 64:  AB2_LAUNCH(h, KID_FIRST_X1, (k_first_x1<NS,GRAV,64><<<grid, 64, 0, st>>>(g, dt, l[2]))); break;
       case 96:  AB2_LAUNCH(h, KID_FIRST_X1, (k_first_x1<NS,GRAV,96><<<grid, 96, 0, st>>>(g, dt, l[2]))); break;
@@ -797,9 +838,11 @@ static int integrate_range(ab2_grid* h, const GridDev& g, double dt, int ka, int
     const int nf2 = u[1]-l[1], nf3 = u[2]-l[2];             // faces [l+1, u] along the sweep
     const int seg2 = seg_for(nf2), seg3 = seg_for(nf3);
     dim3 g2((unsigned)((ni*(u[2]-l[2]+1)+127)/128), (nf2 + seg2-1)/seg2, 1);
-    AB2_LAUNCH(h, KID_FIRST_X2, (k_first_march<1,NS,GRAV><<<g2, 128, 0, st>>>(g, dt, seg2, l[2], u[2]-l[2]+1, l[1]+1, u[1])));
+    if (h->first_split & 2) split_dir(1);
+    else AB2_LAUNCH(h, KID_FIRST_X2, (k_first_march<1,NS,GRAV><<<g2, 128, 0, st>>>(g, dt, seg2, l[2], u[2]-l[2]+1, l[1]+1, u[1])));
     dim3 g3((unsigned)((ni*(u[1]-l[1]+1)+127)/128), (nf3 + seg3-1)/seg3, 1);
-    AB2_LAUNCH(h, KID_FIRST_X3, (k_first_march<2,NS,GRAV><<<g3, 128, 0, st>>>(g, dt, seg3, l[1], u[1]-l[1]+1, l[2]+1, u[2])));
+    if (h->first_split & 4) split_dir(2);
+    else AB2_LAUNCH(h, KID_FIRST_X3, (k_first_march<2,NS,GRAV><<<g3, 128, 0, st>>>(g, dt, seg3, l[1], u[1]-l[1]+1, l[2]+1, u[2])));
   }
   Box act; for (int a=0; a<3; a++) { act.lo[a] = s[a]; act.hi[a] = e[a]; }
   // Pass B (d^{n+1/2}) is folded into pass E: the first-pass fluxes outlive pass D now that the final ones have their own arrays

@@ -541,7 +541,7 @@ def gpu_arm(args):
         dropin = run_dropin(args.workload, n, max(200, args.warmup + args.steps))     # long enough to amortise its one-time set-up
         if dropin and "value" in dropin:
             dropin["what"] += ("; includes the first step's one-time work (potential tables from the host callback, Userwork discovery, first upload) "
-                               "and the re-validations of the Userwork replay against the real host function at steps 1, 2, 4, 8, ... (each a full download)")
+                               "and the re-validations of the Userwork replay against the real host function at steps 1, 4, 16, 64, ... (each a full download)")
 
     if rank == 0:
         line = {
