@@ -217,8 +217,14 @@ __device__ __forceinline__ bool box_cell(const Box& b, int& i, int& j, int& k)
 // overwrites them; the face-state arrays carry PRIMITIVE states between the second and third kernel because the
 // reference hands the primitive L/R states themselves to fluxes() in this pass (integrate_3d_ctu.c:248-300).
 // ---------------------------------------------------------------------------------------------------
+#ifndef AB2_LB_PPM_SLOPE
+#define AB2_LB_PPM_SLOPE 1
+#endif
+#ifndef AB2_LB_PPM_STATES
+#define AB2_LB_PPM_STATES 1
+#endif
 template <int DIR, int NS>
-__global__ void __launch_bounds__(128) k_ppm_slope(GridDev g, Box b)
+__global__ void __launch_bounds__(128, AB2_LB_PPM_SLOPE) k_ppm_slope(GridDev g, Box b)
 {
   int i,j,k; if (!box_cell(b,i,j,k)) return;
   const long c = (long)k*g.st[2] + (long)j*g.st[1] + i;
@@ -234,7 +240,7 @@ __global__ void __launch_bounds__(128) k_ppm_slope(GridDev g, Box b)
 }
 
 template <int DIR, int NS, bool GRAV>
-__global__ void __launch_bounds__(128) k_ppm_states(GridDev g, Box b, double dt)
+__global__ void __launch_bounds__(128, AB2_LB_PPM_STATES) k_ppm_states(GridDev g, Box b, double dt)
 {
   int i,j,k; if (!box_cell(b,i,j,k)) return;
   const long c = (long)k*g.st[2] + (long)j*g.st[1] + i;

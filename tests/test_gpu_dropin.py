@@ -247,3 +247,43 @@ def test_dropin_vtk_dumps_are_the_reference_bytes(cfg, deck, nlim, out):
     assert len(files["ref"]) == 2 and sorted(files["ref"]) == sorted(files["b200"]), (sorted(files["ref"]), sorted(files["b200"]))
     for f in files["ref"]:
         assert files["b200"][f] == files["ref"][f], f"{f}: {len(files['b200'][f])} vs {len(files['ref'][f])} bytes"
+
+
+def test_dropin_forced_host_paths_give_the_same_bits():
+    """The opt-outs of INTEGRATION.md ("Problem-file hooks that touch the state"): AB2_USERWORK=host runs the problem file's
+    Userwork_in_loop on the host every step (download, hook, upload) instead of the device replay; the dump must not change."""
+    case = Case("ioniz24_k3")
+    os.environ["AB2_USERWORK"] = "host"
+    try:
+        d1, rad, r = run_dropin(case)
+    finally:
+        os.environ.pop("AB2_USERWORK", None)
+    assert "Userwork_in_loop replayed on the device" not in r.stdout
+    assert rad == [int(x) for x in case.gold["rad"][:, 0]]
+    assert d1["time"] == float(case.gold["time1"]) and d1["dt"] == float(case.gold["dt1"])
+    for v in case.U1:
+        assert np.array_equal(d1["grids"][0][v], case.U1[v], equal_nan=True), v
+    assert np.array_equal(d1["grids"][0]["edgeflux"], case.gold["U1_edgeflux"])
+
+
+def test_dropin_replay_survives_its_revalidation_steps():
+    """20 steps of ioniz_sphere 24^3 through the drop-in cross the re-validation steps 1, 4 and 16 of the Userwork replay; the
+    replay must stay enabled (no fall-back message) and the run must equal the engine's own 20-step run bit for bit."""
+    from athena_b200.driver import Run
+    case = Case("ioniz24_k3")
+    exe = os.path.join(ROOT, "build", "dropin", case.build, "athena")
+    if not os.path.exists(exe):
+        pytest.skip("build/dropin not built")
+    with tempfile.TemporaryDirectory() as tmp:
+        cmd = [exe, "-i", os.path.join(DECKS, str(case.gold["deck"])), "time/nlim=20"] + [str(x) for x in case.gold["overrides"]]
+        r = subprocess.run(cmd, cwd=tmp, capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        rst = sorted(f for f in os.listdir(tmp) if f.endswith(".rst"))
+        d1 = read_restart(os.path.join(tmp, rst[-1]))
+    assert "Userwork_in_loop replayed on the device" in r.stdout and "no longer matches" not in r.stdout
+    R = Run(case.par, case.problem, device=0, U0=case.U0)
+    R.run(20)
+    out = R.G.download_active()
+    assert d1["nstep"] == 20 and d1["time"] == R.time
+    for v in out:
+        assert np.array_equal(d1["grids"][0][v], out[v], equal_nan=True), v
