@@ -218,10 +218,10 @@ __device__ __forceinline__ bool box_cell(const Box& b, int& i, int& j, int& k)
 // reference hands the primitive L/R states themselves to fluxes() in this pass (integrate_3d_ctu.c:248-300).
 // ---------------------------------------------------------------------------------------------------
 #ifndef AB2_LB_PPM_SLOPE
-#define AB2_LB_PPM_SLOPE 1
+#define AB2_LB_PPM_SLOPE 6
 #endif
 #ifndef AB2_LB_PPM_STATES
-#define AB2_LB_PPM_STATES 1
+#define AB2_LB_PPM_STATES 6
 #endif
 template <int DIR, int NS>
 __global__ void __launch_bounds__(128, AB2_LB_PPM_SLOPE) k_ppm_slope(GridDev g, Box b)
