@@ -59,7 +59,8 @@ static const char* KERNEL_NAMES[KID_N] = {
   "k_bvals", "k_max_speeds", "k_first_x1", "k_first_march<1>", "k_first_march<2>", "k_dhalf",
   "k_correct<0>", "k_correct<1>", "k_correct<2>", "k_final<0>", "k_final<1>", "k_final<2>", "k_update",
   "k_apply_fixed", "k_ion_prep", "k_ion_rates", "k_ion_update", "k_bvals_ionrad", "k_transpose",
-  "k_smr_restrict", "k_smr_flux_correct", "k_smr_prolongate", "k_ion_rates<fused update>", "k_cfinal", "k_correct3" };
+  "k_smr_restrict", "k_smr_flux_correct", "k_smr_prolongate", "k_ion_rates<fused update>", "k_cfinal", "k_correct3",
+  "k_ion_rates[memo]", "k_ion_update[memo]", "k_ion_rates<fused update>[memo]" };
 
 cudaEvent_t ab2_prof_event(ab2_grid* h)
 {
@@ -530,6 +531,17 @@ int ab2_ion_init(ab2_grid* h, const ab2_ion_par* par)
     double* s = dev_alloc(h, (ncell+1)/2);
     if (!s) return -1;
     I.sign_state = (int*)s;
+    // sub-cycle memo (engine.cuh IonChunks): one record per ray and 32-cell chunk
+    IonChunks& C = I.ch;
+    C.nch = (h->g.nx[0] + 31)/32;
+    const size_t nchunks = (size_t)h->g.nx[1]*h->g.nx[2]*C.nch;
+    double* fl = dev_alloc(h, (nchunks+1)/2), *cn = dev_alloc(h, (nchunks+1)/2);
+    if (!fl || !cn || !(C.carry_in = dev_alloc(h, nchunks)) || !(C.carry_out = dev_alloc(h, nchunks)) || !(C.dtc = dev_alloc(h, nchunks)) ||
+        !(C.dtt = dev_alloc(h, nchunks)) || !(C.m1 = dev_alloc(h, nchunks)) || !(C.m2 = dev_alloc(h, nchunks)) || !(C.m3 = dev_alloc(h, nchunks))) return -1;
+    C.cnt = (unsigned*)cn;
+    h->ion_ch_flags = (unsigned*)fl; h->ion_nchunks = nchunks;
+    const char* env = getenv("AB2_ION_SKIP");
+    C.flags = (env && atoi(env) == 0) ? nullptr : h->ion_ch_flags;
     CK(cudaStreamSynchronize(h->stream), "ion init sync");
     h->has_ion = true;
   }
@@ -557,5 +569,18 @@ int ab2_ion_radtransfer_3d_fine(ab2_grid* h, double tcoarse, double* dt, int* ni
 }
 
 double ab2_ion_coarse_time(const ab2_grid* h) { return h->tcoarse; }
+
+int ab2_set_ion_memo(ab2_grid* h, int on)
+{
+  if (!h->has_ion) { ab2_set_error("[ab2_set_ion_memo]: ab2_ion_init not called"); return -1; }
+  h->ion.ch.flags = on ? h->ion_ch_flags : nullptr;
+  return 0;
+}
+
+int ab2_ion_memo_stats(ab2_grid* h, long long out[3])
+{
+  if (!h->has_ion) { ab2_set_error("[ab2_ion_memo_stats]: ab2_ion_init not called"); return -1; }
+  return ion_memo_count(h, out);
+}
 
 } // extern "C"

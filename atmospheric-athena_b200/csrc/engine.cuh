@@ -57,6 +57,7 @@ enum {
   SC_MAX_DTI,                         // ion: compute_dt_hydro max (atomicMax)
   SC_COUNT,                           // ion: check_range cell count (u64)
   SC_ERR,                             // sticky error flags
+  SC_MEMO_RATES, SC_MEMO_UPDATE,      // ion: chunks whose rates / update were whose records say re-used (scratch of ab2_ion_memo_stats, not exchanged)
   SC_N = 16
 };
 #define SC_NRED 8                     // SC_MAXV1 .. SC_ERR: the scalars one cross-rank exchange combines (comm.cu)
@@ -69,11 +70,29 @@ struct IonParDev {
   double min_area, d_nlo;
 };
 
+// Sub-cycle memo, one record per (ray, 32-cell chunk along x1) -- ion.cu "sparse sub-cycle".  Within one call of
+// ion_radtransfer_3d a chunk whose cells no update touches (fully ionised ambient gas at the neutral floor, the bulk
+// of an irradiated-planet box) sees the same inputs in every iteration, so its rates, its reductions and its
+// outgoing flux are those of the previous iteration bit for bit: the kernels re-use them instead of re-evaluating.
+#define CH_RFIX      1u      // rates in memory were computed with every cell's sign state at its fixed point
+#define CH_SAME      2u      // the latest rates pass left this chunk's outputs as they were
+#define CH_UINERT    4u      // the latest update left E and s of every cell of the chunk untouched (no cell met the update condition, no floor fired)
+#define CH_UCACHED   8u      // cnt / m1..m3 hold the update's check_range count and wave-speed maxima of the chunk
+#define CH_ALIVE_IN  16u     // the ray was still uncut where it entered the chunk
+#define CH_ALIVE_OUT 32u     // ... where it left it
+struct IonChunks {
+  unsigned* flags;            // NULL: memo off (AB2_ION_SKIP=0), every chunk is evaluated in every iteration
+  unsigned* cnt;
+  double *carry_in, *carry_out, *dtc, *dtt, *m1, *m2, *m3;
+  int nch;                    // chunks per ray = ceil(nx1 / 32)
+};
+
 struct IonDev {
   double *ph_rate, *edot, *nHdot, *e_init, *e_th_init, *x_init;
   int* sign_state;            // (sign_count << 2) | (last_sign + 1)
   double* edgeflux;           // [nx3+1][nx2+1][nx1+1], current
   double* edgeflux_alt;       // written by a fused update+rates launch; becomes current when the sub-cycle continues
+  IonChunks ch;
 };
 
 typedef void (*ab2_reduce_fn_t)(double* vals, int n, int op, void* ctx);
@@ -84,7 +103,8 @@ enum {
   KID_BVALS = 0, KID_MAX_SPEEDS, KID_FIRST_X1, KID_FIRST_X2, KID_FIRST_X3, KID_DHALF,
   KID_CORRECT_X1, KID_CORRECT_X2, KID_CORRECT_X3, KID_FINAL_X1, KID_FINAL_X2, KID_FINAL_X3, KID_UPDATE,
   KID_APPLY_FIXED, KID_ION_PREP, KID_ION_RATES, KID_ION_UPDATE, KID_BVALS_IONRAD, KID_TRANSPOSE,
-  KID_SMR_RESTRICT, KID_SMR_FLUXCORR, KID_SMR_PROLONG, KID_ION_FUSED, KID_CFINAL, KID_CORRECT3, KID_N
+  KID_SMR_RESTRICT, KID_SMR_FLUXCORR, KID_SMR_PROLONG, KID_ION_FUSED, KID_CFINAL, KID_CORRECT3,
+  KID_ION_RATES_MEMO, KID_ION_UPDATE_MEMO, KID_ION_FUSED_MEMO, KID_N
 };
 struct ProfPending { int id; cudaEvent_t a, b; };
 
@@ -104,6 +124,8 @@ struct ab2_grid {
   IonParDev ionpar;
   IonDev ion;
   int maxiter;
+  unsigned* ion_ch_flags;          // the memo's flag array (ion.ch.flags is NULL while AB2_ION_SKIP=0 turns the memo off)
+  size_t ion_nchunks;
   double tcoarse;                  // ionrad_3d.c:1028: dt_done of the last root-level radiation call
   double* scratch;                 // one allocation behind Ul/Ur/F/Ff/eta (and Uin, carry when chunked)
   size_t scratch_doubles;
@@ -161,5 +183,6 @@ int hydro_apply_fixed(ab2_grid* h);
 int ion_bvals_ionrad(ab2_grid* h, double flux_i);
 int ion_radtransfer(ab2_grid* h, double flux_in, double cour_no, double* dt_io, int* niter, int* nchem, int* ntherm,
                     ab2_reduce_fn_t reduce, void* ctx);
+int ion_memo_count(ab2_grid* h, long long out[3]);
 int ion_radtransfer_fine(ab2_grid* h, double tcoarse, double* dt_io, int* niter, int* nchem, int* ntherm,
                          ab2_reduce_fn_t reduce, void* ctx);

@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(128) k_ion_prep(GridDev g, IonParDev p, IonDev
 // ionization_update (:565-590) + floors (:970-971) + check_range (:206-283) + compute_dt_hydro (:593-678) for ONE cell:
 // (E,s) -> (Eo,so), whether the cell counts for check_range, and |v_d| + a per direction.  Pure in its inputs.
 // ---------------------------------------------------------------------------------------------------
-struct CellUpd { double E, s, x1, x2, x3; unsigned count; };
+struct CellUpd { double E, s, x1, x2, x3; unsigned count; bool applied; };
 
 template <bool FAST>
 __device__ __forceinline__ CellUpd cell_update(const GridDev& g, const IonParDev& p, const IonDev& ion, long c, double dt,
@@ -166,7 +166,8 @@ __device__ __forceinline__ CellUpd cell_update(const GridDev& g, const IonParDev
     const double nHdot = ion.nHdot[c];
     double d_nlim = d*IONFRACFLOOR;
     d_nlim = d_nlim < p.d_nlo ? d_nlim : p.d_nlo;
-    if ((nHdot > 0) || (s > 1.0001*d_nlim)) {
+    u.applied = (nHdot > 0) || (s > 1.0001*d_nlim);
+    if (u.applied) {
       E += ion.edot[c] * dt;
       s += nHdot * dt * p.m_H;
     }
@@ -290,6 +291,67 @@ __device__ __forceinline__ CellRates cell_rates(const GridDev& g, const IonParDe
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Sparse sub-cycle (engine.cuh IonChunks).  ion_radtransfer_3d re-evaluates every cell in every iteration; most cells of
+// an irradiated-planet box are ambient gas that is already ionised down to the neutral floor, where ionization_update's
+// own condition (ionrad_3d.c:575 `nHdot > 0 || s > 1.0001 d_nlim`) leaves E and s alone.  A 32-cell chunk of a ray all
+// of whose cells are in that state, whose incoming flux has the bits it had in the previous iteration and whose sign
+// states sit at their fixed point (count 0, last_sign = sign(nHdot)) gets bit-identical rates, dt limits, outgoing flux,
+// check_range count and wave-speed maxima from a re-evaluation -- so both kernels take them from the chunk's record
+// instead.  Nothing is approximated: a chunk is re-used only when every input of the reference's arithmetic is unchanged.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool ordered_bits(double x)
+{ // non-negative and not NaN: the bit pattern orders like the value
+  return (unsigned long long)__double_as_longlong(x) <= 0x7ff0000000000000ull;
+}
+__device__ __forceinline__ double warp_min_ordered(double x)
+{
+  const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+  const unsigned hi = (unsigned)(b >> 32), lo = (unsigned)b;
+  const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+  const unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
+  return __longlong_as_double((long long)(((unsigned long long)mh << 32) | ml));
+}
+__device__ __forceinline__ double warp_max_ordered(double x)
+{
+  const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+  const unsigned hi = (unsigned)(b >> 32), lo = (unsigned)b;
+  const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+  const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+  return __longlong_as_double((long long)(((unsigned long long)mh << 32) | ml));
+}
+__device__ __forceinline__ bool same_bits(double a, double b) { return __double_as_longlong(a) == __double_as_longlong(b); }
+
+// One chunk of k_ion_update for a warp: the cells' update + the chunk's memo.  Returns the (possibly changed) flags.
+// E, s are the lane's values on entry and the updated ones on return.
+__device__ __forceinline__ unsigned update_chunk(const GridDev& g, const IonParDev& p, const IonDev& ion, long c, long q, bool valid, int lane,
+                                                 double dt, double d, double M1, double M2, double M3, double& E, double& s, unsigned fl,
+                                                 unsigned& count, double& m1, double& m2, double& m3)
+{
+  CellUpd u; u.E = E; u.s = s; u.x1 = u.x2 = u.x3 = 0.0; u.count = 0; u.applied = false;
+  if (valid) {
+    ION_GUARDED(u = cell_update(g, p, ion, c, dt, d, M1, M2, M3, E, s, ar));
+    g.U[4][c] = u.E; g.U[5][c] = u.s;
+    count += u.count;
+    m1 = AB2_MAX(m1, u.x1); m2 = AB2_MAX(m2, u.x2); m3 = AB2_MAX(m3, u.x3);
+  }
+  if (ion.ch.flags) {
+    const bool inert = __all_sync(0xffffffffu, !valid || (!u.applied && same_bits(u.E, E) && same_bits(u.s, s)
+                                                          && ordered_bits(u.x1) && ordered_bits(u.x2) && ordered_bits(u.x3)));
+    unsigned nf = fl & ~(CH_UINERT | CH_UCACHED);
+    if (inert) {
+      const double c1 = warp_max_ordered(u.x1), c2 = warp_max_ordered(u.x2), c3 = warp_max_ordered(u.x3);
+      const unsigned cc = __popc(__ballot_sync(0xffffffffu, u.count != 0));
+      if (lane == 0) { ion.ch.m1[q] = c1; ion.ch.m2[q] = c2; ion.ch.m3[q] = c3; ion.ch.cnt[q] = cc; }
+      nf |= CH_UINERT | CH_UCACHED;
+    }
+    if (lane == 0) ion.ch.flags[q] = nf;
+    fl = nf;
+  }
+  E = u.E; s = u.s;
+  return fl;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // k_ion_rates: ray trace (ionradplane_3d.c:254-310) + chem rates (ionrad_3d.c:307-394) + therm rates (:433-550)
 // ---------------------------------------------------------------------------------------------------
 // UPDATE = true fuses the previous iteration's k_ion_update (same arithmetic, same order) in front of the rates of
@@ -312,30 +374,61 @@ __global__ void __launch_bounds__(128, AB2_LB_ION_RATES) k_ion_rates(GridDev g, 
   double* ef = ef_out_base + efo;
   const double dx1 = g.dx[0];
   const int nx1 = g.nx[0];
+  const bool memo = ion.ch.flags != nullptr;
 
   // root level: the time-ramped plane flux; finer levels: the value handed down into EdgeFlux[k][j][0] (ionradplane_3d.c:263-272)
   const double flux_in = finegrid ? ef_in_base[efo] : flux_in_root;
-  unsigned long long count = 0;                       // check_range / compute_dt_hydro of the fused update
+  unsigned count = 0;                                 // check_range / compute_dt_hydro of the fused update
   double m1 = 0.0, m2 = 0.0, m3 = 0.0;
   double carry = flux_in;         // flux entering the current chunk
   bool alive = true;              // false once the ray has been cut
   double dt_chem_min = LARGE, dt_therm_min = LARGE;
   unsigned long long err = 0;
 
-  for (int c0 = 0; c0 < nx1; c0 += 32) {
+  long q = ray*ion.ch.nch;
+  unsigned fl_ray = 0;            // the flags of (up to) 32 chunks of the ray, one per lane
+  for (int c0 = 0, ch = 0; c0 < nx1; c0 += 32, ch++, q++) {
     const int ii = c0 + lane;
     const bool valid = ii < nx1;
     const long c = row + (valid ? ii : nx1-1);
-    const double d = g.U[0][c], M1 = g.U[1][c], M2 = g.U[2][c], M3 = g.U[3][c];
-    double E = g.U[4][c], s = g.U[5][c];
-    if (UPDATE && valid) {
-      CellUpd u;
-      ION_GUARDED(u = cell_update(g, p, ion, c, dt_upd, d, M1, M2, M3, E, s, ar));
-      E = u.E; s = u.s;
-      g.U[4][c] = E; g.U[5][c] = s;
-      count += u.count;
-      m1 = AB2_MAX(m1, u.x1); m2 = AB2_MAX(m2, u.x2); m3 = AB2_MAX(m3, u.x3);
+    if (memo && (ch & 31) == 0) fl_ray = (ch + lane < ion.ch.nch) ? ion.ch.flags[q + lane] : 0u;
+    unsigned fl = __shfl_sync(0xffffffffu, fl_ray, ch & 31);
+    // the chunk's update is re-used when its rates are the previous iteration's and that iteration's update touched nothing;
+    // its rates when, on top, the ray reaches it as it did before (flux bits, or cut in both)
+    const bool uskip = !UPDATE || ((fl & (CH_SAME|CH_UINERT|CH_UCACHED)) == (CH_SAME|CH_UINERT|CH_UCACHED));
+    double rec_in = 0.0, rec_out = 0.0, rec_dtc = LARGE, rec_dtt = LARGE;      // the record, fetched in one go
+    if (fl & CH_RFIX) { rec_in = ion.ch.carry_in[q]; rec_out = ion.ch.carry_out[q]; rec_dtc = ion.ch.dtc[q]; rec_dtt = ion.ch.dtt[q]; }
+    const bool rmatch = (fl & CH_RFIX) && (((fl & CH_ALIVE_IN) != 0) == alive) && (!alive || same_bits(carry, rec_in));
+    bool rskip = uskip && rmatch && (fl & CH_UINERT);
+    double d = 0.0, M1 = 0.0, M2 = 0.0, M3 = 0.0, E = 0.0, s = 0.0;
+    if (!rskip) {
+      d = g.U[0][c]; M1 = g.U[1][c]; M2 = g.U[2][c]; M3 = g.U[3][c];
+      E = g.U[4][c]; s = g.U[5][c];
     }
+    if (UPDATE) {
+      if (uskip) {
+        if (lane == 0) count += ion.ch.cnt[q];
+        const double c1 = ion.ch.m1[q], c2 = ion.ch.m2[q], c3 = ion.ch.m3[q];
+        m1 = AB2_MAX(m1, c1); m2 = AB2_MAX(m2, c2); m3 = AB2_MAX(m3, c3);
+      } else {
+        fl = update_chunk(g, p, ion, c, q, valid, lane, dt_upd, d, M1, M2, M3, E, s, fl, count, m1, m2, m3);
+        rskip = rmatch && (fl & CH_UINERT);
+      }
+    }
+    if (rskip) {
+      // same inputs as in the previous iteration: rates, ph_rate, sign states in memory stand; only the flux the chunk hands on,
+      // its dt limits and (fused launches write the alternate buffer) its EdgeFlux entries are needed
+      if (UPDATE && valid) ef[ii] = (ef_in_base + efo)[ii];
+      if (rec_dtc < dt_chem_min) dt_chem_min = rec_dtc;
+      if (rec_dtt < dt_therm_min) dt_therm_min = rec_dtt;
+      carry = rec_out;
+      alive = (fl & CH_ALIVE_OUT) != 0;
+      if (lane == 0 && !(fl & CH_SAME)) ion.ch.flags[q] = fl | CH_SAME;
+      continue;
+    }
+    // evaluated: the record's flags are rebuilt (CH_SAME off); the incoming flux is noted now, it only counts once CH_RFIX is set
+    fl = (fl & (CH_UINERT | CH_UCACHED)) | (alive ? CH_ALIVE_IN : 0u);
+    if (memo && lane == 0) ion.ch.carry_in[q] = carry;
 
     // --- ray: tau, attenuation, photoionisation rate
     double n_H;
@@ -370,6 +463,8 @@ __global__ void __launch_bounds__(128, AB2_LB_ION_RATES) k_ion_rates(GridDev g, 
     carry = __shfl_sync(0xffffffffu, flux_after, 31);
     if (first < 32) alive = false;
 
+    bool keep = true;                   // this cell allows the chunk's record to stand in for a re-evaluation
+    double cdtc = LARGE, cdtt = LARGE;  // (dead code unless the memo is on)
     if (valid) {
       CellRates r;
       const int st = ion.sign_state[c];
@@ -380,6 +475,23 @@ __global__ void __launch_bounds__(128, AB2_LB_ION_RATES) k_ion_rates(GridDev g, 
       if (r.dt_chem < dt_chem_min) dt_chem_min = r.dt_chem;
       if (r.dt_chem < 0) err |= ERR_DT_CHEM_NEG;
       if (r.dt_therm < dt_therm_min) dt_therm_min = r.dt_therm;
+      if (memo) {
+        double d_nlim = d*IONFRACFLOOR;
+        d_nlim = d_nlim < p.d_nlo ? d_nlim : p.d_nlo;
+        // sign_count 0 after the transition = fixed point (last_sign is always the current sign); the update's condition on
+        // the stored (damped) rate is false; dt limits are plain non-negative numbers
+        keep = ((r.sign_state >> 2) == 0) && !((r.nHdot > 0) || (s > 1.0001*d_nlim)) && ordered_bits(r.dt_chem) && ordered_bits(r.dt_therm);
+        cdtc = r.dt_chem; cdtt = r.dt_therm;
+      }
+    }
+    if (memo) {
+      if (alive) fl |= CH_ALIVE_OUT;
+      if (__all_sync(0xffffffffu, keep)) {
+        cdtc = warp_min_ordered(cdtc); cdtt = warp_min_ordered(cdtt);
+        if (lane == 0) { ion.ch.carry_out[q] = carry; ion.ch.dtc[q] = cdtc; ion.ch.dtt[q] = cdtt; }
+        fl |= CH_RFIX;
+      }
+      if (lane == 0) ion.ch.flags[q] = fl;
     }
   }
   if (lane == 0) ef[nx1] = alive ? carry : 0.0;      // ionradplane_3d.c:308
@@ -403,7 +515,7 @@ __global__ void __launch_bounds__(128, AB2_LB_ION_RATES) k_ion_rates(GridDev g, 
     atomic_min_double(&scal[SC_DT_THERM], dt_therm_min);
     if (err) atomicOr(&scal[SC_ERR], err);
     if (UPDATE) {
-      if (count) atomicAdd(&scal[SC_COUNT], count);
+      if (count) atomicAdd(&scal[SC_COUNT], (unsigned long long)count);
       atomic_max_double(&scal[SC_MAXV1], m1);
       atomic_max_double(&scal[SC_MAXV2], m2);
       atomic_max_double(&scal[SC_MAXV3], m3);
@@ -412,21 +524,38 @@ __global__ void __launch_bounds__(128, AB2_LB_ION_RATES) k_ion_rates(GridDev g, 
 }
 
 // ---------------------------------------------------------------------------------------------------
-// k_ion_update: ionization_update (:565-590) + floors (:970-971) + check_range (:206-283) + compute_dt_hydro (:593-678)
+// k_ion_update: ionization_update (:565-590) + floors (:970-971) + check_range (:206-283) + compute_dt_hydro (:593-678).
+// One warp per ray, 32 cells at a time like k_ion_rates, so that both kernels address the same chunk records.
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128, AB2_LB_ION_UPDATE) k_ion_update(GridDev g, IonParDev p, IonDev ion, double dt, unsigned long long* scal)
 {
-  long c;
-  const bool act = active_cell(g, c);
-  unsigned long long count = 0;
+  const int lane = threadIdx.x & 31;
+  const long ray = (long)blockIdx.x*(blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long nrays = (long)g.nx[1]*g.nx[2];
+  if (ray >= nrays) return;
+  const int jj = (int)(ray % g.nx[1]), kk = (int)(ray / g.nx[1]);
+  const long row = (long)(kk+NG)*g.st[2] + (long)(jj+NG)*g.st[1] + NG;
+  const int nx1 = g.nx[0];
+  const bool memo = ion.ch.flags != nullptr;
+  unsigned count = 0;
   double m1 = 0.0, m2 = 0.0, m3 = 0.0;
-  if (act) {
+  long q = ray*ion.ch.nch;
+  unsigned fl_ray = 0;
+  for (int c0 = 0, ch = 0; c0 < nx1; c0 += 32, ch++, q++) {
+    if (memo && (ch & 31) == 0) fl_ray = (ch + lane < ion.ch.nch) ? ion.ch.flags[q + lane] : 0u;
+    const unsigned fl = __shfl_sync(0xffffffffu, fl_ray, ch & 31);
+    if ((fl & (CH_SAME|CH_UINERT|CH_UCACHED)) == (CH_SAME|CH_UINERT|CH_UCACHED)) {
+      if (lane == 0) count += ion.ch.cnt[q];
+      const double c1 = ion.ch.m1[q], c2 = ion.ch.m2[q], c3 = ion.ch.m3[q];
+      m1 = AB2_MAX(m1, c1); m2 = AB2_MAX(m2, c2); m3 = AB2_MAX(m3, c3);
+      continue;
+    }
+    const int ii = c0 + lane;
+    const bool valid = ii < nx1;
+    const long c = row + (valid ? ii : nx1-1);
     const double d = g.U[0][c], M1 = g.U[1][c], M2 = g.U[2][c], M3 = g.U[3][c];
-    const double E = g.U[4][c], s = g.U[5][c];
-    CellUpd u;
-    ION_GUARDED(u = cell_update(g, p, ion, c, dt, d, M1, M2, M3, E, s, ar));
-    g.U[4][c] = u.E; g.U[5][c] = u.s;
-    count = u.count; m1 = AB2_MAX(m1, u.x1); m2 = AB2_MAX(m2, u.x2); m3 = AB2_MAX(m3, u.x3);
+    double E = g.U[4][c], s = g.U[5][c];
+    update_chunk(g, p, ion, c, q, valid, lane, dt, d, M1, M2, M3, E, s, fl, count, m1, m2, m3);
   }
   for (int o=16; o>0; o>>=1) {
     count += __shfl_xor_sync(0xffffffffu, count, o);
@@ -435,12 +564,38 @@ __global__ void __launch_bounds__(128, AB2_LB_ION_UPDATE) k_ion_update(GridDev g
     y = __shfl_xor_sync(0xffffffffu, m2, o); m2 = AB2_MAX(m2, y);
     y = __shfl_xor_sync(0xffffffffu, m3, o); m3 = AB2_MAX(m3, y);
   }
-  if ((threadIdx.x & 31) == 0) {
-    if (count) atomicAdd(&scal[SC_COUNT], count);
+  if (lane == 0) {
+    if (count) atomicAdd(&scal[SC_COUNT], (unsigned long long)count);
     atomic_max_double(&scal[SC_MAXV1], m1);
     atomic_max_double(&scal[SC_MAXV2], m2);
     atomic_max_double(&scal[SC_MAXV3], m3);
   }
+}
+
+// how many chunk records say "re-used by the latest rates pass" / "the next update would be re-used" (ab2_ion_memo_stats)
+__global__ void k_ion_memo_count(const unsigned* flags, long n, unsigned long long* scal)
+{
+  const long t = (long)blockIdx.x*blockDim.x + threadIdx.x;
+  const unsigned fl = t < n ? flags[t] : 0u;
+  const unsigned a = __popc(__ballot_sync(0xffffffffu, (fl & CH_SAME) != 0));
+  const unsigned b = __popc(__ballot_sync(0xffffffffu, (fl & (CH_SAME|CH_UINERT|CH_UCACHED)) == (CH_SAME|CH_UINERT|CH_UCACHED)));
+  if ((threadIdx.x & 31) == 0) {
+    if (a) atomicAdd(&scal[SC_MEMO_RATES], (unsigned long long)a);
+    if (b) atomicAdd(&scal[SC_MEMO_UPDATE], (unsigned long long)b);
+  }
+}
+
+int ion_memo_count(ab2_grid* h, long long out[3])
+{
+  out[0] = out[1] = 0; out[2] = (long long)h->ion_nchunks;
+  if (!h->ion.ch.flags) return 0;
+  unsigned long long v[2] = { 0, 0 };
+  if (!ab2_check(cudaMemcpyAsync(h->d_scal + SC_MEMO_RATES, v, sizeof v, cudaMemcpyHostToDevice, h->stream), "memo stats H2D")) return -1;
+  k_ion_memo_count<<<(unsigned)((h->ion_nchunks + 255)/256), 256, 0, h->stream>>>(h->ion.ch.flags, (long)h->ion_nchunks, h->d_scal);
+  if (!ab2_check(cudaMemcpyAsync(v, h->d_scal + SC_MEMO_RATES, sizeof v, cudaMemcpyDeviceToHost, h->stream), "memo stats D2H")) return -1;
+  if (!ab2_check(cudaStreamSynchronize(h->stream), "memo stats sync")) return -1;
+  out[0] = (long long)v[0]; out[1] = (long long)v[1];
+  return 0;
 }
 
 __global__ void k_bvals_ionrad(IonDev ion, int nx1, int nx2, int nx3, double flux_i)
@@ -506,6 +661,9 @@ static int ion_radtransfer_impl(ab2_grid* h, int finegrid, double flux_in, doubl
   auto read_scalars = [&]() -> bool { return comm_read_scalars(h) == 0; };
 
   AB2_LAUNCH(h, KID_ION_PREP, (k_ion_prep<<<cgrid, 128, 0, st>>>(g, p, h->ion)));
+  // the memo of the sparse sub-cycle never outlives a call: the hydro step in between changes every cell
+  const bool memo = h->ion.ch.flags != nullptr;
+  if (memo && !ab2_check(cudaMemsetAsync(h->ion.ch.flags, 0, h->ion_nchunks*sizeof(unsigned), st), "ion memo reset")) return -1;
 
   // first iteration's rates (ph_rate_init + get_ph_rate_plane + compute_chem_rates + compute_therm_rates, :922-938)
   if (!reset_scalars()) return -1;
@@ -532,8 +690,10 @@ static int ion_radtransfer_impl(ab2_grid* h, int finegrid, double flux_in, doubl
     const bool last = hydro_done || coarsetime_done;          // the loop ends after this update whatever it finds
 
     if (!reset_scalars()) return -1;
-    if (last || !fuse) AB2_LAUNCH(h, KID_ION_UPDATE, (k_ion_update<<<cgrid, 128, 0, st>>>(g, p, h->ion, dt, h->d_scal)));
-    else      AB2_LAUNCH(h, KID_ION_FUSED, (k_ion_rates<true><<<rgrid, 128, 0, st>>>(g, p, h->ion, flux_in, finegrid, dt, h->ion.edgeflux, h->ion.edgeflux_alt, h->d_scal)));
+    // profile ids: from the second iteration on the kernels run against the memo and their time is no longer that of a full pass
+    const bool sparse = memo && niter > 0;
+    if (last || !fuse) AB2_LAUNCH(h, sparse ? KID_ION_UPDATE_MEMO : KID_ION_UPDATE, (k_ion_update<<<rgrid, 128, 0, st>>>(g, p, h->ion, dt, h->d_scal)));
+    else      AB2_LAUNCH(h, sparse ? KID_ION_FUSED_MEMO : KID_ION_FUSED, (k_ion_rates<true><<<rgrid, 128, 0, st>>>(g, p, h->ion, flux_in, finegrid, dt, h->ion.edgeflux, h->ion.edgeflux_alt, h->d_scal)));
     dt_done += dt;
     niter++;
     if (!read_scalars()) return -1;
@@ -555,7 +715,7 @@ static int ion_radtransfer_impl(ab2_grid* h, int finegrid, double flux_in, doubl
       dt_chem = v[2]; dt_therm = v[3];
     } else {               // separate rates pass of the next iteration
       if (!reset_scalars()) return -1;
-      AB2_LAUNCH(h, KID_ION_RATES, (k_ion_rates<false><<<rgrid, 128, 0, st>>>(g, p, h->ion, flux_in, finegrid, 0.0, h->ion.edgeflux, h->ion.edgeflux, h->d_scal)));
+      AB2_LAUNCH(h, memo ? KID_ION_RATES_MEMO : KID_ION_RATES, (k_ion_rates<false><<<rgrid, 128, 0, st>>>(g, p, h->ion, flux_in, finegrid, 0.0, h->ion.edgeflux, h->ion.edgeflux, h->d_scal)));
       if (!read_scalars()) return -1;
       if (hs[SC_ERR] & ERR_DT_CHEM_NEG) { ab2_set_error("[compute_chem_rates]: dt_chem < 0"); return -2; }
       v[2] = bits_to_double(hs[SC_DT_CHEM]); v[3] = bits_to_double(hs[SC_DT_THERM]);

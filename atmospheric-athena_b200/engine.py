@@ -68,7 +68,7 @@ EXPORTS = ["ab2_last_error", "ab2_version", "ab2_device_count", "ab2_grid_create
            "ab2_ion_init", "ab2_ion_derived", "ab2_bvals_ionrad", "ab2_ion_entering_flux", "ab2_ion_radtransfer_3d",
            "ab2_profile_enable", "ab2_profile_kernels", "ab2_profile_kernel_name", "ab2_profile_read",
            "ab2_smr_restrict_correct", "ab2_smr_ion_restrict", "ab2_smr_prolongate", "ab2_smr_ion_prolong",
-           "ab2_ion_radtransfer_3d_fine", "ab2_ion_coarse_time",
+           "ab2_ion_radtransfer_3d_fine", "ab2_ion_coarse_time", "ab2_set_ion_memo", "ab2_ion_memo_stats",
            "ab2_set_riemann_solver", "ab2_set_reconstruction",
            "ab2_comm_get_unique_id", "ab2_comm_init_rank", "ab2_comm_destroy", "ab2_comm_rank", "ab2_comm_size",
            "ab2_comm_exchanges", "ab2_comm_reductions", "ab2_comm_allreduce", "ab2_comm_bcast", "ab2_grid_set_comm",
@@ -143,6 +143,8 @@ def lib():
     L.ab2_ion_radtransfer_3d_fine.argtypes = [vp, C.c_double, dp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), vp, vp]
     L.ab2_ion_coarse_time.argtypes = [vp]
     L.ab2_ion_coarse_time.restype = C.c_double
+    L.ab2_set_ion_memo.argtypes = [vp, C.c_int]
+    L.ab2_ion_memo_stats.argtypes = [vp, C.POINTER(C.c_longlong)]
     L.ab2_profile_enable.argtypes = [vp, C.c_int]
     L.ab2_profile_kernel_name.argtypes = [C.c_int]
     L.ab2_profile_kernel_name.restype = C.c_char_p
@@ -459,6 +461,16 @@ class Grid:
     @property
     def ion_coarse_time(self):
         return lib().ab2_ion_coarse_time(self.h)
+
+    def set_ion_memo(self, on):
+        """Sparse sub-cycle on/off (include/athena_b200.h ab2_set_ion_memo): off re-evaluates every chunk in every iteration."""
+        self._ck(lib().ab2_set_ion_memo(self.h, int(bool(on))))
+
+    def ion_memo_stats(self):
+        """(chunks the latest rates pass re-used, chunks an update would re-use now, chunks per pass): a snapshot of the records."""
+        out = (C.c_longlong * 3)()
+        self._ck(lib().ab2_ion_memo_stats(self.h, out))
+        return int(out[0]), int(out[1]), int(out[2])
 
     # -- more than one GPU ------------------------------------------------------------------------
     def set_comm(self, comm, lo=None, hi=None):

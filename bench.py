@@ -470,9 +470,11 @@ def gpu_arm(args):
             ent["alg_bytes_per_launch"] = bpz * zones_local
             ent["gbs"] = round(bpz * zones_local / (kms / cnt * 1e-3) / 1e9, 1)
         ktab[name] = ent
-    dom = next(iter(ktab)) if ktab else None
+    # dominant kernel = largest total time among the kernels whose compulsory bytes per launch are known (the [memo] launches of
+    # the sparse ion sub-cycle evaluate a data-dependent fraction of the grid and carry no fixed figure)
+    dom = next((k for k in ktab if "gbs" in ktab[k]), None)
     roof = None
-    if dom and "gbs" in ktab[dom]:
+    if dom:
         prof_all = {}
         try:
             prof_all = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
@@ -502,6 +504,16 @@ def gpu_arm(args):
             pair_ms = ktab["k_ion_rates"]["ms_total"] / ktab["k_ion_rates"]["launches"] + ktab["k_ion_update"]["ms_total"] / ktab["k_ion_update"]["launches"]
             roof["ion_iteration_ms"] = round(pair_ms, 4)
             roof["ion_iteration_frac_at_112B"] = round(112.0 * zones_local / (pair_ms * 1e-3) / 1e9 / peak, 4)
+        if R.ion:
+            # sparse sub-cycle (csrc/ion.cu): from the second iteration of a step on, chunks of inert cells re-use their records
+            re_r, re_u, nchunk = G.ion_memo_stats()
+            memo_ms = sum(ktab[k]["ms_total"] for k in ktab if k.endswith("[memo]"))
+            memo_n = sum(ktab[k]["launches"] for k in ktab if k.endswith("[memo]"))
+            roof["ion_memo"] = {"rates_chunks_reused_frac": round(re_r / max(1, nchunk), 4), "update_chunks_reused_frac": round(re_u / max(1, nchunk), 4),
+                                "snapshot": "records after the last timed step's last pass", "memo_launches": memo_n,
+                                "memo_ms_per_launch": round(memo_ms / memo_n, 4) if memo_n else None,
+                                "note": "step_frac and ion_iteration_frac_at_112B count SURVEY 8(d)'s bytes for every zone and iteration, "
+                                        "re-used chunks included; ion_iteration_* is measured on the full first-iteration passes"}
         roof["per_kernel_ncu"] = {k: {"dram_util": round(v["dram_pct"] / 100.0, 3), "fp64_util": round(v["fp64_pipe_pct"] / 100.0, 3),
                                       "issue_util": round(v["issue_pct"] / 100.0, 3) if "issue_pct" in v else None}
                                   for k, v in prof_all.items() if k.startswith("k_") and "dram_pct" in v}

@@ -168,6 +168,15 @@ int ab2_ion_radtransfer_3d_fine(ab2_grid* g, double tcoarse, double* dt, int* ni
                                 ab2_reduce_fn reduce, void* ctx);
 /* the reference's file-static tcoarse (ionrad_3d.c:47,1028): dt_done of the last root-level ab2_ion_radtransfer_3d */
 double ab2_ion_coarse_time(const ab2_grid* g);
+/* Sparse sub-cycle.  ion_radtransfer_3d re-evaluates every cell in every sub-cycle iteration (ionrad_3d.c:919-1014); the
+ * library keeps one record per ray and 32-cell chunk and re-uses a chunk's rates, dt limits, check_range count and wave-speed
+ * maxima while every input of that arithmetic is bitwise unchanged (cells at the neutral floor that ionization_update's own
+ * condition :575 leaves alone, same incoming flux, sign states at their fixed point) -- results are bit-identical to the full
+ * re-evaluation.  on = 0 turns the memo off (every chunk evaluated every iteration; also AB2_ION_SKIP=0 in the environment at
+ * ab2_ion_init).  ab2_ion_memo_stats: out[0] = chunks the latest rates pass re-used, out[1] = chunks an update
+ * pass would re-use now, out[2] = chunks per pass of this Grid (a snapshot of the records, e.g. after a step). */
+int ab2_set_ion_memo(ab2_grid* g, int on);
+int ab2_ion_memo_stats(ab2_grid* g, long long out[3]);
 
 /* ---- the device side of the driver's writers ---------------------------------------------------------- */
 /* Page-lock a host array the driver owns (GridS.U) so the coherence copies run at PCIe speed straight into it. */

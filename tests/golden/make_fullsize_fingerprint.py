@@ -6,6 +6,7 @@ fingerprints are committed; same scheme as make_hires5_fingerprint.py):
     blast256_k2  configs[1]: blast 256^3 periodic, 2 steps        (oracle/_ref/blast)
     ifront64_k30 configs[0]: ifront 64^3 as shipped, 30 steps     (oracle/_ref/ifront)
     ioniz64s_k2 / blast64s_k4 / ifront64s_k3: 32x32x64 grids for the multi-GPU parity gate inside bench.py
+    ioniz96_k12 / ioniz80_k6: ioniz_sphere 96^3 x 12 steps and 80x48x40 x 6 steps for the sparse sub-cycle
 
 A bit-identical run reproduces every hash (tests/test_gpu_longrun.py).   python tests/golden/make_fullsize_fingerprint.py
 """
@@ -31,6 +32,10 @@ CASES = {
     "ioniz64s_k2": ("ioniz_sphere", "ioniz_sphere.athinput", 2, ["job/num_domains=1", "domain1/Nx1=32", "domain1/Nx2=32", "domain1/Nx3=64"]),
     "blast64s_k4": ("blast", "blast.athinput", 4, ["job/num_domains=1", "domain1/Nx1=32", "domain1/Nx2=32", "domain1/Nx3=64", "problem/radius=0.25"]),
     "ifront64s_k3": ("ifront", "ifront.athinput", 3, ["job/num_domains=1", "domain1/Nx1=32", "domain1/Nx2=32", "domain1/Nx3=64"]),
+    # the sparse sub-cycle (csrc/ion.cu): a box most of whose chunks are inert ambient gas, over enough steps and sub-cycle
+    # iterations that a wrongly re-used chunk would show (Nx1 = 96: three chunks per ray; Nx1 = 80: a ragged last chunk)
+    "ioniz96_k12": ("ioniz_sphere", "ioniz_sphere.athinput", 12, ["job/num_domains=1", "domain1/Nx1=96", "domain1/Nx2=96", "domain1/Nx3=96"]),
+    "ioniz80_k6": ("ioniz_sphere", "ioniz_sphere.athinput", 6, ["job/num_domains=1", "domain1/Nx1=80", "domain1/Nx2=48", "domain1/Nx3=40"]),
 }
 
 

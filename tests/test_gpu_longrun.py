@@ -113,11 +113,9 @@ def test_full_size_determinism_and_bounds_ioniz_256():
     assert np.isfinite(a["E"]).all()
 
 
-@pytest.mark.parametrize("name", ["ioniz256_k1", "blast256_k2", "ifront64_k30"])
-def test_full_size_matches_reference_fingerprint(name):
-    """BASELINE configs[2] / configs[1] / configs[0] AT FULL SIZE (256^3, 256^3, 64^3) against the reference itself: SHA-256 of every conserved
-    variable (and EdgeFlux) of the reference's dump, generated by tests/golden/make_fullsize_fingerprint.py from the
-    reference binary on this container's CPU; the engine's dump must hash to the same bytes."""
+def run_against_fingerprint(name, setup=None):
+    """Run the deck of tests/golden/<name>.json and compare SHA-256 of every variable (and EdgeFlux), time, dt and the sub-cycle
+    iteration counts with the reference's own dump.  Returns the Run."""
     import importlib.util
     import json
     from athena_b200.driver import Run
@@ -130,6 +128,8 @@ def test_full_size_matches_reference_fingerprint(name):
     par = ParFile.par_open(os.path.join(DECKS, gold["deck"]))
     par.par_cmdline(gold["overrides"])
     R = Run(par, gold["build"], device=0)
+    if setup is not None:
+        setup(R)
     R.run(gold["nstep"])
     g = R.G.download_active()
     ion = gold["build"] != "blast"
@@ -142,3 +142,34 @@ def test_full_size_matches_reference_fingerprint(name):
         got = mine["levels"][0][v]
         assert got["shape"] == ref["shape"]
         assert got["sha256"] == ref["sha256"], f"{v}: sum {got['sum']!r} vs {ref['sum']!r}, absmax {got['absmax']!r} vs {ref['absmax']!r}"
+    return R
+
+
+@pytest.mark.parametrize("name", ["ioniz256_k1", "blast256_k2", "ifront64_k30"])
+def test_full_size_matches_reference_fingerprint(name):
+    """BASELINE configs[2] / configs[1] / configs[0] AT FULL SIZE (256^3, 256^3, 64^3) against the reference itself: SHA-256 of every conserved
+    variable (and EdgeFlux) of the reference's dump, generated by tests/golden/make_fullsize_fingerprint.py from the
+    reference binary on this container's CPU; the engine's dump must hash to the same bytes."""
+    run_against_fingerprint(name)
+
+
+@pytest.mark.parametrize("name", ["ioniz96_k12", "ioniz80_k6", "ifront64s_k3"])
+@pytest.mark.parametrize("fuse", [0, 1])
+@pytest.mark.parametrize("memo", [1, 0])
+def test_sparse_subcycle_matches_reference_fingerprint(name, fuse, memo):
+    """The sub-cycle memo (csrc/ion.cu "sparse sub-cycle": chunks of inert ambient cells re-use the previous iteration's rates
+    and reductions) changes nothing: ioniz_sphere boxes most of whose chunks are inert -- 96^3 over 12 steps and 51 sub-cycle
+    iterations, 80x48x40 (ragged last chunk) -- and an ifront box where no chunk is, with the memo on and off, through the
+    rates/update pair (fuse 0) and the fused update+rates kernel (fuse 1), hash to the reference's dump: every variable,
+    EdgeFlux, time, dt and the iteration count of every step."""
+    os.environ["AB2_ION_FUSE"] = str(fuse)
+    try:
+        R = run_against_fingerprint(name, setup=lambda R: R.G.set_ion_memo(memo))
+    finally:
+        os.environ.pop("AB2_ION_FUSE", None)
+    re_r, re_u, n = R.G.ion_memo_stats()
+    if not memo:
+        assert re_r == 0 and re_u == 0
+    elif name.startswith("ioniz"):
+        # the records of the last step's last pass: the bulk of the box was re-used, and not all of it (the planet is active)
+        assert 0.5 * n < re_r < n and 0.5 * n < re_u < n, (re_r, re_u, n)
