@@ -60,7 +60,7 @@ static const char* KERNEL_NAMES[KID_N] = {
   "k_correct<0>", "k_correct<1>", "k_correct<2>", "k_final<0>", "k_final<1>", "k_final<2>", "k_update",
   "k_apply_fixed", "k_ion_prep", "k_ion_rates", "k_ion_update", "k_bvals_ionrad", "k_transpose",
   "k_smr_restrict", "k_smr_flux_correct", "k_smr_prolongate", "k_ion_rates<fused update>", "k_cfinal", "k_correct3",
-  "k_ion_rates[memo]", "k_ion_update[memo]", "k_ion_rates<fused update>[memo]" };
+  "k_ion_rates[memo]", "k_ion_update[memo]", "k_ion_walk" };
 
 cudaEvent_t ab2_prof_event(ab2_grid* h)
 {
@@ -159,6 +159,7 @@ ab2_grid* ab2_grid_create(const ab2_grid_desc* d)
   ab2_grid* h = new ab2_grid();
   memset(&h->g, 0, sizeof h->g);
   h->nscal = d->nscal; h->device = d->device;
+  h->ion_ch_flags = nullptr; h->ion_nchunks = 0; h->ion_last_ntask = 0; h->ion_last_nskip = 0;
   h->has_grav = false; h->has_ion = false; h->n_fixed = 0; h->d_fixed_cells = nullptr; h->d_fixed_vals = nullptr;
   h->bytes_allocated = 0; h->launches = 0; h->maxiter = 0; h->tcoarse = 0.0;
   h->prof_on = false;
@@ -531,15 +532,15 @@ int ab2_ion_init(ab2_grid* h, const ab2_ion_par* par)
     double* s = dev_alloc(h, (ncell+1)/2);
     if (!s) return -1;
     I.sign_state = (int*)s;
-    // sub-cycle memo (engine.cuh IonChunks): one record per ray and 32-cell chunk
+    // sub-cycle memo (engine.cuh IonChunks): one record per ray and 32-cell chunk, one task slot per ray
     IonChunks& C = I.ch;
     C.nch = (h->g.nx[0] + 31)/32;
-    const size_t nchunks = (size_t)h->g.nx[1]*h->g.nx[2]*C.nch;
-    double* fl = dev_alloc(h, (nchunks+1)/2), *cn = dev_alloc(h, (nchunks+1)/2);
-    if (!fl || !cn || !(C.carry_in = dev_alloc(h, nchunks)) || !(C.carry_out = dev_alloc(h, nchunks)) || !(C.dtc = dev_alloc(h, nchunks)) ||
-        !(C.dtt = dev_alloc(h, nchunks)) || !(C.m1 = dev_alloc(h, nchunks)) || !(C.m2 = dev_alloc(h, nchunks)) || !(C.m3 = dev_alloc(h, nchunks))) return -1;
-    C.cnt = (unsigned*)cn;
+    const size_t nrays = (size_t)h->g.nx[1]*h->g.nx[2], nchunks = nrays*C.nch;
+    double* fl = dev_alloc(h, nchunks + 1), *tk = dev_alloc(h, nrays*sizeof(IonTask)/sizeof(double));
+    if (!fl || !tk || !(C.rec = dev_alloc(h, 8*nchunks))) return -1;
+    C.tasks = (IonTask*)tk;
     h->ion_ch_flags = (unsigned*)fl; h->ion_nchunks = nchunks;
+    C.uflags = (unsigned*)fl + nchunks;
     const char* env = getenv("AB2_ION_SKIP");
     C.flags = (env && atoi(env) == 0) ? nullptr : h->ion_ch_flags;
     CK(cudaStreamSynchronize(h->stream), "ion init sync");

@@ -57,7 +57,9 @@ enum {
   SC_MAX_DTI,                         // ion: compute_dt_hydro max (atomicMax)
   SC_COUNT,                           // ion: check_range cell count (u64)
   SC_ERR,                             // sticky error flags
-  SC_MEMO_RATES, SC_MEMO_UPDATE,      // ion: chunks whose rates / update were whose records say re-used (scratch of ab2_ion_memo_stats, not exchanged)
+  // sparse ion sub-cycle, written by k_ion_walk: reductions over the re-used chunks (folded into the pass scalars by the
+  // first warp of the kernels that run over the task list), number of listed rays, number of re-used chunks
+  SC_W_DTC, SC_W_DTT, SC_W_M1, SC_W_M2, SC_W_M3, SC_W_CNT, SC_NTASK, SC_W_NSKIP,
   SC_N = 16
 };
 #define SC_NRED 8                     // SC_MAXV1 .. SC_ERR: the scalars one cross-rank exchange combines (comm.cu)
@@ -73,17 +75,17 @@ struct IonParDev {
 // Sub-cycle memo, one record per (ray, 32-cell chunk along x1) -- ion.cu "sparse sub-cycle".  Within one call of
 // ion_radtransfer_3d a chunk whose cells no update touches (fully ionised ambient gas at the neutral floor, the bulk
 // of an irradiated-planet box) sees the same inputs in every iteration, so its rates, its reductions and its
-// outgoing flux are those of the previous iteration bit for bit: the kernels re-use them instead of re-evaluating.
-#define CH_RFIX      1u      // rates in memory were computed with every cell's sign state at its fixed point
-#define CH_SAME      2u      // the latest rates pass left this chunk's outputs as they were
-#define CH_UINERT    4u      // the latest update left E and s of every cell of the chunk untouched (no cell met the update condition, no floor fired)
-#define CH_UCACHED   8u      // cnt / m1..m3 hold the update's check_range count and wave-speed maxima of the chunk
-#define CH_ALIVE_IN  16u     // the ray was still uncut where it entered the chunk
-#define CH_ALIVE_OUT 32u     // ... where it left it
+// outgoing flux are those of the previous iteration bit for bit: they are re-used instead of re-evaluated.
+#define CH_RFIX      1u      // rates in memory were computed with every cell's sign state at its fixed point, no cell meeting the update's condition
+#define CH_UINERT    2u      // the update after those rates left E and s of every cell of the chunk untouched (condition false, no floor fired)
+#define CH_ALIVE_IN  4u      // the ray was still uncut where it entered the chunk
+#define CH_ALIVE_OUT 8u      // ... where it left it
+struct IonTask { int ray, ch0; double carry; int alive, pad; };   // evaluate `ray` from chunk ch0 on, entered with this flux / cut state
 struct IonChunks {
   unsigned* flags;            // NULL: memo off (AB2_ION_SKIP=0), every chunk is evaluated in every iteration
-  unsigned* cnt;
-  double *carry_in, *carry_out, *dtc, *dtt, *m1, *m2, *m3;
+  unsigned* uflags;           // CH_UINERT, written by k_ion_update (flags: the other bits, written by k_ion_rates)
+  double* rec;                // 8 doubles per chunk: flux in, flux out, min dt_chem, min dt_therm | max |v_d|+a (d = 1..3), check_range count
+  IonTask* tasks;             // rays with a chunk to evaluate, listed by k_ion_walk
   int nch;                    // chunks per ray = ceil(nx1 / 32)
 };
 
@@ -104,7 +106,7 @@ enum {
   KID_CORRECT_X1, KID_CORRECT_X2, KID_CORRECT_X3, KID_FINAL_X1, KID_FINAL_X2, KID_FINAL_X3, KID_UPDATE,
   KID_APPLY_FIXED, KID_ION_PREP, KID_ION_RATES, KID_ION_UPDATE, KID_BVALS_IONRAD, KID_TRANSPOSE,
   KID_SMR_RESTRICT, KID_SMR_FLUXCORR, KID_SMR_PROLONG, KID_ION_FUSED, KID_CFINAL, KID_CORRECT3,
-  KID_ION_RATES_MEMO, KID_ION_UPDATE_MEMO, KID_ION_FUSED_MEMO, KID_N
+  KID_ION_RATES_MEMO, KID_ION_UPDATE_MEMO, KID_ION_WALK, KID_N
 };
 struct ProfPending { int id; cudaEvent_t a, b; };
 
@@ -126,6 +128,8 @@ struct ab2_grid {
   int maxiter;
   unsigned* ion_ch_flags;          // the memo's flag array (ion.ch.flags is NULL while AB2_ION_SKIP=0 turns the memo off)
   size_t ion_nchunks;
+  int ion_last_ntask;              // the latest k_ion_walk: rays listed, chunks re-used (ab2_ion_memo_stats)
+  long long ion_last_nskip;
   double tcoarse;                  // ionrad_3d.c:1028: dt_done of the last root-level radiation call
   double* scratch;                 // one allocation behind Ul/Ur/F/Ff/eta (and Uin, carry when chunked)
   size_t scratch_doubles;

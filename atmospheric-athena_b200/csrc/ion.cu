@@ -296,8 +296,13 @@ __device__ __forceinline__ CellRates cell_rates(const GridDev& g, const IonParDe
 // own condition (ionrad_3d.c:575 `nHdot > 0 || s > 1.0001 d_nlim`) leaves E and s alone.  A 32-cell chunk of a ray all
 // of whose cells are in that state, whose incoming flux has the bits it had in the previous iteration and whose sign
 // states sit at their fixed point (count 0, last_sign = sign(nHdot)) gets bit-identical rates, dt limits, outgoing flux,
-// check_range count and wave-speed maxima from a re-evaluation -- so both kernels take them from the chunk's record
-// instead.  Nothing is approximated: a chunk is re-used only when every input of the reference's arithmetic is unchanged.
+// check_range count and wave-speed maxima from a re-evaluation.  So from the second iteration of a call on
+//   k_ion_walk   reads the chunk records ray by ray, finds the first chunk of each ray that has to be evaluated, deposits
+//                the recorded reductions of the chunks before it, and lists the rays that have such a chunk;
+//   k_ion_rates / k_ion_update then run over that list only, each ray from its first such chunk on.
+// Nothing is approximated: a chunk is re-used only while every input of the reference's arithmetic is bitwise unchanged.
+// The pair k_ion_rates<false> / k_ion_update carries the memo; the fused k_ion_rates<true> (small Grids, where an
+// iteration is launch-bound) evaluates everything.
 // ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool ordered_bits(double x)
 { // non-negative and not NaN: the bit pattern orders like the value
@@ -320,36 +325,7 @@ __device__ __forceinline__ double warp_max_ordered(double x)
   return __longlong_as_double((long long)(((unsigned long long)mh << 32) | ml));
 }
 __device__ __forceinline__ bool same_bits(double a, double b) { return __double_as_longlong(a) == __double_as_longlong(b); }
-
-// One chunk of k_ion_update for a warp: the cells' update + the chunk's memo.  Returns the (possibly changed) flags.
-// E, s are the lane's values on entry and the updated ones on return.
-__device__ __forceinline__ unsigned update_chunk(const GridDev& g, const IonParDev& p, const IonDev& ion, long c, long q, bool valid, int lane,
-                                                 double dt, double d, double M1, double M2, double M3, double& E, double& s, unsigned fl,
-                                                 unsigned& count, double& m1, double& m2, double& m3)
-{
-  CellUpd u; u.E = E; u.s = s; u.x1 = u.x2 = u.x3 = 0.0; u.count = 0; u.applied = false;
-  if (valid) {
-    ION_GUARDED(u = cell_update(g, p, ion, c, dt, d, M1, M2, M3, E, s, ar));
-    g.U[4][c] = u.E; g.U[5][c] = u.s;
-    count += u.count;
-    m1 = AB2_MAX(m1, u.x1); m2 = AB2_MAX(m2, u.x2); m3 = AB2_MAX(m3, u.x3);
-  }
-  if (ion.ch.flags) {
-    const bool inert = __all_sync(0xffffffffu, !valid || (!u.applied && same_bits(u.E, E) && same_bits(u.s, s)
-                                                          && ordered_bits(u.x1) && ordered_bits(u.x2) && ordered_bits(u.x3)));
-    unsigned nf = fl & ~(CH_UINERT | CH_UCACHED);
-    if (inert) {
-      const double c1 = warp_max_ordered(u.x1), c2 = warp_max_ordered(u.x2), c3 = warp_max_ordered(u.x3);
-      const unsigned cc = __popc(__ballot_sync(0xffffffffu, u.count != 0));
-      if (lane == 0) { ion.ch.m1[q] = c1; ion.ch.m2[q] = c2; ion.ch.m3[q] = c3; ion.ch.cnt[q] = cc; }
-      nf |= CH_UINERT | CH_UCACHED;
-    }
-    if (lane == 0) ion.ch.flags[q] = nf;
-    fl = nf;
-  }
-  E = u.E; s = u.s;
-  return fl;
-}
+__device__ __forceinline__ double scal_as_double(const unsigned long long* scal, int i) { return __longlong_as_double((long long)scal[i]); }
 
 // ---------------------------------------------------------------------------------------------------
 // k_ion_rates: ray trace (ionradplane_3d.c:254-310) + chem rates (ionrad_3d.c:307-394) + therm rates (:433-550)
@@ -359,14 +335,32 @@ __device__ __forceinline__ unsigned update_chunk(const GridDev& g, const IonParD
 // saves one pass over U per sub-cycle iteration and lets the host read all six loop scalars in ONE synchronisation.
 // The new EdgeFlux goes to ef_out (the alternate buffer) because the iteration may turn out to be the last one,
 // in which case the reference's EdgeFlux is the one written before this update.
-template <bool UPDATE>
+// tasks != NULL (sparse pass of the pair, UPDATE = false): warp w evaluates ray tasks[w].ray from chunk tasks[w].ch0 on, entered with
+// the flux and cut state k_ion_walk found there; the chunks before it keep what is in memory.  The first warp also folds the
+// dt limits k_ion_walk deposited for the re-used chunks into the pass scalars.
+// MEMO: the pass writes the chunk records; TASKS: it runs over k_ion_walk's list (both compile-time, so that the full pass
+// without the memo is the plain kernel).
+template <bool UPDATE, bool MEMO, bool TASKS>
 __global__ void __launch_bounds__(128, AB2_LB_ION_RATES) k_ion_rates(GridDev g, IonParDev p, IonDev ion, double flux_in_root, int finegrid, double dt_upd,
-                                                   const double* ef_in_base, double* ef_out_base, unsigned long long* scal)
+                                                   const double* ef_in_base, double* ef_out_base, unsigned long long* scal,
+                                                   const IonTask* tasks, int ntask)
 {
+  static_assert(!(UPDATE && (MEMO || TASKS)) && !(TASKS && !MEMO), "the memo belongs to the rates / update pair");
   __shared__ double s_etau[128];
   const int lane = threadIdx.x & 31;
-  const long ray = (long)blockIdx.x*(blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long w = (long)blockIdx.x*(blockDim.x >> 5) + (threadIdx.x >> 5);
   const long nrays = (long)g.nx[1]*g.nx[2];
+  constexpr bool memo = MEMO;
+  long ray = w;
+  int c_first = 0;
+  if (TASKS) {
+    if (w == 0 && lane == 0) {
+      atomic_min_double(&scal[SC_DT_CHEM], scal_as_double(scal, SC_W_DTC));
+      atomic_min_double(&scal[SC_DT_THERM], scal_as_double(scal, SC_W_DTT));
+    }
+    if (w >= ntask) return;
+    ray = tasks[w].ray; c_first = tasks[w].ch0*32;
+  }
   if (ray >= nrays) return;
   const int jj = (int)(ray % g.nx[1]), kk = (int)(ray / g.nx[1]);
   const long row = (long)(kk+NG)*g.st[2] + (long)(jj+NG)*g.st[1] + NG;
@@ -374,61 +368,34 @@ __global__ void __launch_bounds__(128, AB2_LB_ION_RATES) k_ion_rates(GridDev g, 
   double* ef = ef_out_base + efo;
   const double dx1 = g.dx[0];
   const int nx1 = g.nx[0];
-  const bool memo = ion.ch.flags != nullptr;
 
   // root level: the time-ramped plane flux; finer levels: the value handed down into EdgeFlux[k][j][0] (ionradplane_3d.c:263-272)
   const double flux_in = finegrid ? ef_in_base[efo] : flux_in_root;
-  unsigned count = 0;                                 // check_range / compute_dt_hydro of the fused update
+  unsigned long long count = 0;                       // check_range / compute_dt_hydro of the fused update
   double m1 = 0.0, m2 = 0.0, m3 = 0.0;
   double carry = flux_in;         // flux entering the current chunk
   bool alive = true;              // false once the ray has been cut
+  if (TASKS) { carry = tasks[w].carry; alive = tasks[w].alive != 0; }
   double dt_chem_min = LARGE, dt_therm_min = LARGE;
   unsigned long long err = 0;
 
-  long q = ray*ion.ch.nch;
-  unsigned fl_ray = 0;            // the flags of (up to) 32 chunks of the ray, one per lane
-  for (int c0 = 0, ch = 0; c0 < nx1; c0 += 32, ch++, q++) {
+  long q = ray*ion.ch.nch + (c_first >> 5);           // the chunk's record
+  for (int c0 = c_first; c0 < nx1; c0 += 32, q++) {
     const int ii = c0 + lane;
     const bool valid = ii < nx1;
     const long c = row + (valid ? ii : nx1-1);
-    if (memo && (ch & 31) == 0) fl_ray = (ch + lane < ion.ch.nch) ? ion.ch.flags[q + lane] : 0u;
-    unsigned fl = __shfl_sync(0xffffffffu, fl_ray, ch & 31);
-    // the chunk's update is re-used when its rates are the previous iteration's and that iteration's update touched nothing;
-    // its rates when, on top, the ray reaches it as it did before (flux bits, or cut in both)
-    const bool uskip = !UPDATE || ((fl & (CH_SAME|CH_UINERT|CH_UCACHED)) == (CH_SAME|CH_UINERT|CH_UCACHED));
-    double rec_in = 0.0, rec_out = 0.0, rec_dtc = LARGE, rec_dtt = LARGE;      // the record, fetched in one go
-    if (fl & CH_RFIX) { rec_in = ion.ch.carry_in[q]; rec_out = ion.ch.carry_out[q]; rec_dtc = ion.ch.dtc[q]; rec_dtt = ion.ch.dtt[q]; }
-    const bool rmatch = (fl & CH_RFIX) && (((fl & CH_ALIVE_IN) != 0) == alive) && (!alive || same_bits(carry, rec_in));
-    bool rskip = uskip && rmatch && (fl & CH_UINERT);
-    double d = 0.0, M1 = 0.0, M2 = 0.0, M3 = 0.0, E = 0.0, s = 0.0;
-    if (!rskip) {
-      d = g.U[0][c]; M1 = g.U[1][c]; M2 = g.U[2][c]; M3 = g.U[3][c];
-      E = g.U[4][c]; s = g.U[5][c];
+    unsigned fl = alive ? CH_ALIVE_IN : 0u;           // the record's flags, rebuilt by every evaluation
+    if (memo && lane == 0) ion.ch.rec[q*8 + 0] = carry;
+    const double d = g.U[0][c], M1 = g.U[1][c], M2 = g.U[2][c], M3 = g.U[3][c];
+    double E = g.U[4][c], s = g.U[5][c];
+    if (UPDATE && valid) {
+      CellUpd u;
+      ION_GUARDED(u = cell_update(g, p, ion, c, dt_upd, d, M1, M2, M3, E, s, ar));
+      E = u.E; s = u.s;
+      g.U[4][c] = E; g.U[5][c] = s;
+      count += u.count;
+      m1 = AB2_MAX(m1, u.x1); m2 = AB2_MAX(m2, u.x2); m3 = AB2_MAX(m3, u.x3);
     }
-    if (UPDATE) {
-      if (uskip) {
-        if (lane == 0) count += ion.ch.cnt[q];
-        const double c1 = ion.ch.m1[q], c2 = ion.ch.m2[q], c3 = ion.ch.m3[q];
-        m1 = AB2_MAX(m1, c1); m2 = AB2_MAX(m2, c2); m3 = AB2_MAX(m3, c3);
-      } else {
-        fl = update_chunk(g, p, ion, c, q, valid, lane, dt_upd, d, M1, M2, M3, E, s, fl, count, m1, m2, m3);
-        rskip = rmatch && (fl & CH_UINERT);
-      }
-    }
-    if (rskip) {
-      // same inputs as in the previous iteration: rates, ph_rate, sign states in memory stand; only the flux the chunk hands on,
-      // its dt limits and (fused launches write the alternate buffer) its EdgeFlux entries are needed
-      if (UPDATE && valid) ef[ii] = (ef_in_base + efo)[ii];
-      if (rec_dtc < dt_chem_min) dt_chem_min = rec_dtc;
-      if (rec_dtt < dt_therm_min) dt_therm_min = rec_dtt;
-      carry = rec_out;
-      alive = (fl & CH_ALIVE_OUT) != 0;
-      if (lane == 0 && !(fl & CH_SAME)) ion.ch.flags[q] = fl | CH_SAME;
-      continue;
-    }
-    // evaluated: the record's flags are rebuilt (CH_SAME off); the incoming flux is noted now, it only counts once CH_RFIX is set
-    fl = (fl & (CH_UINERT | CH_UCACHED)) | (alive ? CH_ALIVE_IN : 0u);
-    if (memo && lane == 0) ion.ch.carry_in[q] = carry;
 
     // --- ray: tau, attenuation, photoionisation rate
     double n_H;
@@ -463,8 +430,8 @@ __global__ void __launch_bounds__(128, AB2_LB_ION_RATES) k_ion_rates(GridDev g, 
     carry = __shfl_sync(0xffffffffu, flux_after, 31);
     if (first < 32) alive = false;
 
-    bool keep = true;                   // this cell allows the chunk's record to stand in for a re-evaluation
-    double cdtc = LARGE, cdtt = LARGE;  // (dead code unless the memo is on)
+    bool keep = true;                   // this cell lets the chunk's record stand in for a re-evaluation
+    double cdtc = LARGE, cdtt = LARGE;
     if (valid) {
       CellRates r;
       const int st = ion.sign_state[c];
@@ -479,7 +446,7 @@ __global__ void __launch_bounds__(128, AB2_LB_ION_RATES) k_ion_rates(GridDev g, 
         double d_nlim = d*IONFRACFLOOR;
         d_nlim = d_nlim < p.d_nlo ? d_nlim : p.d_nlo;
         // sign_count 0 after the transition = fixed point (last_sign is always the current sign); the update's condition on
-        // the stored (damped) rate is false; dt limits are plain non-negative numbers
+        // the stored (damped) rate is false; the dt limits are plain non-negative numbers
         keep = ((r.sign_state >> 2) == 0) && !((r.nHdot > 0) || (s > 1.0001*d_nlim)) && ordered_bits(r.dt_chem) && ordered_bits(r.dt_therm);
         cdtc = r.dt_chem; cdtt = r.dt_therm;
       }
@@ -488,10 +455,10 @@ __global__ void __launch_bounds__(128, AB2_LB_ION_RATES) k_ion_rates(GridDev g, 
       if (alive) fl |= CH_ALIVE_OUT;
       if (__all_sync(0xffffffffu, keep)) {
         cdtc = warp_min_ordered(cdtc); cdtt = warp_min_ordered(cdtt);
-        if (lane == 0) { ion.ch.carry_out[q] = carry; ion.ch.dtc[q] = cdtc; ion.ch.dtt[q] = cdtt; }
+        if (lane >= 1 && lane < 4) ion.ch.rec[q*8 + lane] = (lane == 1) ? carry : (lane == 2) ? cdtc : cdtt;
         fl |= CH_RFIX;
       }
-      if (lane == 0) ion.ch.flags[q] = fl;
+      if (lane == 0) ion.ch.flags[q] = fl;              // CH_UINERT lives in uflags: the update that follows decides
     }
   }
   if (lane == 0) ef[nx1] = alive ? carry : 0.0;      // ionradplane_3d.c:308
@@ -515,7 +482,7 @@ __global__ void __launch_bounds__(128, AB2_LB_ION_RATES) k_ion_rates(GridDev g, 
     atomic_min_double(&scal[SC_DT_THERM], dt_therm_min);
     if (err) atomicOr(&scal[SC_ERR], err);
     if (UPDATE) {
-      if (count) atomicAdd(&scal[SC_COUNT], (unsigned long long)count);
+      if (count) atomicAdd(&scal[SC_COUNT], count);
       atomic_max_double(&scal[SC_MAXV1], m1);
       atomic_max_double(&scal[SC_MAXV2], m2);
       atomic_max_double(&scal[SC_MAXV3], m3);
@@ -525,38 +492,61 @@ __global__ void __launch_bounds__(128, AB2_LB_ION_RATES) k_ion_rates(GridDev g, 
 
 // ---------------------------------------------------------------------------------------------------
 // k_ion_update: ionization_update (:565-590) + floors (:970-971) + check_range (:206-283) + compute_dt_hydro (:593-678).
-// One warp per ray, 32 cells at a time like k_ion_rates, so that both kernels address the same chunk records.
+// One warp per 32-cell chunk of a ray, so that it addresses the chunk records of k_ion_rates.
+// tasks != NULL (sparse pass): warp w takes ray tasks[w].ray and the chunks from tasks[w].ch0 on; the first warp folds in the
+// count and maxima k_ion_walk deposited for the re-used chunks.
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128, AB2_LB_ION_UPDATE) k_ion_update(GridDev g, IonParDev p, IonDev ion, double dt, unsigned long long* scal)
+template <bool MEMO, bool TASKS>
+__global__ void __launch_bounds__(128, AB2_LB_ION_UPDATE) k_ion_update(GridDev g, IonParDev p, IonDev ion, double dt, unsigned long long* scal,
+                                                                      const IonTask* tasks, int ntask)
 {
+  static_assert(!(TASKS && !MEMO), "the task list belongs to the memo");
   const int lane = threadIdx.x & 31;
-  const long ray = (long)blockIdx.x*(blockDim.x >> 5) + (threadIdx.x >> 5);
-  const long nrays = (long)g.nx[1]*g.nx[2];
-  if (ray >= nrays) return;
-  const int jj = (int)(ray % g.nx[1]), kk = (int)(ray / g.nx[1]);
-  const long row = (long)(kk+NG)*g.st[2] + (long)(jj+NG)*g.st[1] + NG;
-  const int nx1 = g.nx[0];
-  const bool memo = ion.ch.flags != nullptr;
-  unsigned count = 0;
-  double m1 = 0.0, m2 = 0.0, m3 = 0.0;
-  long q = ray*ion.ch.nch;
-  unsigned fl_ray = 0;
-  for (int c0 = 0, ch = 0; c0 < nx1; c0 += 32, ch++, q++) {
-    if (memo && (ch & 31) == 0) fl_ray = (ch + lane < ion.ch.nch) ? ion.ch.flags[q + lane] : 0u;
-    const unsigned fl = __shfl_sync(0xffffffffu, fl_ray, ch & 31);
-    if ((fl & (CH_SAME|CH_UINERT|CH_UCACHED)) == (CH_SAME|CH_UINERT|CH_UCACHED)) {
-      if (lane == 0) count += ion.ch.cnt[q];
-      const double c1 = ion.ch.m1[q], c2 = ion.ch.m2[q], c3 = ion.ch.m3[q];
-      m1 = AB2_MAX(m1, c1); m2 = AB2_MAX(m2, c2); m3 = AB2_MAX(m3, c3);
-      continue;
+  const long w = (long)blockIdx.x*(blockDim.x >> 5) + (threadIdx.x >> 5);
+  // consecutive warps take consecutive chunks of a ray (of a listed ray: from its first chunk to evaluate on)
+  long ray = w / ion.ch.nch;
+  int ch = (int)(w - ray*ion.ch.nch);
+  if (TASKS) {
+    if (w == 0 && lane == 0) {
+      const unsigned long long wc = scal[SC_W_CNT];
+      if (wc) atomicAdd(&scal[SC_COUNT], wc);
+      atomic_max_double(&scal[SC_MAXV1], scal_as_double(scal, SC_W_M1));
+      atomic_max_double(&scal[SC_MAXV2], scal_as_double(scal, SC_W_M2));
+      atomic_max_double(&scal[SC_MAXV3], scal_as_double(scal, SC_W_M3));
     }
-    const int ii = c0 + lane;
-    const bool valid = ii < nx1;
-    const long c = row + (valid ? ii : nx1-1);
-    const double d = g.U[0][c], M1 = g.U[1][c], M2 = g.U[2][c], M3 = g.U[3][c];
-    double E = g.U[4][c], s = g.U[5][c];
-    update_chunk(g, p, ion, c, q, valid, lane, dt, d, M1, M2, M3, E, s, fl, count, m1, m2, m3);
+    if (ray >= ntask) return;
+    const IonTask t = tasks[ray];
+    ray = t.ray; ch += t.ch0;
   }
+  if (ray >= (long)g.nx[1]*g.nx[2] || ch >= ion.ch.nch) return;
+  const int jj = (int)(ray % g.nx[1]), kk = (int)(ray / g.nx[1]);
+  const int ii = ch*32 + lane;
+  const bool valid = ii < g.nx[0];
+  const long c = (long)(kk+NG)*g.st[2] + (long)(jj+NG)*g.st[1] + NG + (valid ? ii : g.nx[0]-1);
+  CellUpd u; u.x1 = u.x2 = u.x3 = 0.0; u.count = 0; u.applied = false;
+  bool inert = true;
+  if (valid) {
+    const double d = g.U[0][c], M1 = g.U[1][c], M2 = g.U[2][c], M3 = g.U[3][c];
+    const double E = g.U[4][c], s = g.U[5][c];
+    ION_GUARDED(u = cell_update(g, p, ion, c, dt, d, M1, M2, M3, E, s, ar));
+    g.U[4][c] = u.E; g.U[5][c] = u.s;
+    inert = !u.applied && same_bits(u.E, E) && same_bits(u.s, s) && ordered_bits(u.x1) && ordered_bits(u.x2) && ordered_bits(u.x3);
+  }
+  unsigned long long count = u.count;
+  double m1 = u.x1, m2 = u.x2, m3 = u.x3;           // >= 0 or NaN; a NaN never wins below (as in the running MAX from 0.0)
+  if (MEMO) {
+    // the chunk's record: no cell met the update's condition and no floor fired -> with unchanged rates the next update
+    // of this chunk changes nothing either and contributes this count and these maxima
+    const long q = ray*ion.ch.nch + ch;
+    inert = __all_sync(0xffffffffu, inert);
+    if (inert) {
+      const double c1 = warp_max_ordered(u.x1), c2 = warp_max_ordered(u.x2), c3 = warp_max_ordered(u.x3);
+      const unsigned cc = __popc(__ballot_sync(0xffffffffu, u.count != 0));
+      if (lane >= 4 && lane < 8) ion.ch.rec[q*8 + lane] = (lane == 4) ? c1 : (lane == 5) ? c2 : (lane == 6) ? c3 : (double)cc;
+    }
+    if (lane == 0) ion.ch.uflags[q] = inert ? CH_UINERT : 0u;          // its own array: a plain store, no read-modify-write of the rates' flags
+  }
+  m1 = AB2_MAX(0.0, m1); m2 = AB2_MAX(0.0, m2); m3 = AB2_MAX(0.0, m3);
   for (int o=16; o>0; o>>=1) {
     count += __shfl_xor_sync(0xffffffffu, count, o);
     double y;
@@ -565,37 +555,94 @@ __global__ void __launch_bounds__(128, AB2_LB_ION_UPDATE) k_ion_update(GridDev g
     y = __shfl_xor_sync(0xffffffffu, m3, o); m3 = AB2_MAX(m3, y);
   }
   if (lane == 0) {
-    if (count) atomicAdd(&scal[SC_COUNT], (unsigned long long)count);
+    if (count) atomicAdd(&scal[SC_COUNT], count);
     atomic_max_double(&scal[SC_MAXV1], m1);
     atomic_max_double(&scal[SC_MAXV2], m2);
     atomic_max_double(&scal[SC_MAXV3], m3);
   }
 }
 
-// how many chunk records say "re-used by the latest rates pass" / "the next update would be re-used" (ab2_ion_memo_stats)
-__global__ void k_ion_memo_count(const unsigned* flags, long n, unsigned long long* scal)
-{
-  const long t = (long)blockIdx.x*blockDim.x + threadIdx.x;
-  const unsigned fl = t < n ? flags[t] : 0u;
-  const unsigned a = __popc(__ballot_sync(0xffffffffu, (fl & CH_SAME) != 0));
-  const unsigned b = __popc(__ballot_sync(0xffffffffu, (fl & (CH_SAME|CH_UINERT|CH_UCACHED)) == (CH_SAME|CH_UINERT|CH_UCACHED)));
-  if ((threadIdx.x & 31) == 0) {
-    if (a) atomicAdd(&scal[SC_MEMO_RATES], (unsigned long long)a);
-    if (b) atomicAdd(&scal[SC_MEMO_UPDATE], (unsigned long long)b);
+// ---------------------------------------------------------------------------------------------------
+// k_ion_walk: one warp per ray, one lane per chunk record.  Chunk ch is re-usable when its record says so (CH_RFIX: rates
+// evaluated at the sign states' fixed point; CH_UINERT: the update after them touched nothing) AND it would be entered as
+// it was when the record was made: same cut state, same flux bits -- where "entered" is what the record of chunk ch-1
+// says it hands on, which holds by induction while every chunk before is re-usable too.  The first chunk that fails
+// starts the ray's task; the chunks before it deposit their recorded dt limits (rates pass) and count / wave-speed
+// maxima (update pass) in the SC_W_* scalars.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_ion_walk(GridDev g, IonDev ion, double flux_in_root, int finegrid, const double* ef_in_base,
+                                                  unsigned long long* scal)
+{ // persistent: every warp walks rays w, w + (warps in the grid), ...; one set of deposits per block at the end
+  __shared__ double s_red[5][8];
+  __shared__ unsigned s_cnt[2][8];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const long nrays = (long)g.nx[1]*g.nx[2];
+  const long nwarps = (long)gridDim.x*(blockDim.x >> 5);
+  const int nch = ion.ch.nch;
+  double mdtc = LARGE, mdtt = LARGE, mm1 = 0.0, mm2 = 0.0, mm3 = 0.0;    // lane-level, over all rays of this warp
+  unsigned mcnt = 0, nskip = 0;
+  for (long ray = (long)blockIdx.x*(blockDim.x >> 5) + wib; ray < nrays; ray += nwarps) {
+    const int jj = (int)(ray % g.nx[1]), kk = (int)(ray / g.nx[1]);
+    const long efo = ((long)kk*(g.nx[1]+1) + jj)*(g.nx[0]+1);
+    double prev_out = finegrid ? ef_in_base[efo] : flux_in_root;   // what the chunk before hands on
+    int prev_alive = 1;
+    for (int base = 0; base < nch; base += 32) {
+      const int ch = base + lane;
+      const bool valid = ch < nch;
+      const long q = ray*nch + (valid ? ch : nch-1);
+      const unsigned f = valid ? (ion.ch.flags[q] | ion.ch.uflags[q]) : 0u;
+      const double r_in = ion.ch.rec[q*8 + 0], r_out = ion.ch.rec[q*8 + 1];
+      double po = __shfl_up_sync(0xffffffffu, r_out, 1);
+      int pa = __shfl_up_sync(0xffffffffu, (int)((f & CH_ALIVE_OUT) != 0), 1);
+      if (lane == 0) { po = prev_out; pa = prev_alive; }
+      const bool ok = (f & CH_RFIX) && (f & CH_UINERT) && (((f & CH_ALIVE_IN) != 0) == (pa != 0)) && (!pa || same_bits(r_in, po));
+      const unsigned bad = __ballot_sync(0xffffffffu, valid && !ok);
+      const int first = bad ? (__ffs(bad) - 1) : 32;
+      if (valid && lane < first) {
+        const double a = ion.ch.rec[q*8 + 2], b = ion.ch.rec[q*8 + 3];
+        const double c1 = ion.ch.rec[q*8 + 4], c2 = ion.ch.rec[q*8 + 5], c3 = ion.ch.rec[q*8 + 6], cc = ion.ch.rec[q*8 + 7];
+        if (a < mdtc) mdtc = a;
+        if (b < mdtt) mdtt = b;
+        mm1 = AB2_MAX(mm1, c1); mm2 = AB2_MAX(mm2, c2); mm3 = AB2_MAX(mm3, c3);
+        mcnt += (unsigned)cc;
+        nskip++;
+      }
+      if (bad) {
+        const double tcarry = __shfl_sync(0xffffffffu, po, first);
+        const int talive = __shfl_sync(0xffffffffu, pa, first);
+        if (lane == 0) {
+          IonTask t; t.ray = (int)ray; t.ch0 = base + first; t.carry = tcarry; t.alive = talive; t.pad = 0;
+          ion.ch.tasks[atomicAdd(&scal[SC_NTASK], 1ull)] = t;
+        }
+        break;
+      }
+      prev_out = __shfl_sync(0xffffffffu, r_out, 31);
+      prev_alive = __shfl_sync(0xffffffffu, (int)((f & CH_ALIVE_OUT) != 0), 31);
+    }
   }
-}
-
-int ion_memo_count(ab2_grid* h, long long out[3])
-{
-  out[0] = out[1] = 0; out[2] = (long long)h->ion_nchunks;
-  if (!h->ion.ch.flags) return 0;
-  unsigned long long v[2] = { 0, 0 };
-  if (!ab2_check(cudaMemcpyAsync(h->d_scal + SC_MEMO_RATES, v, sizeof v, cudaMemcpyHostToDevice, h->stream), "memo stats H2D")) return -1;
-  k_ion_memo_count<<<(unsigned)((h->ion_nchunks + 255)/256), 256, 0, h->stream>>>(h->ion.ch.flags, (long)h->ion_nchunks, h->d_scal);
-  if (!ab2_check(cudaMemcpyAsync(v, h->d_scal + SC_MEMO_RATES, sizeof v, cudaMemcpyDeviceToHost, h->stream), "memo stats D2H")) return -1;
-  if (!ab2_check(cudaStreamSynchronize(h->stream), "memo stats sync")) return -1;
-  out[0] = (long long)v[0]; out[1] = (long long)v[1];
-  return 0;
+  // recorded values are non-negative, never NaN (checked when recorded): bit-pattern reductions
+  mdtc = warp_min_ordered(mdtc); mdtt = warp_min_ordered(mdtt);
+  mm1 = warp_max_ordered(mm1); mm2 = warp_max_ordered(mm2); mm3 = warp_max_ordered(mm3);
+  mcnt = __reduce_add_sync(0xffffffffu, mcnt); nskip = __reduce_add_sync(0xffffffffu, nskip);
+  if (lane == 0) { s_red[0][wib] = mdtc; s_red[1][wib] = mdtt; s_red[2][wib] = mm1; s_red[3][wib] = mm2; s_red[4][wib] = mm3; s_cnt[0][wib] = mcnt; s_cnt[1][wib] = nskip; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i=1; i<8; i++) {
+      if (s_red[0][i] < mdtc) mdtc = s_red[0][i];
+      if (s_red[1][i] < mdtt) mdtt = s_red[1][i];
+      mm1 = AB2_MAX(mm1, s_red[2][i]); mm2 = AB2_MAX(mm2, s_red[3][i]); mm3 = AB2_MAX(mm3, s_red[4][i]);
+      mcnt += s_cnt[0][i]; nskip += s_cnt[1][i];
+    }
+    if (nskip) {
+      atomic_min_double(&scal[SC_W_DTC], mdtc);
+      atomic_min_double(&scal[SC_W_DTT], mdtt);
+      atomic_max_double(&scal[SC_W_M1], mm1);
+      atomic_max_double(&scal[SC_W_M2], mm2);
+      atomic_max_double(&scal[SC_W_M3], mm3);
+      if (mcnt) atomicAdd(&scal[SC_W_CNT], (unsigned long long)mcnt);
+      atomicAdd(&scal[SC_W_NSKIP], (unsigned long long)nskip);
+    }
+  }
 }
 
 __global__ void k_bvals_ionrad(IonDev ion, int nx1, int nx2, int nx3, double flux_i)
@@ -604,6 +651,12 @@ __global__ void k_bvals_ionrad(IonDev ion, int nx1, int nx2, int nx3, double flu
   if (t >= (long)(nx2+1)*(nx3+1)) return;
   ion.edgeflux[t*(nx1+1)] = flux_i;
   ion.edgeflux_alt[t*(nx1+1)] = flux_i;
+}
+
+int ion_memo_count(ab2_grid* h, long long out[3])
+{ // what the latest k_ion_walk of this Grid found (it is queued behind every update but a call's last)
+  out[0] = h->ion_last_nskip; out[1] = h->ion_last_ntask; out[2] = (long long)h->ion_nchunks;
+  return 0;
 }
 
 int ion_bvals_ionrad(ab2_grid* h, double flux_i)
@@ -647,6 +700,8 @@ static int ion_radtransfer_impl(ab2_grid* h, int finegrid, double flux_in, doubl
   const dim3 cgrid((unsigned)((nij+127)/128), (unsigned)g.nx[2], 1);
   const long nrays = (long)g.nx[1]*g.nx[2];
   const unsigned rgrid = (unsigned)((nrays + 3)/4);
+  const long nch = h->ion.ch.nch;
+  const unsigned ugrid = (unsigned)((nrays*nch + 3)/4);            // k_ion_update: warp per (ray, chunk)
   unsigned long long* hs = h->h_scal;
 
   // one host<->device round trip of the loop scalars: reset, run `launch`, read back
@@ -661,24 +716,38 @@ static int ion_radtransfer_impl(ab2_grid* h, int finegrid, double flux_in, doubl
   auto read_scalars = [&]() -> bool { return comm_read_scalars(h) == 0; };
 
   AB2_LAUNCH(h, KID_ION_PREP, (k_ion_prep<<<cgrid, 128, 0, st>>>(g, p, h->ion)));
-  // the memo of the sparse sub-cycle never outlives a call: the hydro step in between changes every cell
-  const bool memo = h->ion.ch.flags != nullptr;
-  if (memo && !ab2_check(cudaMemsetAsync(h->ion.ch.flags, 0, h->ion_nchunks*sizeof(unsigned), st), "ion memo reset")) return -1;
+
+  // Fusing update(n) with rates(n+1) halves the host synchronisations and cross-rank exchanges per iteration but
+  // spends one discarded rates evaluation whenever check_range / dt_hydro end the loop unannounced.  Measured on B200:
+  // a gain where an iteration is launch/latency-bound (small Grids), a 2 % loss at 256^3 on one GPU.
+  bool fuse = (reduce != nullptr) || ((long)g.nx[0]*g.nx[1]*g.nx[2] < (4L<<20));
+  if (const char* env = getenv("AB2_ION_FUSE")) fuse = (atoi(env) != 0);
+  // Sparse sub-cycle (the rates / update pair only): after the first update of a call k_ion_walk lists the rays that still
+  // have chunks to evaluate; the passes of the later iterations run over that list.  The walk for iteration n+1 is queued
+  // right behind update(n), so its task count arrives with the scalars of update(n) in the same synchronisation; the
+  // list lives exactly as long as this call (the hydro step in between changes every cell).
+  const bool memo = !fuse && h->ion.ch.flags != nullptr;
+  unsigned long long* h_walk = hs + SC_W_DTC;                       // pinned: initial values of the SC_W_* block
+  int ntask = -1;                                                   // -1: full pass; else rays listed for the coming passes
+  auto queue_walk = [&]() -> bool {
+    h_walk[0] = h_walk[1] = double_to_bits(LARGE);                                      // SC_W_DTC, SC_W_DTT
+    h_walk[2] = h_walk[3] = h_walk[4] = double_to_bits(0.0);                            // SC_W_M1..3
+    h_walk[5] = h_walk[6] = h_walk[7] = 0;                                              // SC_W_CNT, SC_NTASK, SC_W_NSKIP
+    if (!ab2_check(cudaMemcpyAsync(h->d_scal + SC_W_DTC, h_walk, 8*sizeof(unsigned long long), cudaMemcpyHostToDevice, st), "ion walk scalars H2D")) return false;
+    AB2_LAUNCH(h, KID_ION_WALK, (k_ion_walk<<<(unsigned)((nrays + 7)/8 < 148*8 ? (nrays + 7)/8 : 148*8), 256, 0, st>>>(g, h->ion, flux_in, finegrid, h->ion.edgeflux, h->d_scal)));
+    return ab2_check(cudaMemcpyAsync(h_walk, h->d_scal + SC_W_DTC, 8*sizeof(unsigned long long), cudaMemcpyDeviceToHost, st), "ion walk scalars D2H");
+  };
+  const IonTask* tasks = h->ion.ch.tasks;
 
   // first iteration's rates (ph_rate_init + get_ph_rate_plane + compute_chem_rates + compute_therm_rates, :922-938)
   if (!reset_scalars()) return -1;
-  AB2_LAUNCH(h, KID_ION_RATES, (k_ion_rates<false><<<rgrid, 128, 0, st>>>(g, p, h->ion, flux_in, finegrid, 0.0, h->ion.edgeflux, h->ion.edgeflux, h->d_scal)));
+  if (memo) AB2_LAUNCH(h, KID_ION_RATES, (k_ion_rates<false,true,false><<<rgrid, 128, 0, st>>>(g, p, h->ion, flux_in, finegrid, 0.0, h->ion.edgeflux, h->ion.edgeflux, h->d_scal, nullptr, 0)));
+  else      AB2_LAUNCH(h, KID_ION_RATES, (k_ion_rates<false,false,false><<<rgrid, 128, 0, st>>>(g, p, h->ion, flux_in, finegrid, 0.0, h->ion.edgeflux, h->ion.edgeflux, h->d_scal, nullptr, 0)));
   if (!read_scalars()) return -1;
   if (hs[SC_ERR] & ERR_DT_CHEM_NEG) { ab2_set_error("[compute_chem_rates]: dt_chem < 0"); return -2; }
   double v[4] = { 0.0, 0.0, bits_to_double(hs[SC_DT_CHEM]), bits_to_double(hs[SC_DT_THERM]) };
   if (reduce) reduce(v + 2, 2, 0, ctx);
   double dt_chem = v[2], dt_therm = v[3];
-
-  // Fusing update(n) with rates(n+1) halves the host synchronisations and cross-rank exchanges per iteration but
-  // spends one discarded rates evaluation whenever check_range / dt_hydro end the loop unannounced.  Measured on B200:
-  // a gain where an iteration is launch/latency-bound (small Grids, several ranks), a 2 % loss at 256^3 on one GPU.
-  bool fuse = (reduce != nullptr) || ((long)g.nx[0]*g.nx[1]*g.nx[2] < (4L<<20));
-  if (const char* env = getenv("AB2_ION_FUSE")) fuse = (atoi(env) != 0);
 
   double grid_dt = *dt_io, dt_done = 0.0, dt = 0.0, dt_hydro = 0.0;
   int niter = 0, hydro_done = 0, nchem = 0, ntherm = 0, coarsetime_done = 0;
@@ -690,14 +759,18 @@ static int ion_radtransfer_impl(ab2_grid* h, int finegrid, double flux_in, doubl
     const bool last = hydro_done || coarsetime_done;          // the loop ends after this update whatever it finds
 
     if (!reset_scalars()) return -1;
-    // profile ids: from the second iteration on the kernels run against the memo and their time is no longer that of a full pass
-    const bool sparse = memo && niter > 0;
-    if (last || !fuse) AB2_LAUNCH(h, sparse ? KID_ION_UPDATE_MEMO : KID_ION_UPDATE, (k_ion_update<<<rgrid, 128, 0, st>>>(g, p, h->ion, dt, h->d_scal)));
-    else      AB2_LAUNCH(h, sparse ? KID_ION_FUSED_MEMO : KID_ION_FUSED, (k_ion_rates<true><<<rgrid, 128, 0, st>>>(g, p, h->ion, flux_in, finegrid, dt, h->ion.edgeflux, h->ion.edgeflux_alt, h->d_scal)));
+    if (last || !fuse) {
+      if (!memo)          AB2_LAUNCH(h, KID_ION_UPDATE, (k_ion_update<false,false><<<ugrid, 128, 0, st>>>(g, p, h->ion, dt, h->d_scal, nullptr, 0)));
+      else if (ntask < 0) AB2_LAUNCH(h, KID_ION_UPDATE, (k_ion_update<true,false><<<ugrid, 128, 0, st>>>(g, p, h->ion, dt, h->d_scal, nullptr, 0)));
+      else AB2_LAUNCH(h, KID_ION_UPDATE_MEMO, (k_ion_update<true,true><<<(unsigned)((ntask*nch + 3)/4 > 0 ? (ntask*nch + 3)/4 : 1), 128, 0, st>>>(g, p, h->ion, dt, h->d_scal, tasks, ntask)));
+      if (memo && !last && !queue_walk()) return -1;          // for the next iteration; arrives with this update's scalars
+    }
+    else      AB2_LAUNCH(h, KID_ION_FUSED, (k_ion_rates<true,false,false><<<rgrid, 128, 0, st>>>(g, p, h->ion, flux_in, finegrid, dt, h->ion.edgeflux, h->ion.edgeflux_alt, h->d_scal, nullptr, 0)));
     dt_done += dt;
     niter++;
     if (!read_scalars()) return -1;
     if (hs[SC_ERR] & ERR_DT_CHEM_NEG) { ab2_set_error("[compute_chem_rates]: dt_chem < 0"); return -2; }
+    if (memo && !last) { ntask = (int)h_walk[6]; h->ion_last_ntask = ntask; h->ion_last_nskip = (long long)h_walk[7]; }
     double mx = 0.0;
     for (int dd=0; dd<3; dd++) if (g.nx[dd] > 1) { const double x = bits_to_double(hs[SC_MAXV1+dd])/g.dx[dd]; mx = AB2_MAX(mx, x); }
     v[0] = (double)hs[SC_COUNT]; v[1] = mx; v[2] = bits_to_double(hs[SC_DT_CHEM]); v[3] = bits_to_double(hs[SC_DT_THERM]);
@@ -715,7 +788,9 @@ static int ion_radtransfer_impl(ab2_grid* h, int finegrid, double flux_in, doubl
       dt_chem = v[2]; dt_therm = v[3];
     } else {               // separate rates pass of the next iteration
       if (!reset_scalars()) return -1;
-      AB2_LAUNCH(h, memo ? KID_ION_RATES_MEMO : KID_ION_RATES, (k_ion_rates<false><<<rgrid, 128, 0, st>>>(g, p, h->ion, flux_in, finegrid, 0.0, h->ion.edgeflux, h->ion.edgeflux, h->d_scal)));
+      if (!memo)          AB2_LAUNCH(h, KID_ION_RATES, (k_ion_rates<false,false,false><<<rgrid, 128, 0, st>>>(g, p, h->ion, flux_in, finegrid, 0.0, h->ion.edgeflux, h->ion.edgeflux, h->d_scal, nullptr, 0)));
+      else if (ntask < 0) AB2_LAUNCH(h, KID_ION_RATES, (k_ion_rates<false,true,false><<<rgrid, 128, 0, st>>>(g, p, h->ion, flux_in, finegrid, 0.0, h->ion.edgeflux, h->ion.edgeflux, h->d_scal, nullptr, 0)));
+      else AB2_LAUNCH(h, KID_ION_RATES_MEMO, (k_ion_rates<false,true,true><<<(unsigned)((ntask + 3)/4 > 0 ? (ntask + 3)/4 : 1), 128, 0, st>>>(g, p, h->ion, flux_in, finegrid, 0.0, h->ion.edgeflux, h->ion.edgeflux, h->d_scal, tasks, ntask)));
       if (!read_scalars()) return -1;
       if (hs[SC_ERR] & ERR_DT_CHEM_NEG) { ab2_set_error("[compute_chem_rates]: dt_chem < 0"); return -2; }
       v[2] = bits_to_double(hs[SC_DT_CHEM]); v[3] = bits_to_double(hs[SC_DT_THERM]);

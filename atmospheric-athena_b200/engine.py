@@ -467,7 +467,7 @@ class Grid:
         self._ck(lib().ab2_set_ion_memo(self.h, int(bool(on))))
 
     def ion_memo_stats(self):
-        """(chunks the latest rates pass re-used, chunks an update would re-use now, chunks per pass): a snapshot of the records."""
+        """(chunks re-used, rays with a chunk left to evaluate, chunks per pass) as the latest scan of the records found them."""
         out = (C.c_longlong * 3)()
         self._ck(lib().ab2_ion_memo_stats(self.h, out))
         return int(out[0]), int(out[1]), int(out[2])

@@ -173,8 +173,8 @@ double ab2_ion_coarse_time(const ab2_grid* g);
  * maxima while every input of that arithmetic is bitwise unchanged (cells at the neutral floor that ionization_update's own
  * condition :575 leaves alone, same incoming flux, sign states at their fixed point) -- results are bit-identical to the full
  * re-evaluation.  on = 0 turns the memo off (every chunk evaluated every iteration; also AB2_ION_SKIP=0 in the environment at
- * ab2_ion_init).  ab2_ion_memo_stats: out[0] = chunks the latest rates pass re-used, out[1] = chunks an update
- * pass would re-use now, out[2] = chunks per pass of this Grid (a snapshot of the records, e.g. after a step). */
+ * ab2_ion_init).  ab2_ion_memo_stats, from the latest scan of the records (queued behind every update of a call but the
+ * last): out[0] = chunks re-used, out[1] = rays that still had a chunk to evaluate, out[2] = chunks per pass of this Grid. */
 int ab2_set_ion_memo(ab2_grid* g, int on);
 int ab2_ion_memo_stats(ab2_grid* g, long long out[3]);
 

@@ -158,7 +158,7 @@ def test_full_size_matches_reference_fingerprint(name):
 @pytest.mark.parametrize("memo", [1, 0])
 def test_sparse_subcycle_matches_reference_fingerprint(name, fuse, memo):
     """The sub-cycle memo (csrc/ion.cu "sparse sub-cycle": chunks of inert ambient cells re-use the previous iteration's rates
-    and reductions) changes nothing: ioniz_sphere boxes most of whose chunks are inert -- 96^3 over 12 steps and 51 sub-cycle
+    and reductions; k_ion_walk lists the rays with chunks left to evaluate) changes nothing: ioniz_sphere boxes most of whose chunks are inert -- 96^3 over 12 steps and 51 sub-cycle
     iterations, 80x48x40 (ragged last chunk) -- and an ifront box where no chunk is, with the memo on and off, through the
     rates/update pair (fuse 0) and the fused update+rates kernel (fuse 1), hash to the reference's dump: every variable,
     EdgeFlux, time, dt and the iteration count of every step."""
@@ -167,9 +167,12 @@ def test_sparse_subcycle_matches_reference_fingerprint(name, fuse, memo):
         R = run_against_fingerprint(name, setup=lambda R: R.G.set_ion_memo(memo))
     finally:
         os.environ.pop("AB2_ION_FUSE", None)
-    re_r, re_u, n = R.G.ion_memo_stats()
-    if not memo:
-        assert re_r == 0 and re_u == 0
+    nskip, ntask, n = R.G.ion_memo_stats()
+    rays = R.nx[1] * R.nx[2]
+    if not memo or fuse:                       # the memo belongs to the rates / update pair; the fused kernel evaluates everything
+        assert nskip == 0 and ntask == 0
     elif name.startswith("ioniz"):
-        # the records of the last step's last pass: the bulk of the box was re-used, and not all of it (the planet is active)
-        assert 0.5 * n < re_r < n and 0.5 * n < re_u < n, (re_r, re_u, n)
+        # the last scan of the records: the bulk of the box was re-used, and not all of it (the planet is active)
+        assert 0.5 * n < nskip < n and 0 < ntask < 0.5 * rays, (nskip, ntask, n, rays)
+    else:
+        assert nskip == 0 and ntask == rays, (nskip, ntask)   # ifront: every chunk is ionising, nothing to re-use
