@@ -719,8 +719,9 @@ static int ion_radtransfer_impl(ab2_grid* h, int finegrid, double flux_in, doubl
 
   // Fusing update(n) with rates(n+1) halves the host synchronisations and cross-rank exchanges per iteration but
   // spends one discarded rates evaluation whenever check_range / dt_hydro end the loop unannounced.  Measured on B200:
-  // a gain where an iteration is launch/latency-bound (small Grids), a 2 % loss at 256^3 on one GPU.
-  bool fuse = (reduce != nullptr) || ((long)g.nx[0]*g.nx[1]*g.nx[2] < (4L<<20));
+  // a gain where an iteration is launch/latency-bound (64^3: 0.86 vs 1.03 ms per step), a loss from 128^3 on (2.45 vs 2.26 ms),
+  // where the pair's sparse sub-cycle takes over (profiles/r2f_fuse_threshold.json).
+  bool fuse = (reduce != nullptr) || ((long)g.nx[0]*g.nx[1]*g.nx[2] < (1L<<20));
   if (const char* env = getenv("AB2_ION_FUSE")) fuse = (atoi(env) != 0);
   // Sparse sub-cycle (the rates / update pair only): after the first update of a call k_ion_walk lists the rays that still
   // have chunks to evaluate; the passes of the later iterations run over that list.  The walk for iteration n+1 is queued

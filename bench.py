@@ -301,7 +301,7 @@ GATE_CASES = {"ioniz_sphere": ["ioniz64s_k2", "blast64s_k4"], "blast": ["blast64
               "ioniz_smr": ["ioniz64s_k2"]}
 
 
-def parity_gate(workload, rank, world, local, dist, riemann=0, order=2):
+def parity_gate(workload, rank, world, local, dist, riemann=0, order=2, pair=False):
     """Runs tests/golden/<case>.json (SHA-256 fingerprints of the reference binary's own dump: 32x32x64 zones, so each of up
     to 8 x3 slabs keeps 8 layers) through driver.Run on `world` GPUs, gathers the slabs and compares every variable,
     EdgeFlux, time, dt and the sub-cycle counts.  Returns the dict that goes into the JSON line; the caller exits non-zero
@@ -313,6 +313,25 @@ def parity_gate(workload, rank, world, local, dist, riemann=0, order=2):
     out = {"cases": [], "bit_equal": True, "against": "SHA-256 fingerprints of the reference binary's dump (tests/golden/*.json)", "n_gpus": world}
     if riemann != 0 or order != 2:
         return {"cases": [], "bit_equal": None, "note": "gate fixtures exist for the shipped configuration (PLM + Roe + H-correction) only"}
+    # Grids as small as the gate's take the fused update+rates kernel by default; when the Grid about to be timed is large enough
+    # for the rates / update pair with its sparse sub-cycle (csrc/ion.cu), the gate is run through that pair too
+    force_pair = pair and "AB2_ION_FUSE" not in os.environ
+    if force_pair:
+        os.environ["AB2_ION_FUSE"] = "0"
+    out["ion_path"] = "rates/update pair + sub-cycle memo" if (pair and os.environ.get("AB2_ION_FUSE") == "0" and os.environ.get("AB2_ION_SKIP") != "0") else "as chosen by the library for the gate's Grid size"
+    try:
+        _parity_cases(out, workload, world, local, dist)
+    finally:
+        if force_pair:
+            os.environ.pop("AB2_ION_FUSE", None)
+    return out
+
+
+def _parity_cases(out, workload, world, local, dist):
+    import numpy as np
+    import torch
+    from athena_b200.driver import Run
+    from athena_b200.restart import fingerprint
     for name in GATE_CASES[workload]:
         gold = json.load(open(os.path.join(ROOT, "tests", "golden", name + ".json")))
         par = ParFile.par_open(os.path.join(DECKS, gold["deck"]))
@@ -346,7 +365,6 @@ def parity_gate(workload, rank, world, local, dist, riemann=0, order=2):
         R.G.close()
         if R.comm:
             R.comm.close()
-    return out
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -397,7 +415,9 @@ def gpu_arm(args):
 
     # the bench's own static potential (csrc/problems.c ab2_planet_pot) is re-entrant: tabulate it with several host threads
     os.environ.setdefault("AB2_GRAV_THREADS", str(max(1, min(32, (os.cpu_count() or 1) // max(1, world)))))
-    parity = parity_gate(args.workload, rank, world, local, d, args.riemann, args.order) if not args.no_parity_gate else None
+    zones_gate = args.n * args.n * (args.n // world if args.strong else args.n)
+    parity = (parity_gate(args.workload, rank, world, local, d, args.riemann, args.order, pair=zones_gate >= (1 << 20))
+              if not args.no_parity_gate else None)
     if parity is not None and parity["bit_equal"] is False:
         if rank == 0:
             print(json.dumps({"metric": "zone-updates/s per hydro+ion-RT step", "value": None, "n_gpus": world, "parity": parity,

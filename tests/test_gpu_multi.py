@@ -23,6 +23,12 @@ def test_two_gpu_run_equals_one_gpu_run():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=1200)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("MULTI_GPU_OK") == 5, r.stdout
+    # the rates / update pair with its sparse sub-cycle across two ranks (slabs this small take the fused kernel otherwise):
+    # 96^3 over 12 steps and 51 sub-cycle iterations against the reference's fingerprint, and a golden where nothing is re-usable
+    cmd = cmd[:cmd.index(os.path.join(ROOT, "tests", "multi_gpu_check.py")) + 1] + ["ioniz96_k12", "ifront32_k4"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, AB2_ION_FUSE="0"))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("MULTI_GPU_OK") == 2, r.stdout
 
 
 def test_two_gpu_smr_equals_one_gpu_and_reference():

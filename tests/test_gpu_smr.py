@@ -30,9 +30,18 @@ def test_smr_hydro_bit_exact(name):
 
 
 @pytest.mark.parametrize("name", ["ifrontsmr_k1", "ifrontsmr_k3", "ifrontsmr3_k1", "ifrontsmr3_k3", "ifrontsmredge_k3"])
-def test_smr_ion(name):
+@pytest.mark.parametrize("pair", [False, True])
+def test_smr_ion(name, pair):
+    """pair: force the rates / update pair with its sub-cycle memo and task lists (AB2_ION_FUSE=0; Grids this small take the
+    fused update+rates kernel by default), so that the fine levels' entering flux from EdgeFlux goes through k_ion_walk too."""
+    import os
     case = SmrCase(name)
-    R = gpu_run_smr(case)
+    if pair:
+        os.environ["AB2_ION_FUSE"] = "0"
+    try:
+        R = gpu_run_smr(case)
+    finally:
+        os.environ.pop("AB2_ION_FUSE", None)
     assert [r[0] for r in R.rad_log] == [int(x) for x in case.gold["rad"][:, 0]]
     assert R.time == float(case.gold["time1"]) and R.dt == float(case.gold["dt1"])
     for n, (G, lv) in enumerate(zip(R.grids, case.levels)):
