@@ -22,8 +22,22 @@ def short(name):
     base, targs = m.group(1), m.group(2) or ""
     if base in ("k_first_march", "k_correct", "k_final", "k_ppm_slope", "k_ppm_states", "k_ppm_flux"):
         return f"{base}<{targs[1:].split(',')[0].strip()}>"
-    if base == "k_ion_rates":
-        return "k_ion_rates<fused update>" if targs.startswith("<1") or "true" in targs else "k_ion_rates"
+    if base == "k_ion_rates":        # <UPDATE[, MEMO, TASKS]> (the last two since r2h: sparse sub-cycle)
+        a = [x.strip() for x in targs[1:-1].split(",")] if targs else []
+        if a and a[0] in ("1", "true", "(bool)1"):
+            return "k_ion_rates<fused update>"
+        if len(a) == 3 and a[2] in ("1", "true", "(bool)1"):
+            return "k_ion_rates[memo]"           # over k_ion_walk's task list
+        if len(a) == 3 and a[1] in ("0", "false", "(bool)0"):
+            return "k_ion_rates<no memo>"
+        return "k_ion_rates"                     # full pass (writes the chunk records when the memo is on)
+    if base == "k_ion_update":       # <MEMO, TASKS>
+        a = [x.strip() for x in targs[1:-1].split(",")] if targs else []
+        if len(a) == 2 and a[1] in ("1", "true", "(bool)1"):
+            return "k_ion_update[memo]"
+        if len(a) == 2 and a[0] in ("0", "false", "(bool)0"):
+            return "k_ion_update<no memo>"
+        return "k_ion_update"
     return base
 
 
@@ -120,10 +134,12 @@ def full_multi(tag, names):
               "pair": "bench.py default workload: k_correct3 / k_final / k_update (the default passes C, D, E since r2)",
               "default": "bench.py default workload (256^3 ioniz_sphere), unfused correct/final pair, separate ion kernels",
               "fused": "the same with AB2_HYDRO_FUSE=1 (k_cfinal) and AB2_ION_FUSE=1 (k_ion_rates<fused update>)",
+              "ion": "bench.py default workload, the ion kernels of the sparse sub-cycle: full first-iteration passes (k_ion_rates / k_ion_update, "
+                     "writing the chunk records), k_ion_walk, and the passes over its task list ([memo])",
               "ppm": "--workload blast --order 3 (PPM pass A)", "smr": "--workload ioniz_smr (shipped 5-level deck)"}
     traffic = {}
     with open(os.path.join(HERE, f"{tag}_ncu_full_table.md"), "w") as f:
-        f.write(f"# ncu --set full, {tag}\n\n`profiles/capture2.sh {tag}` on one B200: every command first ran plain (exit 0), then its launch list, "
+        f.write(f"# ncu --set full, {tag}\n\n`profiles/capture2.sh {tag}` (r2h: `profiles/capture4.sh`) on one B200: every command first ran plain (exit 0), then its launch list, "
                 "then ONE `ncu --set full --clock-control none --import-source on -k regex:^k_` capture.  Averages over the captured launches of "
                 "each kernel; times are cold-cache and serialised (compare shares, not absolutes, with bench.py's CUDA-event times).\n")
         for name in names:
