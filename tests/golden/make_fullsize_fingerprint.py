@@ -6,7 +6,7 @@ fingerprints are committed; same scheme as make_hires5_fingerprint.py):
     blast256_k2  configs[1]: blast 256^3 periodic, 2 steps        (oracle/_ref/blast)
     ifront64_k30 configs[0]: ifront 64^3 as shipped, 30 steps     (oracle/_ref/ifront)
     ioniz64s_k2 / blast64s_k4 / ifront64s_k3: 32x32x64 grids for the multi-GPU parity gate inside bench.py
-    ioniz96_k12 / ioniz80_k6: ioniz_sphere 96^3 x 12 steps and 80x48x40 x 6 steps for the sparse sub-cycle
+    ioniz96_k12 / ioniz80_k6 / ioniz1100_k4: ioniz_sphere 96^3 x 12 steps, 80x48x40 x 6 steps, 1100x12x10 x 4 steps for the sparse sub-cycle
 
 A bit-identical run reproduces every hash (tests/test_gpu_longrun.py).   python tests/golden/make_fullsize_fingerprint.py
 """
@@ -36,6 +36,8 @@ CASES = {
     # iterations that a wrongly re-used chunk would show (Nx1 = 96: three chunks per ray; Nx1 = 80: a ragged last chunk)
     "ioniz96_k12": ("ioniz_sphere", "ioniz_sphere.athinput", 12, ["job/num_domains=1", "domain1/Nx1=96", "domain1/Nx2=96", "domain1/Nx3=96"]),
     "ioniz80_k6": ("ioniz_sphere", "ioniz_sphere.athinput", 6, ["job/num_domains=1", "domain1/Nx1=80", "domain1/Nx2=48", "domain1/Nx3=40"]),
+    # more than 32 chunks per ray (k_ion_walk scans the records of a ray 32 at a time)
+    "ioniz1100_k4": ("ioniz_sphere", "ioniz_sphere.athinput", 4, ["job/num_domains=1", "domain1/Nx1=1100", "domain1/Nx2=12", "domain1/Nx3=10"]),
 }
 
 

@@ -197,11 +197,19 @@ def test_hydro_bit_exact_vs_reference(name):
 
 @pytest.mark.parametrize("name", ["ifront32_k1", "ifront32_k4", "ioniz24_k1", "ioniz24_k3", "ifront32hllc_k4", "ifront32ppm_k4",
                                   "ifronttiny_k3", "ionizodd_k1"])
-def test_ion_hydro_bit_exact_vs_reference(name):
+@pytest.mark.parametrize("pair", [False, True])
+def test_ion_hydro_bit_exact_vs_reference(name, pair):
     """stricter than north_star asks: with the host libm's exp/pow restated on the device (csrc/glibc_math.cuh) the
-    hydro + ion-RT step reproduces the reference's dump to the last bit, EdgeFlux and sub-cycle counts included"""
+    hydro + ion-RT step reproduces the reference's dump to the last bit, EdgeFlux and sub-cycle counts included --
+    through the fused update+rates kernel Grids this small take by default, and (pair) through the rates / update pair with
+    its sparse sub-cycle (k_ion_walk and the task-list passes; rows shorter than one 32-cell chunk, odd extents)"""
     case = Case(name)
-    R = gpu_run(case)
+    if pair:
+        os.environ["AB2_ION_FUSE"] = "0"
+    try:
+        R = gpu_run(case)
+    finally:
+        os.environ.pop("AB2_ION_FUSE", None)
     out = R.G.download_active()
     assert [tuple(r[:3]) for r in R.rad_log] == [(int(a), int(b), int(c)) for a, b, c in case.gold["rad"][:, :3]]
     assert R.time == float(case.gold["time1"]) and R.dt == float(case.gold["dt1"])
