@@ -80,6 +80,7 @@ struct IonParDev {
 #define CH_UINERT    2u      // the update after those rates left E and s of every cell of the chunk untouched (condition false, no floor fired)
 #define CH_ALIVE_IN  4u      // the ray was still uncut where it entered the chunk
 #define CH_ALIVE_OUT 8u      // ... where it left it
+#define CH_STAMP_SHIFT 4     // flags >> 4: number of the rates pass (1, 2, ... within a call) that last EVALUATED the chunk
 struct IonTask { int ray, ch0; double carry; int alive, pad; };   // evaluate `ray` from chunk ch0 on, entered with this flux / cut state
 struct IonChunks {
   unsigned* flags;            // NULL: memo off (AB2_ION_SKIP=0), every chunk is evaluated in every iteration

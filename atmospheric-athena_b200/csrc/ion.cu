@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(128) k_ion_prep(GridDev g, IonParDev p, IonDev
 // ionization_update (:565-590) + floors (:970-971) + check_range (:206-283) + compute_dt_hydro (:593-678) for ONE cell:
 // (E,s) -> (Eo,so), whether the cell counts for check_range, and |v_d| + a per direction.  Pure in its inputs.
 // ---------------------------------------------------------------------------------------------------
-struct CellUpd { double E, s, x1, x2, x3; unsigned count; bool applied; };
+struct CellUpd { double E, s, x1, x2, x3, nHdot, edot; unsigned count; bool applied; };
 
 template <bool FAST>
 __device__ __forceinline__ CellUpd cell_update(const GridDev& g, const IonParDev& p, const IonDev& ion, long c, double dt,
@@ -167,8 +167,10 @@ __device__ __forceinline__ CellUpd cell_update(const GridDev& g, const IonParDev
     double d_nlim = d*IONFRACFLOOR;
     d_nlim = d_nlim < p.d_nlo ? d_nlim : p.d_nlo;
     u.applied = (nHdot > 0) || (s > 1.0001*d_nlim);
+    u.nHdot = nHdot; u.edot = 0.0;
     if (u.applied) {
-      E += ion.edot[c] * dt;
+      u.edot = ion.edot[c];
+      E += u.edot * dt;
       s += nHdot * dt * p.m_H;
     }
     // floors (apply_temp_floor :70-136, apply_neutral_floor :140-157), keeping the cell's chemistry state: when no
@@ -343,7 +345,7 @@ __device__ __forceinline__ double scal_as_double(const unsigned long long* scal,
 template <bool UPDATE, bool MEMO, bool TASKS>
 __global__ void __launch_bounds__(128, AB2_LB_ION_RATES) k_ion_rates(GridDev g, IonParDev p, IonDev ion, double flux_in_root, int finegrid, double dt_upd,
                                                    const double* ef_in_base, double* ef_out_base, unsigned long long* scal,
-                                                   const IonTask* tasks, int ntask)
+                                                   const IonTask* tasks, int ntask, unsigned stamp)
 {
   static_assert(!(UPDATE && (MEMO || TASKS)) && !(TASKS && !MEMO), "the memo belongs to the rates / update pair");
   __shared__ double s_etau[128];
@@ -384,7 +386,22 @@ __global__ void __launch_bounds__(128, AB2_LB_ION_RATES) k_ion_rates(GridDev g, 
     const int ii = c0 + lane;
     const bool valid = ii < nx1;
     const long c = row + (valid ? ii : nx1-1);
-    unsigned fl = alive ? CH_ALIVE_IN : 0u;           // the record's flags, rebuilt by every evaluation
+    if (TASKS) {
+      // a chunk further down a listed ray may still be re-usable (the neutral, shielded inside of the planet behind its
+      // ionisation front): same test as k_ion_walk's, with the ray's actual state in hand
+      const unsigned f = ion.ch.flags[q];
+      if ((f & CH_RFIX) && (ion.ch.uflags[q] & CH_UINERT) && (((f & CH_ALIVE_IN) != 0) == alive)) {
+        const double r_in = ion.ch.rec[q*8 + 0], r_out = ion.ch.rec[q*8 + 1], r_dtc = ion.ch.rec[q*8 + 2], r_dtt = ion.ch.rec[q*8 + 3];
+        if (!alive || same_bits(carry, r_in)) {
+          if (r_dtc < dt_chem_min) dt_chem_min = r_dtc;
+          if (r_dtt < dt_therm_min) dt_therm_min = r_dtt;
+          carry = r_out;
+          alive = (f & CH_ALIVE_OUT) != 0;
+          continue;                                   // flags keep their old stamp: k_ion_update re-uses the chunk too
+        }
+      }
+    }
+    unsigned fl = (stamp << CH_STAMP_SHIFT) | (alive ? CH_ALIVE_IN : 0u);     // the record's flags, rebuilt by every evaluation
     if (memo && lane == 0) ion.ch.rec[q*8 + 0] = carry;
     const double d = g.U[0][c], M1 = g.U[1][c], M2 = g.U[2][c], M3 = g.U[3][c];
     double E = g.U[4][c], s = g.U[5][c];
@@ -443,11 +460,9 @@ __global__ void __launch_bounds__(128, AB2_LB_ION_RATES) k_ion_rates(GridDev g, 
       if (r.dt_chem < 0) err |= ERR_DT_CHEM_NEG;
       if (r.dt_therm < dt_therm_min) dt_therm_min = r.dt_therm;
       if (memo) {
-        double d_nlim = d*IONFRACFLOOR;
-        d_nlim = d_nlim < p.d_nlo ? d_nlim : p.d_nlo;
-        // sign_count 0 after the transition = fixed point (last_sign is always the current sign); the update's condition on
-        // the stored (damped) rate is false; the dt limits are plain non-negative numbers
-        keep = ((r.sign_state >> 2) == 0) && !((r.nHdot > 0) || (s > 1.0001*d_nlim)) && ordered_bits(r.dt_chem) && ordered_bits(r.dt_therm);
+        // sign_count 0 after the transition = fixed point (last_sign is always the current sign); the dt limits are plain
+        // non-negative numbers.  Whether the update leaves the cells alone is k_ion_update's finding (CH_UINERT).
+        keep = ((r.sign_state >> 2) == 0) && ordered_bits(r.dt_chem) && ordered_bits(r.dt_therm);
         cdtc = r.dt_chem; cdtt = r.dt_therm;
       }
     }
@@ -496,9 +511,10 @@ __global__ void __launch_bounds__(128, AB2_LB_ION_RATES) k_ion_rates(GridDev g, 
 // tasks != NULL (sparse pass): warp w takes ray tasks[w].ray and the chunks from tasks[w].ch0 on; the first warp folds in the
 // count and maxima k_ion_walk deposited for the re-used chunks.
 // ---------------------------------------------------------------------------------------------------
+// dt_max: no later update of this call can use a longer sub-step (what is left of the hydro step / coarse time).
 template <bool MEMO, bool TASKS>
 __global__ void __launch_bounds__(128, AB2_LB_ION_UPDATE) k_ion_update(GridDev g, IonParDev p, IonDev ion, double dt, unsigned long long* scal,
-                                                                      const IonTask* tasks, int ntask)
+                                                                      const IonTask* tasks, int ntask, unsigned stamp, double dt_max)
 {
   static_assert(!(TASKS && !MEMO), "the task list belongs to the memo");
   const int lane = threadIdx.x & 31;
@@ -523,6 +539,21 @@ __global__ void __launch_bounds__(128, AB2_LB_ION_UPDATE) k_ion_update(GridDev g
   const int ii = ch*32 + lane;
   const bool valid = ii < g.nx[0];
   const long c = (long)(kk+NG)*g.st[2] + (long)(jj+NG)*g.st[1] + NG + (valid ? ii : g.nx[0]-1);
+  if (TASKS) {
+    // the rates pass of this iteration re-used the chunk (its flags still carry an older stamp, which it only does for a chunk
+    // the previous update left alone): rates unchanged, cells unchanged, sub-step not longer -> this update changes nothing
+    const long q = ray*ion.ch.nch + ch;
+    if ((ion.ch.flags[q] >> CH_STAMP_SHIFT) != stamp) {
+      if (lane == 0) {
+        const unsigned long long cc = (unsigned long long)ion.ch.rec[q*8 + 7];
+        if (cc) atomicAdd(&scal[SC_COUNT], cc);
+        atomic_max_double(&scal[SC_MAXV1], ion.ch.rec[q*8 + 4]);
+        atomic_max_double(&scal[SC_MAXV2], ion.ch.rec[q*8 + 5]);
+        atomic_max_double(&scal[SC_MAXV3], ion.ch.rec[q*8 + 6]);
+      }
+      return;
+    }
+  }
   CellUpd u; u.x1 = u.x2 = u.x3 = 0.0; u.count = 0; u.applied = false;
   bool inert = true;
   if (valid) {
@@ -530,13 +561,17 @@ __global__ void __launch_bounds__(128, AB2_LB_ION_UPDATE) k_ion_update(GridDev g
     const double E = g.U[4][c], s = g.U[5][c];
     ION_GUARDED(u = cell_update(g, p, ion, c, dt, d, M1, M2, M3, E, s, ar));
     g.U[4][c] = u.E; g.U[5][c] = u.s;
-    inert = !u.applied && same_bits(u.E, E) && same_bits(u.s, s) && ordered_bits(u.x1) && ordered_bits(u.x2) && ordered_bits(u.x3);
+    // Inert: E and s came out with the bits they went in with (no floor fired), and would for ANY sub-step up to dt_max --
+    // either the update's condition is false, or its increments round away even at dt_max (rounding is monotone, so they do
+    // for every shorter sub-step: fl(E + fl(edot dt)) lies between E and fl(E + fl(edot dt_max)) = E; neutral, shielded gas).
+    inert = same_bits(u.E, E) && same_bits(u.s, s) && ordered_bits(u.x1) && ordered_bits(u.x2) && ordered_bits(u.x3)
+            && (!u.applied || (same_bits(E + u.edot * dt_max, E) && same_bits(s + u.nHdot * dt_max * p.m_H, s)));
   }
   unsigned long long count = u.count;
   double m1 = u.x1, m2 = u.x2, m3 = u.x3;           // >= 0 or NaN; a NaN never wins below (as in the running MAX from 0.0)
   if (MEMO) {
-    // the chunk's record: no cell met the update's condition and no floor fired -> with unchanged rates the next update
-    // of this chunk changes nothing either and contributes this count and these maxima
+    // the chunk's record: with unchanged rates the next update of this chunk changes nothing either and contributes this
+    // count and these maxima
     const long q = ray*ion.ch.nch + ch;
     inert = __all_sync(0xffffffffu, inert);
     if (inert) {
@@ -742,8 +777,8 @@ static int ion_radtransfer_impl(ab2_grid* h, int finegrid, double flux_in, doubl
 
   // first iteration's rates (ph_rate_init + get_ph_rate_plane + compute_chem_rates + compute_therm_rates, :922-938)
   if (!reset_scalars()) return -1;
-  if (memo) AB2_LAUNCH(h, KID_ION_RATES, (k_ion_rates<false,true,false><<<rgrid, 128, 0, st>>>(g, p, h->ion, flux_in, finegrid, 0.0, h->ion.edgeflux, h->ion.edgeflux, h->d_scal, nullptr, 0)));
-  else      AB2_LAUNCH(h, KID_ION_RATES, (k_ion_rates<false,false,false><<<rgrid, 128, 0, st>>>(g, p, h->ion, flux_in, finegrid, 0.0, h->ion.edgeflux, h->ion.edgeflux, h->d_scal, nullptr, 0)));
+  if (memo) AB2_LAUNCH(h, KID_ION_RATES, (k_ion_rates<false,true,false><<<rgrid, 128, 0, st>>>(g, p, h->ion, flux_in, finegrid, 0.0, h->ion.edgeflux, h->ion.edgeflux, h->d_scal, nullptr, 0, 1u)));
+  else      AB2_LAUNCH(h, KID_ION_RATES, (k_ion_rates<false,false,false><<<rgrid, 128, 0, st>>>(g, p, h->ion, flux_in, finegrid, 0.0, h->ion.edgeflux, h->ion.edgeflux, h->d_scal, nullptr, 0, 1u)));
   if (!read_scalars()) return -1;
   if (hs[SC_ERR] & ERR_DT_CHEM_NEG) { ab2_set_error("[compute_chem_rates]: dt_chem < 0"); return -2; }
   double v[4] = { 0.0, 0.0, bits_to_double(hs[SC_DT_CHEM]), bits_to_double(hs[SC_DT_THERM]) };
@@ -761,12 +796,14 @@ static int ion_radtransfer_impl(ab2_grid* h, int finegrid, double flux_in, doubl
 
     if (!reset_scalars()) return -1;
     if (last || !fuse) {
-      if (!memo)          AB2_LAUNCH(h, KID_ION_UPDATE, (k_ion_update<false,false><<<ugrid, 128, 0, st>>>(g, p, h->ion, dt, h->d_scal, nullptr, 0)));
-      else if (ntask < 0) AB2_LAUNCH(h, KID_ION_UPDATE, (k_ion_update<true,false><<<ugrid, 128, 0, st>>>(g, p, h->ion, dt, h->d_scal, nullptr, 0)));
-      else AB2_LAUNCH(h, KID_ION_UPDATE_MEMO, (k_ion_update<true,true><<<(unsigned)((ntask*nch + 3)/4 > 0 ? (ntask*nch + 3)/4 : 1), 128, 0, st>>>(g, p, h->ion, dt, h->d_scal, tasks, ntask)));
+      const unsigned stamp = (unsigned)(niter + 1);                          // of the rates pass this update follows
+      const double dt_left = (finegrid ? tcoarse : grid_dt) - dt_done;       // >= every sub-step still to come in this call
+      if (!memo)          AB2_LAUNCH(h, KID_ION_UPDATE, (k_ion_update<false,false><<<ugrid, 128, 0, st>>>(g, p, h->ion, dt, h->d_scal, nullptr, 0, stamp, dt_left)));
+      else if (ntask < 0) AB2_LAUNCH(h, KID_ION_UPDATE, (k_ion_update<true,false><<<ugrid, 128, 0, st>>>(g, p, h->ion, dt, h->d_scal, nullptr, 0, stamp, dt_left)));
+      else AB2_LAUNCH(h, KID_ION_UPDATE_MEMO, (k_ion_update<true,true><<<(unsigned)((ntask*nch + 3)/4 > 0 ? (ntask*nch + 3)/4 : 1), 128, 0, st>>>(g, p, h->ion, dt, h->d_scal, tasks, ntask, stamp, dt_left)));
       if (memo && !last && !queue_walk()) return -1;          // for the next iteration; arrives with this update's scalars
     }
-    else      AB2_LAUNCH(h, KID_ION_FUSED, (k_ion_rates<true,false,false><<<rgrid, 128, 0, st>>>(g, p, h->ion, flux_in, finegrid, dt, h->ion.edgeflux, h->ion.edgeflux_alt, h->d_scal, nullptr, 0)));
+    else      AB2_LAUNCH(h, KID_ION_FUSED, (k_ion_rates<true,false,false><<<rgrid, 128, 0, st>>>(g, p, h->ion, flux_in, finegrid, dt, h->ion.edgeflux, h->ion.edgeflux_alt, h->d_scal, nullptr, 0, 0u)));
     dt_done += dt;
     niter++;
     if (!read_scalars()) return -1;
@@ -789,9 +826,10 @@ static int ion_radtransfer_impl(ab2_grid* h, int finegrid, double flux_in, doubl
       dt_chem = v[2]; dt_therm = v[3];
     } else {               // separate rates pass of the next iteration
       if (!reset_scalars()) return -1;
-      if (!memo)          AB2_LAUNCH(h, KID_ION_RATES, (k_ion_rates<false,false,false><<<rgrid, 128, 0, st>>>(g, p, h->ion, flux_in, finegrid, 0.0, h->ion.edgeflux, h->ion.edgeflux, h->d_scal, nullptr, 0)));
-      else if (ntask < 0) AB2_LAUNCH(h, KID_ION_RATES, (k_ion_rates<false,true,false><<<rgrid, 128, 0, st>>>(g, p, h->ion, flux_in, finegrid, 0.0, h->ion.edgeflux, h->ion.edgeflux, h->d_scal, nullptr, 0)));
-      else AB2_LAUNCH(h, KID_ION_RATES_MEMO, (k_ion_rates<false,true,true><<<(unsigned)((ntask + 3)/4 > 0 ? (ntask + 3)/4 : 1), 128, 0, st>>>(g, p, h->ion, flux_in, finegrid, 0.0, h->ion.edgeflux, h->ion.edgeflux, h->d_scal, tasks, ntask)));
+      const unsigned stamp = (unsigned)(niter + 1);                          // rates pass of iteration niter+1
+      if (!memo)          AB2_LAUNCH(h, KID_ION_RATES, (k_ion_rates<false,false,false><<<rgrid, 128, 0, st>>>(g, p, h->ion, flux_in, finegrid, 0.0, h->ion.edgeflux, h->ion.edgeflux, h->d_scal, nullptr, 0, stamp)));
+      else if (ntask < 0) AB2_LAUNCH(h, KID_ION_RATES, (k_ion_rates<false,true,false><<<rgrid, 128, 0, st>>>(g, p, h->ion, flux_in, finegrid, 0.0, h->ion.edgeflux, h->ion.edgeflux, h->d_scal, nullptr, 0, stamp)));
+      else AB2_LAUNCH(h, KID_ION_RATES_MEMO, (k_ion_rates<false,true,true><<<(unsigned)((ntask + 3)/4 > 0 ? (ntask + 3)/4 : 1), 128, 0, st>>>(g, p, h->ion, flux_in, finegrid, 0.0, h->ion.edgeflux, h->ion.edgeflux, h->d_scal, tasks, ntask, stamp)));
       if (!read_scalars()) return -1;
       if (hs[SC_ERR] & ERR_DT_CHEM_NEG) { ab2_set_error("[compute_chem_rates]: dt_chem < 0"); return -2; }
       v[2] = bits_to_double(hs[SC_DT_CHEM]); v[3] = bits_to_double(hs[SC_DT_THERM]);

@@ -736,6 +736,9 @@ def smr_arm(args):
             time.sleep(0.05)
     l0 = sum(G.kernel_launches for G in grids)
     it0 = len(R.rad_log)
+    for G in grids:
+        G.profile_enable(True)
+        G.profile_read(reset=True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     w0 = time.time()
@@ -747,6 +750,18 @@ def smr_arm(args):
     w1 = time.time()
     ms = e0.elapsed_time(e1)
     launches = sum(G.kernel_launches for G in grids) - l0
+    # per level: zones, sub-cycle iterations per step, kernel time per step (CUDA events inside the library), memo snapshot
+    per_level = []
+    nlev_here = len(grids)
+    for n, G in enumerate(grids):
+        prof = G.profile_read(reset=True)
+        G.profile_enable(False)
+        ion = {k: round(v[0] / args.steps, 3) for k, v in prof.items() if k.startswith("k_ion")}
+        lv_its = [r[0] for r in R.rad_log[it0:]][n::nlev_here] if world == 1 else []
+        nskip, ntask, nchunk = G.ion_memo_stats()
+        per_level.append({"zones": G.nx[0] * G.nx[1] * G.nx[2], "iterations_per_step": round(sum(lv_its) / max(1, len(lv_its)), 2) if lv_its else None,
+                          "ion_ms_per_step": ion,      # (the levels' hydro kernels overlap on their own streams: no per-level split)
+                          "memo": {"chunks_reused_frac": round(nskip / max(1, nchunk), 4), "rays_listed_frac": round(ntask / max(1, G.nx[1] * G.nx[2]), 4)}})
     if world > 1:
         t = torch.tensor([ms, float(launches)], dtype=torch.float64, device="cuda")
         dist.all_reduce(t[:1], op=dist.ReduceOp.MAX)
@@ -765,6 +780,7 @@ def smr_arm(args):
                 "config": {"workload": f"configs[3] ioniz_sphere SMR, shipped 5-level deck {zones_total} zones, steps {args.warmup}..{args.warmup + args.steps} from t=0",
                            "parallelism": f"x3 cut planes at root layers {cuts}", "ion_iterations_per_level_step": round(n_iter, 2),
                            "l2": "working set >> L2, no flush needed", "setup_s": round(t_setup, 1)},
+                "per_level": per_level,
                 "parity": parity, "e2e": None, "gpu_launches": int(launches), "clocks": clocks,
                 "roofline": {"bound": "hbm", "kernel": "whole step", "achieved": round(value / world * b_alg / 1e9, 1), "peak": peak, "unit": "GB/s",
                              "frac": round(value / world * b_alg / 1e9 / peak, 4), "traffic": None, "peak_source": peak_src,
