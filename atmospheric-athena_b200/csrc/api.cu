@@ -60,7 +60,7 @@ static const char* KERNEL_NAMES[KID_N] = {
   "k_correct<0>", "k_correct<1>", "k_correct<2>", "k_final<0>", "k_final<1>", "k_final<2>", "k_update",
   "k_apply_fixed", "k_ion_prep", "k_ion_rates", "k_ion_update", "k_bvals_ionrad", "k_transpose",
   "k_smr_restrict", "k_smr_flux_correct", "k_smr_prolongate", "k_ion_rates<fused update>", "k_cfinal", "k_correct3",
-  "k_ion_rates[memo]", "k_ion_update[memo]", "k_ion_walk" };
+  "k_ion_rates[memo]", "k_ion_update[memo]", "k_ion_walk", "k_ion_rates[first]" };
 
 cudaEvent_t ab2_prof_event(ab2_grid* h)
 {

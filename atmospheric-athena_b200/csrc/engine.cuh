@@ -107,7 +107,7 @@ enum {
   KID_CORRECT_X1, KID_CORRECT_X2, KID_CORRECT_X3, KID_FINAL_X1, KID_FINAL_X2, KID_FINAL_X3, KID_UPDATE,
   KID_APPLY_FIXED, KID_ION_PREP, KID_ION_RATES, KID_ION_UPDATE, KID_BVALS_IONRAD, KID_TRANSPOSE,
   KID_SMR_RESTRICT, KID_SMR_FLUXCORR, KID_SMR_PROLONG, KID_ION_FUSED, KID_CFINAL, KID_CORRECT3,
-  KID_ION_RATES_MEMO, KID_ION_UPDATE_MEMO, KID_ION_WALK, KID_N
+  KID_ION_RATES_MEMO, KID_ION_UPDATE_MEMO, KID_ION_WALK, KID_ION_RATES_FIRST, KID_N
 };
 struct ProfPending { int id; cudaEvent_t a, b; };
 

@@ -73,6 +73,7 @@ __device__ __forceinline__ void atomic_max_double(unsigned long long* addr, doub
 }
 
 struct CellChem { double n_H, n_Hplus, n_e, x, ke, e_thermal, T; };
+__device__ __forceinline__ bool same_bits_h(double a, double b) { return __double_as_longlong(a) == __double_as_longlong(b); }
 
 // The kinetic energy keeps the plain operator: its numerator M.M is below the fast path's range (2^-120) wherever the
 // gas is nearly at rest in CGS units, and those cells would all take the guarded block's second pass.
@@ -116,6 +117,29 @@ __device__ __forceinline__ void floors(const IonParDev& p, double Gamma_1, doubl
   d_nlim = d_nlim < p.d_nlo ? d_nlim : p.d_nlo;
   if (s < d_nlim) so = d_nlim;
   else if (s > d) so = d;
+}
+
+// The same two floors for a caller that wants the chemistry state of the floored cell as well (the first rates pass of a
+// call, which does ion_radtransfer_3d's prologue on the fly): cs is the state of (Eo,so) on return.
+template <bool FAST>
+__device__ __forceinline__ void floors_state(const IonParDev& p, double Gamma_1, double d, double M1, double M2, double M3, double E, double s,
+                                             double& Eo, double& so, CellChem& cs, Arith<FAST>& ar)
+{
+  cs = chem_state(p, Gamma_1, d, M1, M2, M3, E, s, ar);
+  Eo = E; so = s;
+  if (cs.T < p.tfloor) {
+    const double e_sp = ar.div(p.tfloor * p.k_B, (cs.x*0.5*p.m_H+(1.0-cs.x)*p.mu) * Gamma_1);
+    Eo = cs.ke + e_sp * d;
+  }
+  if ((cs.T > p.tceil) && (p.tceil > 0)) {
+    const double e_sp = ar.div(p.tceil * p.k_B, (cs.x*0.5*p.m_H+(1.0-cs.x)*p.mu) * Gamma_1);
+    Eo = cs.ke + e_sp * d;
+  }
+  double d_nlim = d*IONFRACFLOOR;
+  d_nlim = d_nlim < p.d_nlo ? d_nlim : p.d_nlo;
+  if (s < d_nlim) so = d_nlim;
+  else if (s > d) so = d;
+  if (!same_bits_h(Eo, E) || !same_bits_h(so, s)) cs = chem_state(p, Gamma_1, d, M1, M2, M3, Eo, so, ar);
 }
 
 // thread -> active cell
@@ -220,11 +244,11 @@ struct CellRates { double nHdot, edot, dt_chem, dt_therm; int sign_state; };
 
 template <bool FAST>
 __device__ __forceinline__ CellRates cell_rates(const GridDev& g, const IonParDev& p, double d, double M1, double M2, double M3,
-                                                double E, double s, double ph, int st, Arith<FAST>& ar)
+                                                double E, double s, double ph, int st, Arith<FAST>& ar, const CellChem* have = nullptr)
 {
       CellRates r;
-      // --- chemistry (ionrad_3d.c:313-391)
-      const CellChem cs = chem_state(p, g.Gamma_1, d, M1, M2, M3, E, s, ar);
+      // --- chemistry (ionrad_3d.c:313-391); `have`: the same state, already evaluated on these very E, s by the caller
+      const CellChem cs = have ? *have : chem_state(p, g.Gamma_1, d, M1, M2, M3, E, s, ar);
       double T = cs.T;
       if (T < p.tfloor) T = p.tfloor;
       double nHdot = 2.59e-13*gl_pow(ar.div(T, 1.0e4), -0.7) * p.time_unit * cs.n_e * cs.n_Hplus - ph * cs.n_H;
@@ -342,12 +366,15 @@ __device__ __forceinline__ double scal_as_double(const unsigned long long* scal,
 // dt limits k_ion_walk deposited for the re-used chunks into the pass scalars.
 // MEMO: the pass writes the chunk records; TASKS: it runs over k_ion_walk's list (both compile-time, so that the full pass
 // without the memo is the plain kernel).
-template <bool UPDATE, bool MEMO, bool TASKS>
+// FIRST: the first rates pass of a call also does the call's prologue (ionrad_3d.c:896-905: temperature and neutral floors,
+// save_energy_and_x, sign states reset) on the cells as they stream through, instead of a k_ion_prep pass before it.
+template <bool UPDATE, bool MEMO, bool TASKS, bool FIRST = false>
 __global__ void __launch_bounds__(128, AB2_LB_ION_RATES) k_ion_rates(GridDev g, IonParDev p, IonDev ion, double flux_in_root, int finegrid, double dt_upd,
                                                    const double* ef_in_base, double* ef_out_base, unsigned long long* scal,
                                                    const IonTask* tasks, int ntask, unsigned stamp)
 {
   static_assert(!(UPDATE && (MEMO || TASKS)) && !(TASKS && !MEMO), "the memo belongs to the rates / update pair");
+  static_assert(!(FIRST && (UPDATE || TASKS)), "the prologue rides on the first, full rates pass");
   __shared__ double s_etau[128];
   const int lane = threadIdx.x & 31;
   const long w = (long)blockIdx.x*(blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -405,6 +432,17 @@ __global__ void __launch_bounds__(128, AB2_LB_ION_RATES) k_ion_rates(GridDev g, 
     if (memo && lane == 0) ion.ch.rec[q*8 + 0] = carry;
     const double d = g.U[0][c], M1 = g.U[1][c], M2 = g.U[2][c], M3 = g.U[3][c];
     double E = g.U[4][c], s = g.U[5][c];
+    CellChem cs1;                                      // FIRST: chemistry state of the floored cell, handed on to cell_rates
+    if (FIRST && valid) {
+      double Ef, sf;
+      ION_GUARDED(floors_state(p, g.Gamma_1, d, M1, M2, M3, E, s, Ef, sf, cs1, ar));
+      if (!same_bits_h(Ef, E)) g.U[4][c] = Ef;
+      if (!same_bits_h(sf, s)) g.U[5][c] = sf;
+      E = Ef; s = sf;
+      ion.e_init[c] = E;                               // save_energy_and_x (ionrad_3d.c:162-201)
+      ion.e_th_init[c] = cs1.e_thermal;
+      ion.x_init[c] = cs1.x;
+    }
     if (UPDATE && valid) {
       CellUpd u;
       ION_GUARDED(u = cell_update(g, p, ion, c, dt_upd, d, M1, M2, M3, E, s, ar));
@@ -451,8 +489,8 @@ __global__ void __launch_bounds__(128, AB2_LB_ION_RATES) k_ion_rates(GridDev g, 
     double cdtc = LARGE, cdtt = LARGE;
     if (valid) {
       CellRates r;
-      const int st = ion.sign_state[c];
-      ION_GUARDED(r = cell_rates(g, p, d, M1, M2, M3, E, s, ph, st, ar));
+      const int st = FIRST ? 1 : ion.sign_state[c];     // 1 = last_sign 0, sign_count 0
+      ION_GUARDED(r = cell_rates(g, p, d, M1, M2, M3, E, s, ph, st, ar, FIRST ? &cs1 : nullptr));
       ion.sign_state[c] = r.sign_state;
       ion.nHdot[c] = r.nHdot;
       ion.edot[c] = r.edot;
@@ -750,7 +788,9 @@ static int ion_radtransfer_impl(ab2_grid* h, int finegrid, double flux_in, doubl
   // combined (the MPI_Allreduce sites of ionrad_3d.c:275,399,554,672 in ONE exchange, comm.cu)
   auto read_scalars = [&]() -> bool { return comm_read_scalars(h) == 0; };
 
-  AB2_LAUNCH(h, KID_ION_PREP, (k_ion_prep<<<cgrid, 128, 0, st>>>(g, p, h->ion)));
+  // the call's prologue (floors, save_energy_and_x): on the fly in the first rates pass, or (AB2_ION_PREP=1) as its own pass
+  static const bool prep_pass = getenv("AB2_ION_PREP") && atoi(getenv("AB2_ION_PREP")) != 0;
+  if (prep_pass) AB2_LAUNCH(h, KID_ION_PREP, (k_ion_prep<<<cgrid, 128, 0, st>>>(g, p, h->ion)));
 
   // Fusing update(n) with rates(n+1) halves the host synchronisations and cross-rank exchanges per iteration but
   // spends one discarded rates evaluation whenever check_range / dt_hydro end the loop unannounced.  Measured on B200:
@@ -777,8 +817,10 @@ static int ion_radtransfer_impl(ab2_grid* h, int finegrid, double flux_in, doubl
 
   // first iteration's rates (ph_rate_init + get_ph_rate_plane + compute_chem_rates + compute_therm_rates, :922-938)
   if (!reset_scalars()) return -1;
-  if (memo) AB2_LAUNCH(h, KID_ION_RATES, (k_ion_rates<false,true,false><<<rgrid, 128, 0, st>>>(g, p, h->ion, flux_in, finegrid, 0.0, h->ion.edgeflux, h->ion.edgeflux, h->d_scal, nullptr, 0, 1u)));
-  else      AB2_LAUNCH(h, KID_ION_RATES, (k_ion_rates<false,false,false><<<rgrid, 128, 0, st>>>(g, p, h->ion, flux_in, finegrid, 0.0, h->ion.edgeflux, h->ion.edgeflux, h->d_scal, nullptr, 0, 1u)));
+#define AB2_RATES1(M, F) AB2_LAUNCH(h, (F) ? KID_ION_RATES_FIRST : KID_ION_RATES, (k_ion_rates<false,M,false,F><<<rgrid, 128, 0, st>>>(g, p, h->ion, flux_in, finegrid, 0.0, h->ion.edgeflux, h->ion.edgeflux, h->d_scal, nullptr, 0, 1u)))
+  if (memo) { if (prep_pass) AB2_RATES1(true, false); else AB2_RATES1(true, true); }
+  else      { if (prep_pass) AB2_RATES1(false, false); else AB2_RATES1(false, true); }
+#undef AB2_RATES1
   if (!read_scalars()) return -1;
   if (hs[SC_ERR] & ERR_DT_CHEM_NEG) { ab2_set_error("[compute_chem_rates]: dt_chem < 0"); return -2; }
   double v[4] = { 0.0, 0.0, bits_to_double(hs[SC_DT_CHEM]), bits_to_double(hs[SC_DT_THERM]) };

@@ -26,9 +26,11 @@ def short(name):
         a = [x.strip() for x in targs[1:-1].split(",")] if targs else []
         if a and a[0] in ("1", "true", "(bool)1"):
             return "k_ion_rates<fused update>"
-        if len(a) == 3 and a[2] in ("1", "true", "(bool)1"):
+        if len(a) >= 3 and a[2] in ("1", "true", "(bool)1"):
             return "k_ion_rates[memo]"           # over k_ion_walk's task list
-        if len(a) == 3 and a[1] in ("0", "false", "(bool)0"):
+        if len(a) == 4 and a[3] in ("1", "true", "(bool)1"):
+            return "k_ion_rates[first]" if a[1] in ("1", "true", "(bool)1") else "k_ion_rates[first]<no memo>"
+        if len(a) >= 3 and a[1] in ("0", "false", "(bool)0"):
             return "k_ion_rates<no memo>"
         return "k_ion_rates"                     # full pass (writes the chunk records when the memo is on)
     if base == "k_ion_update":       # <MEMO, TASKS>
