@@ -138,6 +138,7 @@ def full_multi(tag, names):
               "fused": "the same with AB2_HYDRO_FUSE=1 (k_cfinal) and AB2_ION_FUSE=1 (k_ion_rates<fused update>)",
               "ion": "bench.py default workload, the ion kernels of the sparse sub-cycle: full first-iteration passes (k_ion_rates / k_ion_update, "
                      "writing the chunk records), k_ion_walk, and the passes over its task list ([memo])",
+              "first": "bench.py default workload since the call's prologue rides on the first rates pass (k_ion_rates[first]); profiles/capture5.sh",
               "ppm": "--workload blast --order 3 (PPM pass A)", "smr": "--workload ioniz_smr (shipped 5-level deck)"}
     traffic = {}
     with open(os.path.join(HERE, f"{tag}_ncu_full_table.md"), "w") as f:
