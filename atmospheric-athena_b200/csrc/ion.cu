@@ -10,8 +10,12 @@
 //   k_ion_rates  : one WARP per ray; 32 cells at a time, exp(-tau) in parallel, attenuation as the reference's
 //                  sequential product (every lane applies the factors of the lanes before it, in order) with its
 //                  1e-3 ray cut, then photo/chem/thermal rates and the per-cell dt limits of those same cells
-//                  while they are in registers.
+//                  while they are in registers.  The first pass of a call also does the call's prologue (floors,
+//                  save_energy_and_x) on the fly.
 //   k_ion_update : E,s update, temperature and neutral floors, check_range count and the new hydro dt.
+// From the second iteration of a call on both run over the rays k_ion_walk lists, i.e. those with 32-cell chunks whose
+// inputs changed; everything else re-uses the previous iteration's results bit for bit ("Sparse sub-cycle" below).
+// Small Grids take k_ion_rates<UPDATE = true> instead: update(n) and rates(n+1) in one launch, no memo.
 // Arithmetic: every per-cell formula keeps the reference's operations and order; exp() and pow() are the host glibc's
 // own algorithms re-implemented operation for operation (glibc_math.cuh), and the attenuation along a ray is the
 // reference's sequential product.  On hosts whose libm selects the same (FMA) variants this path is bit-identical to
@@ -319,13 +323,18 @@ __device__ __forceinline__ CellRates cell_rates(const GridDev& g, const IonParDe
 // ---------------------------------------------------------------------------------------------------
 // Sparse sub-cycle (engine.cuh IonChunks).  ion_radtransfer_3d re-evaluates every cell in every iteration; most cells of
 // an irradiated-planet box are ambient gas that is already ionised down to the neutral floor, where ionization_update's
-// own condition (ionrad_3d.c:575 `nHdot > 0 || s > 1.0001 d_nlim`) leaves E and s alone.  A 32-cell chunk of a ray all
-// of whose cells are in that state, whose incoming flux has the bits it had in the previous iteration and whose sign
-// states sit at their fixed point (count 0, last_sign = sign(nHdot)) gets bit-identical rates, dt limits, outgoing flux,
-// check_range count and wave-speed maxima from a re-evaluation.  So from the second iteration of a call on
+// own condition (ionrad_3d.c:575 `nHdot > 0 || s > 1.0001 d_nlim`) leaves E and s alone.  A 32-cell chunk of a ray
+//   - whose sign states sit at their fixed point (count 0, last_sign = sign(nHdot))              [CH_RFIX, k_ion_rates]
+//   - whose cells the update left bitwise untouched and would for any sub-step still to come in this call: the
+//     condition false, or the increments rounding away even at the longest possible sub-step     [CH_UINERT, k_ion_update]
+//   - which the ray enters as it did when the chunk was last evaluated (same cut state, same flux bits)
+// gets bit-identical rates, dt limits, outgoing flux, check_range count and wave-speed maxima from a re-evaluation.
+// So from the second iteration of a call on
 //   k_ion_walk   reads the chunk records ray by ray, finds the first chunk of each ray that has to be evaluated, deposits
 //                the recorded reductions of the chunks before it, and lists the rays that have such a chunk;
-//   k_ion_rates / k_ion_update then run over that list only, each ray from its first such chunk on.
+//   k_ion_rates / k_ion_update then run over that list only, each ray from its first such chunk on, applying the same
+//                test to the chunks further down (a chunk the rates pass evaluates carries the pass number as a stamp,
+//                which is how the update behind it tells evaluated from re-used).
 // Nothing is approximated: a chunk is re-used only while every input of the reference's arithmetic is bitwise unchanged.
 // The pair k_ion_rates<false> / k_ion_update carries the memo; the fused k_ion_rates<true> (small Grids, where an
 // iteration is launch-bound) evaluates everything.
