@@ -534,7 +534,8 @@ def gpu_arm(args):
                                 "snapshot": "the last scan of the chunk records in the timed region", "sparse_iterations": memo_n,
                                 "sparse_iteration_ms": round(sum(ktab[k]["ms_total"] for k in memo_k) / memo_n, 4) if memo_n else None,
                                 "note": "step_frac and ion_iteration_frac_at_112B count SURVEY 8(d)'s bytes for every zone and iteration, "
-                                        "re-used chunks included; ion_iteration_* is measured on the full first-iteration passes"}
+                                        "re-used chunks included; ion_iteration_* is measured on the full first-iteration passes (whose rates pass, "
+                                        "k_ion_rates[first], also carries the call's prologue: floors + save_energy_and_x)"}
         roof["per_kernel_ncu"] = {k: {"dram_util": round(v["dram_pct"] / 100.0, 3), "fp64_util": round(v["fp64_pipe_pct"] / 100.0, 3),
                                       "issue_util": round(v["issue_pct"] / 100.0, 3) if "issue_pct" in v else None}
                                   for k, v in prof_all.items() if k.startswith("k_") and "dram_pct" in v}
