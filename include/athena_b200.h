@@ -12,7 +12,8 @@
  *
  * Conventions
  *  - One ab2_grid per reference GridS, owned by the caller through an opaque handle; one CUDA device and
- *    one stream per handle.  Not thread-safe per handle (neither is the reference, SURVEY 8b "Threading").
+ *    one stream per handle.  Not thread-safe per handle (neither is the reference, SURVEY 8b "Threading"); different
+ *    handles may be driven from different host threads at the same time (bench.py's e2e leg does: error text is per thread).
  *  - Arrays with ghosts have extents [Nx3+8][Nx2+8][Nx1+8], x1 fastest, exactly GridS.U (athena.h:289-348,
  *    ath_array.c:78-120).  "aos" = the reference's ConsS layout, nvar = 5+nscal doubles per cell
  *    (d,M1,M2,M3,E[,s0]); "soa" = one array per variable (the device layout).
